@@ -1,0 +1,89 @@
+"""Oracle: the RANSAC driver loop body (test and train branches) and RANSAC3D's
+train branch.
+
+Restates `ransac.py:49-144` (threshold normalisation with the K1[0,0]-twice
+quirk of :52, chunked sample -> solve -> score -> argmax, train-mode
+closest-to-GT selection :87-96) and `ransac.py:352-382` (3-D train branch),
+with the Gumbel noise injected per chunk.  Adaptive early exit, LO and the
+final refit (`ransac.py:134-195`) are outside the hot path.
+
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import fundamental, nister, rigid, sampler, scoring
+
+
+def normalized_threshold(threshold: float, K1: torch.Tensor, K2: torch.Tensor, fmat: bool) -> float:
+    """ransac.py:49-53 (note K1[0,0] appears twice)."""
+    if fmat:
+        return threshold
+    return float(threshold / ((K1[0, 0] + K1[1, 1] + K1[0, 0] + K2[1, 1]) / 4))
+
+
+def solve(minimal: torch.Tensor, solver: str):
+    if solver == "nister":
+        return nister.five_point(minimal), 10
+    if solver == "f8":
+        return fundamental.eight_point(minimal), 1
+    raise ValueError(solver)
+
+
+def test_loop(matches, logits, noises, threshold, solver="nister", sample_size=5, tau=1.0):
+    """ransac.py:55-144, test branch, no adaptive exit: one chunk per entry of
+    `noises` (each [K_c, N]).  Returns dict(best_model, best_mask, best_score,
+    best_chunk, best_idx (index into the chunk's compacted model list),
+    scores (list per chunk), models (list per chunk))."""
+    best = dict(best_score=0, best_model=None, best_mask=None, best_chunk=-1, best_idx=-1,
+                scores=[], models=[], samples=[])
+    for ci, G in enumerate(noises):
+        ret, _, idx = sampler.sample(logits, G, sample_size, tau)
+        minimal = sampler.gather_minimal(matches, ret)
+        models, _ = solve(minimal, solver)
+        scores, masks = scoring.msac_score(matches, models, threshold)
+        bi = int(torch.argmax(scores))
+        best["scores"].append(scores)
+        best["models"].append(models)
+        best["samples"].append(idx)
+        if scores[bi] > best["best_score"] or ci == 0:
+            best.update(best_score=scores[bi], best_mask=masks[bi], best_model=models[bi], best_chunk=ci,
+                        best_idx=bi)
+    return best
+
+
+def train_select(models: torch.Tensor, gt_model: torch.Tensor, n_slots: int) -> torch.Tensor:
+    """ransac.py:87-96: per sample keep the slot closest to GT in raw Frobenius
+    norm (sign-sensitive, as the reference)."""
+    d = torch.norm(models - gt_model, dim=(1, 2)).view(-1, n_slots)
+    pick = torch.argmin(d, dim=-1)
+    return models.view(-1, n_slots, 3, 3)[torch.arange(pick.shape[0]), pick]
+
+
+def train_loop(matches, logits, noises, gt_model, solver="nister", sample_size=5, tau=1.0):
+    """ransac.py:78-108: collect one model per sample and chunk, NaN-filtered."""
+    out = []
+    for G in noises:
+        ret, _, _ = sampler.sample(logits, G, sample_size, tau)
+        minimal = sampler.gather_minimal(matches, ret)
+        models, n_slots = solve(minimal, solver)
+        chosen = models if n_slots == 1 else train_select(models, gt_model, n_slots)
+        ok = ~torch.isnan(chosen).flatten(1).any(1)
+        out.append(chosen[ok])
+    return torch.cat(out)
+
+
+def rigid_train_loop(points, logits, noises, flag=True, tau=1.0):
+    """ransac.py:352-382: per chunk (models [K_c,4,4], residual sums [K_c],
+    mean residual scalar)."""
+    models, res, mean_res = [], [], []
+    for G in noises:
+        ret, _, _ = sampler.sample(logits, G, 3, tau)
+        minimal = sampler.gather_minimal(points, ret)
+        m, _, _, _ = rigid.estimate(minimal, flag=flag)
+        r, mr, _ = scoring.rigid_squared_residual(points[:, :3], points[:, 3:], m[:, :3, :].transpose(-1, -2))
+        models.append(m)
+        res.append(r)
+        mean_res.append(mr)
+    return models, res, mean_res

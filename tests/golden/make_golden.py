@@ -1,0 +1,214 @@
+"""Generate golden fixtures by running THE REFERENCE ITSELF (imported from
+/root/reference, CPU) on seeded synthetic inputs.
+
+Run in the build container only (the GPU box has no /root/reference):
+
+    python tests/golden/make_golden.py
+
+Writes tests/golden/*.npz.  Harness patches: stub `h5py`
+(feature_utils.py:7 is the only blocking import), `np.bool = bool`
+(loss.py:134), `estimator.device = 'cpu'` for the Stewenius class
+(stewenius.py:7-8 never sets it), and the Gumbel noise is injected by replacing
+`sampler.gumbel_dist.sample` (gumbel_sampler.py:33).  No other edits.
+"""
+import os
+import sys
+import types
+
+import numpy as np
+
+np.bool = bool
+sys.modules.setdefault("h5py", types.ModuleType("h5py"))
+REF = "/root/reference"
+sys.path.insert(0, REF)
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(1, os.path.abspath(os.path.join(HERE, "..", "..")))
+
+import torch  # noqa: E402
+
+from estimators.essential_matrix_estimator_nister import EssentialMatrixEstimatorNister  # noqa: E402
+from estimators.essential_matrix_estimator_stewenius import EssentialMatrixEstimator  # noqa: E402
+from estimators.fundamental_matrix_estimator import FundamentalMatrixEstimatorNew  # noqa: E402
+from estimators.rigid_transformation_SVD_based_solver import RigidTransformationSVDBasedSolver  # noqa: E402
+from samplers.gumbel_sampler import GumbelSoftmaxSampler  # noqa: E402
+from scorings.msac_score import MSACScore  # noqa: E402
+from model_cl import batch_episym  # noqa: E402
+from ransac import RANSAC, RANSAC3D  # noqa: E402
+
+from differentiable_ransac_b200 import synth  # noqa: E402
+
+
+def save(name, **arrays):
+    out = {}
+    for k, v in arrays.items():
+        out[k] = v.detach().cpu().numpy() if isinstance(v, torch.Tensor) else np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, {k: tuple(v.shape) for k, v in out.items()})
+
+
+def injected_sampler(K, s, noise_list, dtype=torch.float32):
+    smp = GumbelSoftmaxSampler(K, s, device="cpu", data_type=dtype)
+    it = iter(noise_list)
+    smp.gumbel_dist.sample = lambda shape: next(it)
+    return smp
+
+
+def main():
+    torch.set_num_threads(4)
+    K1 = torch.tensor([[800.0, 0, 320], [0, 800.0, 240], [0, 0, 1]])
+
+    # ---- a1/a2 sampler + gather ------------------------------------------------
+    N, K, s = 256, 12, 5
+    m, Egt, inl = synth.relative_pose_pair(N, 0.5, seed=11)
+    for regime in ("L0", "L1"):
+        lg = synth.logits_regime(1, N, regime, seed=5)[0]
+        G = synth.gumbel_noise((K, N), seed=7)
+        smp = injected_sampler(K, s, [G])
+        ret, y_soft = smp.sample(lg)
+        pts = m.repeat([K, 1, 1]) * ret.unsqueeze(-1)
+        minimal = pts[ret != 0].view(K, -1, 4)
+        idx = (ret != 0).nonzero()[:, 1].view(K, -1)
+        save(f"sampler_{regime}", matches=m, logits=lg, noise=G, ret=ret, y_soft=y_soft, minimal=minimal,
+             idx=idx)
+
+    # ---- a3 Nister ---------------------------------------------------------------
+    m, Egt, inl = synth.relative_pose_pair(2000, 0.5, seed=3, noise=5e-4)
+    g = torch.Generator().manual_seed(21)
+    idx = torch.stack([torch.randperm(2000, generator=g)[:5].sort().values for _ in range(96)])
+    # half the samples all-inlier so that well-conditioned cases are covered
+    inl_idx = inl.nonzero().flatten()
+    for k in range(0, 96, 2):
+        idx[k] = inl_idx[torch.randperm(inl_idx.numel(), generator=g)[:5]].sort().values
+    pts = m[idx]
+    est = EssentialMatrixEstimatorNister("cpu")
+    E32 = est.estimate_model(pts)
+    E64 = est.estimate_model(pts.double())
+    save("nister", matches=m, idx=idx, pts=pts, E32=E32, E64=E64, E_gt=Egt)
+
+    # ---- a4 Stewenius -----------------------------------------------------------
+    st = EssentialMatrixEstimator("cpu")
+    st.device = "cpu"
+    Est = st.estimate_minimal_model(pts[:48])
+    save("stewenius", pts=pts[:48], E32=Est)
+
+    # ---- a5 8-point ----------------------------------------------------------------
+    pm, Fgt, Kc, finl = synth.pixel_pair(2000, 0.5, seed=8)
+    idx8 = torch.stack([torch.randperm(2000, generator=g)[:8].sort().values for _ in range(64)])
+    p8 = pm[idx8]
+    f8 = FundamentalMatrixEstimatorNew("cpu")
+    F32 = f8.estimate_model(p8)
+    F64 = f8.estimate_model(p8.double())
+    save("f8", matches=pm, idx=idx8, pts=p8, F32=F32, F64=F64, F_gt=Fgt, K=Kc)
+
+    # ---- a7/a8 rigid -------------------------------------------------------------
+    rp, pose, rinl = synth.rigid_pair(4000, 0.7, seed=5)
+    idx3 = torch.stack([torch.randperm(4000, generator=g)[:3].sort().values for _ in range(64)])
+    p3 = rp[idx3]
+    rs = RigidTransformationSVDBasedSolver()
+    out = {}
+    for flag in (True, False):
+        model, R, t, scale = rs.estimate_model(p3, flag=flag)
+        r, mr, mask = rs.squared_residual(rp[:, :3], rp[:, 3:], model[:, :3, :].transpose(-1, -2))
+        out.update({f"model_{int(flag)}": model, f"res_{int(flag)}": r, f"mean_{int(flag)}": mr,
+                    f"ninl_{int(flag)}": mask.sum(-1)})
+    save("rigid", points=rp, idx=idx3, pts=p3, pose=pose, **out)
+
+    # ---- a9 MSAC -----------------------------------------------------------------
+    thr = 0.75 / 800.0
+    models = E32[:400]
+    sc, masks = MSACScore("cpu").score(m, models, thr)
+    save("msac", matches=m, models=models, threshold=thr, scores=sc, ninl=masks.sum(-1),
+         best=torch.argmax(sc), best_mask=masks[torch.argmax(sc)])
+
+    # ---- a10 episym / MatchLoss core ------------------------------------------------
+    x1 = m[inl][:, :2].repeat(models.shape[0], 1, 1)
+    x2 = m[inl][:, 2:].repeat(models.shape[0], 1, 1)
+    ep = batch_episym(x1, x2, models)
+    el = torch.min(ep, ep.new_ones(ep.shape))
+    save("episym", matches=m, gt_mask=inl, models=models, row_mean=el.mean(1), loss=el.mean())
+
+    # ---- a11 driver: test-mode loop body (two chunks) and train mode ------------------
+    N, Kc_, nchunks = 1000, 32, 2
+    m2, Egt2, inl2 = synth.relative_pose_pair(N, 0.6, seed=17, noise=2e-4)
+    lg2 = synth.logits_regime(1, N, "L0", seed=6)[0]
+    noises = [synth.gumbel_noise((Kc_, N), seed=100 + c) for c in range(nchunks)]
+    thr2 = float(0.75 / ((K1[0, 0] + K1[1, 1] + K1[0, 0] + K1[1, 1]) / 4))
+    smp = injected_sampler(Kc_, 5, noises)
+    best_score, best_chunk, best_hyp = 0, -1, -1
+    chunk_scores, chunk_models, chunk_idx = [], [], []
+    for c in range(nchunks):
+        ret, _ = smp.sample(lg2)
+        pts_ = m2.repeat([Kc_, 1, 1]) * ret.unsqueeze(-1)
+        minimal = pts_[ret != 0].view(Kc_, -1, 4)
+        em = est.estimate_model(minimal)
+        assert em.shape[0] == Kc_ * 10, "rank filter dropped a sample; pick another seed"
+        sc_, mk_ = MSACScore("cpu").score(m2, em, thr2)
+        bi = int(torch.argmax(sc_))
+        chunk_scores.append(sc_)
+        chunk_models.append(em)
+        chunk_idx.append((ret != 0).nonzero()[:, 1].view(Kc_, -1))
+        if sc_[bi] > best_score or c == 0:
+            best_score, best_chunk, best_hyp = sc_[bi], c, bi // 10
+            best_model, best_mask = em[bi], mk_[bi]
+    save("driver_test", matches=m2, logits=lg2, noise=torch.stack(noises), threshold=thr2, K1=K1,
+         scores=torch.stack(chunk_scores), models=torch.stack(chunk_models), idx=torch.stack(chunk_idx),
+         best_score=best_score, best_chunk=best_chunk, best_hyp=best_hyp, best_model=best_model,
+         best_mask=best_mask, E_gt=Egt2)
+
+    # train mode through the reference driver itself, with gradient to the logits
+    for prec, dt in (("32", torch.float32), ("64", torch.float64)):
+        smp = injected_sampler(Kc_, 5, [n.to(dt) for n in noises], dtype=dt)
+        drv = RANSAC(est, smp, MSACScore("cpu"), fmat=False, train=True, ransac_batch_size=Kc_, sampler_id=2,
+                     max_iterations=Kc_ * nchunks)
+        lgr = lg2.to(dt).clone().requires_grad_(True)
+        mr_ = m2.to(dt).clone().requires_grad_(True)
+        models_d, _, _, its = drv(mr_, lgr, K1.to(dt), K1.to(dt), Egt2.to(dt))
+        Es = torch.cat(list(models_d.values()))
+        p1 = m2[inl2][:, :2].to(dt).repeat(Es.shape[0], 1, 1)
+        p2 = m2[inl2][:, 2:].to(dt).repeat(Es.shape[0], 1, 1)
+        ep = batch_episym(p1, p2, Es)
+        loss = torch.min(ep, ep.new_ones(ep.shape)).mean()
+        loss.backward()
+        save(f"driver_train_{prec}", matches=m2, logits=lg2, noise=torch.stack(noises), E_gt=Egt2,
+             gt_mask=inl2, models=Es, loss=loss, grad_logits=lgr.grad, grad_matches=mr_.grad)
+
+    # 8-point training step (cfg3 unit): sampler -> 8pt -> clamped episym mean, grads to logits
+    N8, K8 = 1000, 48
+    pm8, Fgt8, Kc8, finl8 = synth.pixel_pair(N8, 0.5, seed=31)
+    lg8 = synth.logits_regime(1, N8, "L1", seed=9)[0]
+    G8 = synth.gumbel_noise((K8, N8), seed=55)
+    for prec, dt in (("32", torch.float32), ("64", torch.float64)):
+        smp = injected_sampler(K8, 8, [G8.to(dt)], dtype=dt)
+        drv = RANSAC(FundamentalMatrixEstimatorNew("cpu"), smp, MSACScore("cpu"), fmat=True, train=True,
+                     ransac_batch_size=K8, sampler_id=3, max_iterations=K8)
+        lgr = lg8.to(dt).clone().requires_grad_(True)
+        mr_ = pm8.to(dt).clone().requires_grad_(True)
+        models_d, _, _, _ = drv(mr_, lgr, Kc8.to(dt), Kc8.to(dt), Fgt8.to(dt))
+        Fs = torch.cat(list(models_d.values()))
+        p1 = pm8[finl8][:, :2].to(dt).repeat(Fs.shape[0], 1, 1)
+        p2 = pm8[finl8][:, 2:].to(dt).repeat(Fs.shape[0], 1, 1)
+        ep = batch_episym(p1, p2, Fs)
+        loss = torch.min(ep, ep.new_ones(ep.shape)).mean()
+        loss.backward()
+        save(f"f8_train_{prec}", matches=pm8, logits=lg8, noise=G8, gt_mask=finl8, models=Fs, loss=loss,
+             grad_logits=lgr.grad, grad_matches=mr_.grad)
+
+    # ---- a12 RANSAC3D train branch through the reference driver ------------------------
+    N3, K3 = 3000, 32
+    rp3, pose3, _ = synth.rigid_pair(N3, 0.7, seed=9)
+    lg3 = synth.logits_regime(1, N3, "L1", seed=4)[0]
+    noises3 = [synth.gumbel_noise((K3, N3), seed=200 + c) for c in range(2)]
+    smp = injected_sampler(K3, 3, noises3)
+    drv3 = RANSAC3D(rs, smp, MSACScore("cpu"), train=True, ransac_batch_size=K3, sampler_id=2,
+                    max_iterations=2 * K3)
+    lgr = lg3.clone().requires_grad_(True)
+    models3, res3, mres3, _, _ = drv3(rp3, lgr, pose3)
+    loss3 = torch.cat(list(res3.values())).mean()
+    loss3.backward()
+    save("rigid_train", points=rp3, logits=lg3, noise=torch.stack(noises3),
+         models=torch.cat(list(models3.values())), residuals=torch.cat(list(res3.values())),
+         mean_residuals=torch.stack(list(mres3.values())), loss=loss3, grad_logits=lgr.grad)
+
+
+if __name__ == "__main__":
+    main()
