@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the hypothesize-and-score hot path (BASELINE.json metric: hypotheses/sec,
+5PC-E, 2k correspondences x 1k hypotheses, 32 pairs per GPU).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one pass of the hot path over one batch of synthetic pairs: Gumbel top-5 sampling
+(in-kernel Philox, fresh offset every step) -> Nister 5-point on every sample -> Sampson/MSAC
+score of every model against every correspondence -> arg-max + winner mask.  Prints ONE JSON
+line (rank 0).  `value` has the inputs resident in HBM; `e2e` goes through the public API with
+pinned-host inputs and a device->host read of the result inside the timed region.
+
+--impl reference times the reference's own algorithm on the host cores: the CPU oracle
+(`oracle/`, a line-cited restatement of the reference's PyTorch path, pinned to the reference
+by tests/golden) -- /root/reference does not exist on the GPU box.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(B=32, K=1000, N=2000, sample_size=5, slots=10, threshold_px=0.75, focal=800.0)
+# compulsory traffic of the whole forward per hypothesis (matches+logits in,
+# 10 models + 10 scores out, best index + winner mask) at the headline shape.
+ALGO_BYTES_PER_HYP = 442.0
+ALGO_FLOP_PER_HYP = 0.82e6
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx.append(float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(B, N, seed):
+    from differentiable_ransac_b200 import synth
+
+    matches, E_gt, inl = synth.relative_pose_batch(B, N, seed=seed)
+    logits = synth.logits_regime(B, N, "L0", seed=seed + 7)
+    thr = torch.full((B,), WORKLOAD["threshold_px"] / WORKLOAD["focal"])
+    return matches, logits, thr, E_gt
+
+
+# ---------------------------------------------------------------------------------------------------
+def cpu_reference_throughput(max_seconds=12.0, max_pairs=4, K=None, N=None):
+    """The reference's algorithm on the host cores (oracle port): serial over pairs exactly as
+    model_cl.py:488 is, one chunk of K hypotheses per pair (ransac_batch_size = K)."""
+    from differentiable_ransac_b200 import synth
+    from oracle import driver
+
+    K = K or WORKLOAD["K"]
+    N = N or WORKLOAD["N"]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    matches, logits, thr, _ = make_inputs(max_pairs, N, seed=1234)
+    done, t_total = 0, 0.0
+    # warm-up on a small chunk (LAPACK / thread pool initialisation)
+    driver.test_loop(matches[0], logits[0], [synth.gumbel_noise((16, N), seed=1)], float(thr[0]))
+    for b in range(max_pairs):
+        G = synth.gumbel_noise((K, N), seed=100 + b)
+        t0 = time.perf_counter()
+        driver.test_loop(matches[b], logits[b], [G], float(thr[b]))
+        t_total += time.perf_counter() - t0
+        done += 1
+        if t_total > max_seconds:
+            break
+    return dict(value=done * K / t_total, unit="hypotheses/s", cores=cores, kind="port",
+                sample=f"{done} pair(s) x {K} hyps x {N} corrs, oracle/driver.test_loop (sample+5pt+MSAC), "
+                       f"{t_total:.2f} s, torch {torch.__version__} CPU")
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from differentiable_ransac_b200 import synth
+    from oracle import driver
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    K, N = WORKLOAD["K"], WORKLOAD["N"]
+    pairs_per_step = 1
+    matches, logits, thr, _ = make_inputs(pairs_per_step, N, seed=1234)
+    times = []
+    for it in range(args.warmup + args.steps):
+        G = synth.gumbel_noise((K, N), seed=100 + it)
+        t0 = time.perf_counter()
+        driver.test_loop(matches[0], logits[0], [G], float(thr[0]))
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = pairs_per_step * K / (ms / 1e3)
+    line = dict(impl="reference", metric="hypotheses_per_sec", value=value, unit="hypotheses/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="5PC-E Nister test-mode loop body, cfg2 shape", K=K, N=N,
+                            sample="each step = 1 pair x 1000 hyps x 2000 corrs (the reference is serial over "
+                                   "pairs, model_cl.py:488; 32 pairs/step would take ~40 s/step)"),
+                cpu_baseline=dict(value=value, unit="hypotheses/s", cores=cores, kind="port",
+                                  sample=f"{args.steps} step(s) of 1 pair x {K} hyps x {N} corrs"),
+                e2e=dict(value=value, unit="hypotheses/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=dev)
+
+    from differentiable_ransac_b200 import engine, ops
+
+    B, K, N = WORKLOAD["B"], WORKLOAD["K"], WORKLOAD["N"]
+    warmup = max(args.warmup, 3)
+    matches_h, logits_h, thr_h, E_gt = make_inputs(B, N, seed=1234 + 1000 * rank)   # pairs shard over ranks
+    matches_h, logits_h, thr_h = matches_h.pin_memory(), logits_h.pin_memory(), thr_h.pin_memory()
+    matches, logits, thr = matches_h.to(dev), logits_h.to(dev), thr_h.to(dev)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+
+    def step(i):
+        return engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=i)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------
+    for i in range(warmup):
+        out = step(i)
+    barrier()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for i in range(args.steps):
+        flush.fill_(float(i))                   # L2 flush between timed iterations (untimed)
+        ev[i][0].record()
+        out = step(warmup + i)
+        ev[i][1].record()
+    barrier()
+    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    clock_info = clocks.stop() if rank == 0 else None
+    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * B * K * args.steps / (ms_total / 1e3)
+
+    # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
+    h2d = matches_h.numel() * 4 + logits_h.numel() * 4 + thr_h.numel() * 4
+    res_h = dict(best_model=torch.empty(B, 3, 3).pin_memory(), best_id=torch.empty(B, dtype=torch.int32).pin_memory(),
+                 best_score=torch.empty(B).pin_memory(), ninl=torch.empty(B, dtype=torch.int32).pin_memory())
+    d2h = sum(v.numel() * v.element_size() for v in res_h.values())
+
+    def step_e2e(i):
+        m = matches_h.to(dev, non_blocking=True)
+        l = logits_h.to(dev, non_blocking=True)
+        th = thr_h.to(dev, non_blocking=True)
+        o = engine.ransac_e5_test(m, l, K, th, seed=42 + rank, offset=1000 + i)
+        for k_, v in res_h.items():
+            v.copy_(o[k_], non_blocking=True)
+
+    for i in range(warmup):
+        step_e2e(i)
+    barrier()
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev2[i][0].record()
+        step_e2e(warmup + i)
+        ev2[i][1].record()
+    barrier()
+    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_value = world * B * K * args.steps / (float(t2.item()) / 1e3)
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (score_msac_kernel), timed live with CUDA events -------------------
+    idx, _, _, _ = ops.sample(logits, K, 5, 1.0, seed=7, offset=0)
+    models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
+    n_valid = int(cc.sum().item())
+    reps = 10
+    for _ in range(3):
+        ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True)
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b_ in evs:
+        flush.fill_(1.0)
+        a.record()
+        ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True)
+        b_.record()
+    torch.cuda.synchronize()
+    score_ms = sum(a.elapsed_time(b_) for a, b_ in evs) / reps          # includes the 8-byte/pair memset of `best`
+    # stage shares of one step (events around each stage)
+    shares = {}
+    for name, fn in (("sample", lambda: ops.sample(logits, K, 5, 1.0, seed=7, offset=1)),
+                     ("solve_e5", lambda: ops.solve_e5(matches, idx, compact=True)),
+                     ("score_msac", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=False)),
+                     ):
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        fn()
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(5):
+            fn()
+        b_.record()
+        torch.cuda.synchronize()
+        shares[name + "_ms"] = a.elapsed_time(b_) / 5
+    peak, peak_src = load_peaks()
+    score_bytes = B * N * 16 + n_valid * (36 + 4 + 4) + B * 8
+    achieved = score_bytes / (score_ms / 1e3) / 1e9
+    flops_score = n_valid * N * 37.0
+    line = dict(
+        metric="hypotheses_per_sec", value=value, unit="hypotheses/s", n_gpus=world, steps=args.steps,
+        warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
+        dtype="f32", data="synthetic",
+        config=dict(workload="cfg2: Essential 5PC (Nister), 32 pairs x 1000 hyps x 2000 corrs per GPU, fwd only, "
+                             "test-mode semantics (sample -> solve -> MSAC -> arg-max + winner mask)",
+                    pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N, noise="in-kernel Philox4x32-10",
+                    l2="flushed between timed iterations (256 MB write)", parallelism=f"pairs sharded over {world} GPU(s)"),
+        clocks=clock_info,
+        e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
+        gpu_launches=4 * args.steps,
+        roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                      kernel="score_msac_kernel", kernel_ms=score_ms, algorithmic_bytes=score_bytes,
+                      peak_source=peak_src, models_scored=n_valid,
+                      note="FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops",
+                      fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,
+                      step_algorithmic_gbs=ALGO_BYTES_PER_HYP * B * K / (ms_per_step / 1e3) / 1e9, **shares),
+    )
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_reference_throughput()
+    print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,47 @@
+// Philox4x32-10 counter-based generator (Salmon et al., SC'11) and the
+// uniform -> Gumbel(0,1) transform shared by the sampler forward and backward
+// (the backward regenerates the forward's noise instead of storing K x N floats).
+#pragma once
+
+#include "drb_common.cuh"
+
+namespace drb {
+
+struct Philox4 {
+    uint32_t x, y, z, w;
+};
+
+DRB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+    DRB_UNROLL
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)M0 * c0;
+        const uint64_t p1 = (uint64_t)M1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n1 = (uint32_t)p1;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        const uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += W0;
+        k1 += W1;
+    }
+    Philox4 o;
+    o.x = c0; o.y = c1; o.z = c2; o.w = c3;
+    return o;
+}
+
+// 23 random bits -> v in [2^-24, 1 - 2^-24] (both ends exactly representable), then
+// G = -log(-log v).  The clamp keeps the double logarithm finite when the fast
+// log2 rounds -log v to <= 0 next to v = 1.
+DRB_D float gumbel_from_bits(uint32_t r) {
+    const float v = ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
+#if defined(__CUDA_ARCH__)
+    const float e = fmaxf(-__logf(v), 1e-10f);
+    return -__logf(e);
+#else
+    const float e = fmaxf(-logf(v), 1e-10f);
+    return -logf(e);
+#endif
+}
+
+}  // namespace drb

@@ -1,0 +1,200 @@
+// Real roots of a degree-10 polynomial by Sturm-sequence isolation + safeguarded
+// Newton.  Everything is held in registers (fully unrolled, compile-time degrees).
+//
+// The reference finds the roots with a companion-matrix `eigvals` per sample
+// (nister.py:361-370) and documents the Sturm scheme in math_utils.py:111-291
+// (sign-change counting :168, bracket refinement :191); this is an independent
+// implementation of that classical scheme.  Roots with |z| <= 1 are isolated on
+// p(z); roots with |z| > 1 on the reversed polynomial w^10 p(1/w), w in (-1, 1),
+// so that every evaluation happens on the unit interval (no overflow in fp32 and
+// bounded condition numbers).
+#pragma once
+
+#include "drb_common.cuh"
+
+namespace drb {
+
+template <class T>
+struct SturmChain10 {
+    // f_{i-1} = (a[i] z + b[i]) f_i - m[i] f_{i+1},  i = 1..9  (every f_i positively rescaled)
+    T a[10], b[10], m[10];
+    T l1, l0;  // f_9 = l1 z + l0
+    T c;       // f_10
+    T p[11];   // f_0 (ascending coefficients)
+
+    DRB_HD void build(const T* coef) {
+        T u[11], v[11];
+        T sc = T(0);
+        DRB_UNROLL
+        for (int i = 0; i <= 10; ++i) sc = t_max(sc, t_abs(coef[i]));
+        const T inv = sc > T(0) ? T(1) / sc : T(1);
+        DRB_UNROLL
+        for (int i = 0; i <= 10; ++i) {
+            p[i] = coef[i] * inv;
+            u[i] = p[i];
+        }
+        DRB_UNROLL
+        for (int i = 0; i < 10; ++i) v[i] = T(i + 1) * p[i + 1];
+        v[10] = T(0);
+        {   // rescale f_1 (positive factor keeps signs)
+            T s1 = T(0);
+            DRB_UNROLL
+            for (int i = 0; i < 10; ++i) s1 = t_max(s1, t_abs(v[i]));
+            const T i1 = s1 > T(0) ? T(1) / s1 : T(1);
+            DRB_UNROLL
+            for (int i = 0; i < 10; ++i) v[i] *= i1;
+        }
+        const T tiny = T(1e-30);
+        DRB_UNROLL
+        for (int i = 1; i <= 9; ++i) {
+            const int d = 10 - i;  // deg v = d, deg u = d + 1
+            T lead = v[d];
+            if (t_abs(lead) < tiny) lead = lead < T(0) ? -tiny : tiny;
+            const T il = T(1) / lead;
+            const T ai = u[d + 1] * il;
+            const T bi = (u[d] - ai * v[d - 1]) * il;
+            T r[11];
+            T mx = T(0);
+            DRB_UNROLL
+            for (int j = 0; j < d; ++j) {
+                T t = u[j] - bi * v[j];
+                if (j > 0) t -= ai * v[j - 1];
+                r[j] = -t;  // f_{i+1} = -remainder
+                mx = t_max(mx, t_abs(r[j]));
+            }
+            if (!(mx > tiny)) mx = T(1);
+            const T im = T(1) / mx;
+            a[i] = ai;
+            b[i] = bi;
+            m[i] = mx;
+            DRB_UNROLL
+            for (int j = 0; j <= d; ++j) u[j] = v[j];
+            DRB_UNROLL
+            for (int j = 0; j < d; ++j) v[j] = r[j] * im;
+            v[d] = T(0);
+        }
+        // after the loop u = f_9 (degree 1), v = f_10 (degree 0)
+        l0 = u[0];
+        l1 = u[1];
+        c = v[0];
+        a[0] = b[0] = m[0] = T(0);
+    }
+
+    // number of sign changes of the chain at z
+    DRB_HD int count(T z) const {
+        T s_next = c;
+        T s_cur = l1 * z + l0;
+        int changes = 0;
+        int last = (s_next > T(0)) - (s_next < T(0));
+        {
+            const int sg = (s_cur > T(0)) - (s_cur < T(0));
+            if (sg != 0) {
+                if (last != 0 && sg != last) ++changes;
+                last = sg;
+            }
+        }
+        DRB_UNROLL
+        for (int i = 9; i >= 1; --i) {
+            const T s_prev = (a[i] * z + b[i]) * s_cur - m[i] * s_next;
+            s_next = s_cur;
+            s_cur = s_prev;
+            const int sg = (s_cur > T(0)) - (s_cur < T(0));
+            if (sg != 0) {
+                if (last != 0 && sg != last) ++changes;
+                last = sg;
+            }
+        }
+        return changes;
+    }
+
+    DRB_HD void eval(T z, T& f, T& df) const {
+        f = p[10];
+        df = T(0);
+        DRB_UNROLL
+        for (int i = 9; i >= 0; --i) {
+            df = df * z + f;
+            f = f * z + p[i];
+        }
+    }
+
+    // real roots in (-1, 1]; returns how many were written to out[0..max_out)
+    DRB_HD int roots_unit(T* out, int max_out) const {
+        const int n_lo = count(T(-1));
+        const int n_hi = count(T(1));
+        int nroots = n_lo - n_hi;
+        if (nroots <= 0) return 0;
+        if (nroots > max_out) nroots = max_out;
+        T start = T(-1);
+        int written = 0;
+        for (int r = 0; r < nroots; ++r) {
+            T lo = start, hi = T(1);
+            int clo = n_lo - r;  // by construction exactly r roots lie at or below `start`
+            int chi = n_hi;
+            clo = count(lo);
+            for (int it = 0; it < 48; ++it) {
+                if (clo - chi <= 1) break;
+                const T mid = T(0.5) * (lo + hi);
+                if (!(mid > lo) || !(mid < hi)) break;
+                const int cm = count(mid);
+                if (n_lo - cm >= r + 1) {
+                    hi = mid;
+                    chi = cm;
+                } else {
+                    lo = mid;
+                    clo = cm;
+                }
+            }
+            // (lo, hi] now holds root r (and possibly a cluster); refine on p itself
+            T flo, fhi, d;
+            eval(lo, flo, d);
+            eval(hi, fhi, d);
+            T z = T(0.5) * (lo + hi);
+            if ((flo < T(0)) != (fhi < T(0))) {
+                for (int it = 0; it < 40; ++it) {
+                    T f, df;
+                    eval(z, f, df);
+                    if ((f < T(0)) == (flo < T(0))) {
+                        lo = z;
+                    } else {
+                        hi = z;
+                    }
+                    T zn = z - f / df;
+                    if (!(zn > lo && zn < hi)) zn = T(0.5) * (lo + hi);
+                    const T dz = t_abs(zn - z);
+                    z = zn;
+                    if (dz <= T(4) * (sizeof(T) == 4 ? T(6e-8) : T(1.2e-16)) * t_max(t_abs(z), T(1e-3))) break;
+                }
+            }
+            out[written++] = z;
+            start = hi;
+        }
+        return written;
+    }
+};
+
+// All real roots of sum_i coef[i] z^i (degree <= 10).  Returns the count (<= 10).
+template <class T>
+DRB_HD int real_roots_deg10(const T* coef, T* roots) {
+    int n = 0;
+    {
+        SturmChain10<T> s;
+        s.build(coef);
+        n = s.roots_unit(roots, 10);
+    }
+    {
+        T rev[11];
+        DRB_UNROLL
+        for (int i = 0; i <= 10; ++i) rev[i] = coef[10 - i];
+        SturmChain10<T> s;
+        s.build(rev);
+        T w[10];
+        const int nw = s.roots_unit(w, 10 - n);
+        for (int i = 0; i < nw; ++i) {
+            const T aw = t_abs(w[i]);
+            if (aw < T(1) && aw > T(1e-7) && n < 10) roots[n++] = T(1) / w[i];
+        }
+    }
+    return n;
+}
+
+}  // namespace drb

@@ -1,0 +1,266 @@
+// Gumbel top-s sampler: one warp per (pair, hypothesis).
+//
+// Replaces GumbelSoftmaxSampler.sample (samplers/gumbel_sampler.py:25-42) and the
+// boolean-mask gather of ransac.py:64-65.  The reference materialises five K x N
+// temporaries (repeat, gumbels, softmax, one-hot, straight-through) and a K x N x D
+// product; here a warp streams the N keys once, keeps the running top-s in the
+// registers of lanes 0..s-1 and an online log-sum-exp, and writes s indices.
+//
+// Noise: injected ([B,K,N], parity mode -- keys are formed with IEEE add/div so the
+// top-s matches torch.topk bit for bit) or Philox4x32-10 generated in-kernel.
+#include <cuda_runtime.h>
+
+#include "../../include/drb.h"
+#include "drb_common.cuh"
+#include "philox.cuh"
+
+namespace drb {
+
+constexpr int kSamplerWarps = 8;
+
+struct KeyQuad {
+    float k[4];
+};
+
+// Four consecutive keys n0..n0+3 of hypothesis row (b, k); entries past N are -inf.
+__device__ __forceinline__ KeyQuad load_keys(const float* __restrict__ logits_b, const float* __restrict__ noise_row,
+                                             float* __restrict__ noise_out_row, bool vec, int n0, int N, float tau,
+                                             uint32_t k, uint32_t b, uint64_t seed, uint64_t offset) {
+    float l[4], g[4];
+    if (vec) {
+        const float4 lv = __ldg(reinterpret_cast<const float4*>(logits_b + n0));
+        l[0] = lv.x; l[1] = lv.y; l[2] = lv.z; l[3] = lv.w;
+    } else {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) l[i] = (n0 + i < N) ? __ldg(logits_b + n0 + i) : 0.f;
+    }
+    if (noise_row != nullptr) {
+        if (vec) {
+            const float4 gv = __ldcs(reinterpret_cast<const float4*>(noise_row + n0));
+            g[0] = gv.x; g[1] = gv.y; g[2] = gv.z; g[3] = gv.w;
+        } else {
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) g[i] = (n0 + i < N) ? __ldcs(noise_row + n0 + i) : 0.f;
+        }
+    } else {
+        const Philox4 r = philox4x32_10((uint32_t)(n0 >> 2), k, b, (uint32_t)offset, (uint32_t)seed,
+                                        (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32));
+        g[0] = gumbel_from_bits(r.x);
+        g[1] = gumbel_from_bits(r.y);
+        g[2] = gumbel_from_bits(r.z);
+        g[3] = gumbel_from_bits(r.w);
+    }
+    if (noise_out_row != nullptr) {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i)
+            if (n0 + i < N) noise_out_row[n0 + i] = g[i];
+    }
+    KeyQuad q;
+    DRB_UNROLL
+    for (int i = 0; i < 4; ++i) q.k[i] = (n0 + i < N) ? __fdiv_rn(__fadd_rn(l[i], g[i]), tau) : -INFINITY;
+    return q;
+}
+
+template <int S>
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+sample_kernel(const float* __restrict__ logits, const float* __restrict__ noise, uint64_t seed, uint64_t offset,
+              float tau, int B, int K, int N, int32_t* __restrict__ idx_out, float* __restrict__ lse_out,
+              float* __restrict__ sel_key_out, float* __restrict__ noise_out) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const long long row = (long long)blockIdx.x * kSamplerWarps + warp;  // b * K + k
+    if (row >= (long long)B * K) return;
+    const int b = (int)(row / K);
+    const int k = (int)(row % K);
+    const float* logits_b = logits + (size_t)b * N;
+    const float* noise_row = noise ? noise + (size_t)row * N : nullptr;
+    float* noise_out_row = noise_out ? noise_out + (size_t)row * N : nullptr;
+    const bool vec = (N % 4 == 0);
+    const unsigned FULL = 0xffffffffu;
+
+    // running top-S, sorted descending, element j lives in lane j
+    float top_v = -INFINITY;
+    int top_i = -1;
+    float thr = -INFINITY;
+    // online log-sum-exp
+    float run_m = -INFINITY, run_s = 0.f;
+
+    for (int n0 = lane * 4; n0 < ((N + 127) / 128) * 128; n0 += 128) {
+        KeyQuad q;
+        if (n0 < N) {
+            q = load_keys(logits_b, noise_row, noise_out_row, vec, n0, N, tau, (uint32_t)k, (uint32_t)b, seed, offset);
+        } else {
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) q.k[i] = -INFINITY;
+        }
+        if (lse_out != nullptr) {
+            const float m4 = fmaxf(fmaxf(q.k[0], q.k[1]), fmaxf(q.k[2], q.k[3]));
+            if (m4 > -INFINITY) {
+                const float nm = fmaxf(run_m, m4);
+                float s = run_s * __expf(run_m - nm);
+                DRB_UNROLL
+                for (int i = 0; i < 4; ++i) s += __expf(q.k[i] - nm);
+                run_m = nm;
+                run_s = s;
+            }
+        }
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            unsigned cand = __ballot_sync(FULL, q.k[i] > thr);
+            while (cand) {
+                const int src = __ffs(cand) - 1;
+                cand &= cand - 1;
+                const float cv = __shfl_sync(FULL, q.k[i], src);
+                if (!(cv > thr)) continue;  // threshold moved since the ballot (warp-uniform)
+                const int ci = __shfl_sync(FULL, n0 + i, src);
+                const float up_v = __shfl_up_sync(FULL, top_v, 1);
+                const int up_i = __shfl_up_sync(FULL, top_i, 1);
+                if (cv > top_v) {
+                    if (lane > 0 && cv > up_v) {
+                        top_v = up_v;
+                        top_i = up_i;
+                    } else {
+                        top_v = cv;
+                        top_i = ci;
+                    }
+                }
+                thr = __shfl_sync(FULL, top_v, S - 1);
+            }
+        }
+    }
+    // ascending-index order of the boolean-mask gather (ransac.py:65)
+    int rank = 0;
+    DRB_UNROLL
+    for (int j = 0; j < S; ++j) {
+        const int oj = __shfl_sync(FULL, top_i, j);
+        rank += (oj < top_i) ? 1 : 0;
+    }
+    if (lane < S) {
+        idx_out[(size_t)row * S + rank] = top_i;
+        if (sel_key_out) sel_key_out[(size_t)row * S + rank] = top_v;
+    }
+    if (lse_out != nullptr) {
+        DRB_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(FULL, run_m, o);
+            const float os = __shfl_xor_sync(FULL, run_s, o);
+            const float nm = fmaxf(run_m, om);
+            const float a = (run_m > -INFINITY) ? run_s * __expf(run_m - nm) : 0.f;
+            const float c = (om > -INFINITY) ? os * __expf(om - nm) : 0.f;
+            run_m = nm;
+            run_s = a + c;
+        }
+        if (lane == 0) lse_out[row] = run_m + __logf(run_s);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Backward: dL/dlogits[n] += (1/tau) ( sum_{k: n selected} y[k,n] g[k,n]  -  sum_k y[k,n] c_k ),
+// c_k = sum_j y[k, n_j] g_sel[k, j],  y[k,n] = exp(key[k,n] - lse[k]).
+// Pass 1 (one thread per (b,k)): c_k and the sparse term (atomics on s entries).
+// Pass 2 (one thread per 4 consecutive n, K split over blockIdx.y): the dense K x N term,
+// regenerating / re-reading the noise; no K x N tensor is ever stored.
+__global__ void sample_bwd_sparse_kernel(float tau, int B, int K, int N, int S, const int32_t* __restrict__ idx,
+                                         const float* __restrict__ lse, const float* __restrict__ sel_key,
+                                         const float* __restrict__ g_sel, float* __restrict__ ck,
+                                         float* __restrict__ grad_logits) {
+    const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= (long long)B * K) return;
+    const int b = (int)(row / K);
+    const float l = lse[row];
+    float c = 0.f;
+    const float it = 1.f / tau;
+    for (int j = 0; j < S; ++j) {
+        const float y = __expf(sel_key[row * S + j] - l);
+        const float t = y * g_sel[row * S + j];
+        c += t;
+        atomicAdd(grad_logits + (size_t)b * N + idx[row * S + j], t * it);
+    }
+    ck[row] = c;
+}
+
+constexpr int kBwdThreads = 128;
+
+__global__ void __launch_bounds__(kBwdThreads)
+sample_bwd_dense_kernel(const float* __restrict__ logits, const float* __restrict__ noise, uint64_t seed,
+                        uint64_t offset, float tau, int B, int K, int N, int k_per_block,
+                        const float* __restrict__ lse, const float* __restrict__ ck,
+                        float* __restrict__ grad_logits) {
+    const int b = blockIdx.z;
+    const int n0 = (blockIdx.x * kBwdThreads + threadIdx.x) * 4;
+    const int k_begin = blockIdx.y * k_per_block;
+    const int k_end = min(K, k_begin + k_per_block);
+    if (n0 >= N) return;
+    const float* logits_b = logits + (size_t)b * N;
+    const bool vec = (N % 4 == 0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = k_begin; k < k_end; ++k) {
+        const size_t row = (size_t)b * K + k;
+        const float* noise_row = noise ? noise + row * N : nullptr;
+        const KeyQuad q = load_keys(logits_b, noise_row, nullptr, vec, n0, N, tau, (uint32_t)k, (uint32_t)b, seed, offset);
+        const float l = __ldg(lse + row);
+        const float c = __ldg(ck + row);
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) acc[i] += __expf(q.k[i] - l) * c;
+    }
+    const float it = -1.f / tau;
+    DRB_UNROLL
+    for (int i = 0; i < 4; ++i)
+        if (n0 + i < N) atomicAdd(grad_logits + (size_t)b * N + n0 + i, acc[i] * it);
+}
+
+}  // namespace drb
+
+using namespace drb;
+
+static int check_launch() { return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA; }
+
+extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau, int B,
+                          int K, int N, int s, int32_t* idx, float* lse, float* sel_key, float* noise_out,
+                          void* stream) {
+    if (!logits || !idx) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || N <= 0 || s <= 0 || s > N || !(tau > 0.f)) return DRB_ERR_BAD_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows = (long long)B * K;
+    const unsigned grid = (unsigned)((rows + kSamplerWarps - 1) / kSamplerWarps);
+    const dim3 block(kSamplerWarps * 32);
+#define DRB_LAUNCH_SAMPLE(S_)                                                                                   \
+    case S_:                                                                                                    \
+        sample_kernel<S_><<<grid, block, 0, st>>>(logits, noise, seed, offset, tau, B, K, N, idx, lse, sel_key, \
+                                                  noise_out);                                                   \
+        break;
+    switch (s) {
+        DRB_LAUNCH_SAMPLE(3)
+        DRB_LAUNCH_SAMPLE(5)
+        DRB_LAUNCH_SAMPLE(7)
+        DRB_LAUNCH_SAMPLE(8)
+        default:
+            return DRB_ERR_UNSUPPORTED;
+    }
+#undef DRB_LAUNCH_SAMPLE
+    return check_launch();
+}
+
+extern "C" int drb_sample_backward(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau,
+                                   int B, int K, int N, int s, const int32_t* idx, const float* lse,
+                                   const float* sel_key, const float* g_sel, float* scratch, float* grad_logits,
+                                   void* stream) {
+    if (!logits || !idx || !lse || !sel_key || !g_sel || !scratch || !grad_logits) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || N <= 0 || s <= 0 || !(tau > 0.f)) return DRB_ERR_BAD_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    float* ck = scratch;
+    const long long rows = (long long)B * K;
+    sample_bwd_sparse_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, st>>>(tau, B, K, N, s, idx, lse, sel_key, g_sel,
+                                                                             ck, grad_logits);
+    const int n_blocks = (N + kBwdThreads * 4 - 1) / (kBwdThreads * 4);
+    // spread K over enough blocks to fill the machine (148 SMs x several CTAs)
+    int k_split = (148 * 8 + n_blocks * B - 1) / (n_blocks * B);
+    if (k_split < 1) k_split = 1;
+    if (k_split > K) k_split = K;
+    const int k_per_block = (K + k_split - 1) / k_split;
+    k_split = (K + k_per_block - 1) / k_per_block;
+    dim3 grid(n_blocks, k_split, B);
+    sample_bwd_dense_kernel<<<grid, kBwdThreads, 0, st>>>(logits, noise, seed, offset, tau, B, K, N, k_per_block, lse,
+                                                          ck, grad_logits);
+    return check_launch();
+}

@@ -1,0 +1,170 @@
+"""Batched hypothesize-and-score pipelines and their autograd wrappers.
+
+This is the B200-side replacement of the reference's per-pair Python loop
+(`model_cl.py:488-510`) around `RANSAC.__call__` (`ransac.py:41-200`): all B pairs and
+all K hypotheses go through one launch per stage -- sample -> minimal solve ->
+residual/score -> arg-max -- with nothing of size K x N ever materialised.
+
+Test mode  : `ransac_e5_test`, `ransac_f8_test`          (ransac.py:109-142 without early exit)
+Train mode : `HypothesizeE5`, `HypothesizeF8`, `HypothesizeRigid` (ransac.py:78-108 / :352-382)
+Loss       : `EpisymLoss` (loss.py:138-151), `RigidResidual` (rigid...solver.py:76-89)
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+def _noise_args(noise, seed, offset):
+    return dict(noise=noise, seed=int(seed), offset=int(offset))
+
+
+# ---- test mode ---------------------------------------------------------------------------------
+def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False):
+    """matches [B,N,4], logits [B,N], thr [B] (normalised threshold, ransac.py:49-53).
+    Returns dict(best_model [B,3,3], best_hyp [B], best_slot [B], best_score [B], mask [B,N] bool,
+    ninl [B], idx [B,K,5], models [B,K,10,3,3], nsol [B,K] (, scores [B,K*10] in compact order,
+    cids))."""
+    idx, _, _, _ = ops.sample(logits, K, 5, tau, **_noise_args(noise, seed, offset))
+    models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
+    scores, best = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=want_scores)
+    B = matches.shape[0]
+    best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, models.reshape(B, -1, 9), best, thr)
+    out = dict(best_model=best_model, best_id=best_id, best_hyp=torch.div(best_id, ops.E5_SLOTS, rounding_mode="floor"),
+               best_slot=best_id % ops.E5_SLOTS, best_score=best_score, mask=mask.bool(), ninl=ninl, idx=idx,
+               models=models, nsol=nsol)
+    if want_scores:
+        out.update(scores=scores, cids=cid, ccount=cc)
+    return out
+
+
+def ransac_f8_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False):
+    idx, _, _, _ = ops.sample(logits, K, 8, tau, **_noise_args(noise, seed, offset))
+    models, valid = ops.solve_f8(matches, idx)
+    scores, best = ops.score_msac(matches, models, thr, want_scores=want_scores)
+    best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, models, best, thr)
+    out = dict(best_model=best_model, best_id=best_id, best_hyp=best_id, best_score=best_score, mask=mask.bool(),
+               ninl=ninl, idx=idx, models=models, valid=valid.bool())
+    if want_scores:
+        out["scores"] = scores
+    return out
+
+
+# ---- train mode --------------------------------------------------------------------------------
+class _HypothesizeBase(torch.autograd.Function):
+    """sample -> minimal solve (-> slot selection); backward: solver IFT adjoint ->
+    gather backward -> straight-through sampler backward.  Gradients reach `matches`
+    and `logits` (what train.py / train_ransac_loftr.py need)."""
+
+    @staticmethod
+    def _backward_common(ctx, g_pts):
+        matches, logits, idx, lse, sel_key = ctx.saved_tensors[:5]
+        g_sel, gm = ops.gather_backward(matches, idx, g_pts, want_grad_matches=ctx.needs_input_grad[0])
+        gl = None
+        if ctx.needs_input_grad[1]:
+            gl = ops.sample_backward(logits, idx, lse, sel_key, g_sel, ctx.tau, ctx.noise, ctx.seed, ctx.offset)
+        return gm, gl
+
+
+class HypothesizeE5(_HypothesizeBase):
+    @staticmethod
+    def forward(ctx, matches, logits, gt, K, tau=1.0, noise=None, seed=0, offset=0, sign_invariant=True):
+        idx, lse, sel_key, _ = ops.sample(logits, K, 5, tau, noise, seed, offset, want_lse=True)
+        models, nsol = ops.solve_e5(matches, idx)
+        sel, chosen = ops.select_closest(models, nsol, gt, sign_invariant)
+        ctx.save_for_backward(ops._f32(matches), ops._f32(logits), idx, lse, sel_key, models, sel)
+        ctx.tau, ctx.noise, ctx.seed, ctx.offset = float(tau), noise, int(seed), int(offset)
+        valid = sel >= 0
+        ctx.mark_non_differentiable(valid)
+        return chosen, valid
+
+    @staticmethod
+    def backward(ctx, g_chosen, _g_valid):
+        matches, logits, idx, lse, sel_key, models, sel = ctx.saved_tensors
+        g_pts = ops.solve_e5_backward(matches, idx, models, sel, g_chosen.reshape(*sel.shape, 9))
+        gm, gl = _HypothesizeBase._backward_common(ctx, g_pts)
+        return gm, gl, None, None, None, None, None, None, None
+
+
+class HypothesizeF8(_HypothesizeBase):
+    @staticmethod
+    def forward(ctx, matches, logits, K, tau=1.0, noise=None, seed=0, offset=0):
+        idx, lse, sel_key, _ = ops.sample(logits, K, 8, tau, noise, seed, offset, want_lse=True)
+        models, valid = ops.solve_f8(matches, idx)
+        ctx.save_for_backward(ops._f32(matches), ops._f32(logits), idx, lse, sel_key)
+        ctx.tau, ctx.noise, ctx.seed, ctx.offset = float(tau), noise, int(seed), int(offset)
+        valid = valid.bool()
+        ctx.mark_non_differentiable(valid)
+        return models, valid
+
+    @staticmethod
+    def backward(ctx, g_models, _g_valid):
+        matches, logits, idx, lse, sel_key = ctx.saved_tensors
+        g_pts = ops.solve_f8_backward(matches, idx, g_models.reshape(*idx.shape[:2], 9))
+        gm, gl = _HypothesizeBase._backward_common(ctx, g_pts)
+        return gm, gl, None, None, None, None, None
+
+
+class HypothesizeRigid(_HypothesizeBase):
+    @staticmethod
+    def forward(ctx, points, logits, K, flag=True, tau=1.0, noise=None, seed=0, offset=0):
+        idx, lse, sel_key, _ = ops.sample(logits, K, 3, tau, noise, seed, offset, want_lse=True)
+        models, valid = ops.solve_rigid3(points, idx, flag)
+        ctx.save_for_backward(ops._f32(points), ops._f32(logits), idx, lse, sel_key)
+        ctx.tau, ctx.noise, ctx.seed, ctx.offset, ctx.flag = float(tau), noise, int(seed), int(offset), bool(flag)
+        valid = valid.bool()
+        ctx.mark_non_differentiable(valid)
+        return models, valid
+
+    @staticmethod
+    def backward(ctx, g_models, _g_valid):
+        points, logits, idx, lse, sel_key = ctx.saved_tensors
+        g_pts = ops.solve_rigid3_backward(points, idx, g_models.reshape(*idx.shape[:2], 16), ctx.flag)
+        gm, gl = _HypothesizeBase._backward_common(ctx, g_pts)
+        return gm, gl, None, None, None, None, None, None
+
+
+# ---- losses ------------------------------------------------------------------------------------
+class EpisymLoss(torch.autograd.Function):
+    """row_sum[b,k] = sum_p min(episym(pts[b,p], models[b,k]), 1)   (loss.py:138-144).
+    Differentiable w.r.t. models only (the correspondences are data in train.py)."""
+
+    @staticmethod
+    def forward(ctx, pts, models, npts=None, mvalid=None):
+        out = ops.episym_forward(pts, models, npts, mvalid)
+        ctx.save_for_backward(ops._f32(pts), ops._f32(models))
+        ctx.npts, ctx.mvalid = npts, mvalid
+        return out
+
+    @staticmethod
+    def backward(ctx, g_row):
+        pts, models = ctx.saved_tensors
+        g = ops.episym_backward(pts, models, g_row, ctx.npts, ctx.mvalid)
+        return None, g.reshape(models.shape), None, None
+
+
+class RigidResidual(torch.autograd.Function):
+    """res_sum[b,k] = sum_n ||q_n - (R p_n + t)||^2   (rigid...solver.py:76-89)."""
+
+    @staticmethod
+    def forward(ctx, points, models):
+        res, _ = ops.rigid_residual_forward(points, models, want_ninl=False)
+        ctx.save_for_backward(ops._f32(points), ops._f32(models))
+        return res
+
+    @staticmethod
+    def backward(ctx, g_res):
+        points, models = ctx.saved_tensors
+        return None, ops.rigid_residual_backward(points, models, g_res).reshape(models.shape)
+
+
+def match_loss(models, valid, pts, npts=None):
+    """Mean over valid models and points of min(episym, 1): the MatchLoss value of
+    loss.py:138-151 for every pair.  models [B,K,3,3], valid [B,K], pts [B,P,4] (the GT-inlier
+    correspondences, zero-padded to P with npts[b] real ones).  Returns [B]."""
+    B, P, _ = pts.shape
+    row = EpisymLoss.apply(pts, models, npts, valid)
+    n = (npts if npts is not None else torch.full((B,), P, device=pts.device)).to(row.dtype)
+    v = valid.to(row.dtype)
+    return (row * v).sum(1) / (v.sum(1).clamp_min(1.0) * n.clamp_min(1.0))

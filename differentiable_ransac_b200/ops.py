@@ -1,0 +1,276 @@
+"""Thin torch wrappers over the C ABI (include/drb.h): one function per entry point.
+Tensors are CUDA fp32 / int32, contiguous; every call runs on torch's current stream.
+PyTorch here is plumbing (device memory + streams) -- all arithmetic is in libdrb.so."""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+E5_SLOTS = 10
+F7_SLOTS = 3
+
+
+def _p(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32(t: torch.Tensor) -> torch.Tensor:
+    if t.device.type != "cuda":
+        raise _lib.DrbError("libdrb operates on CUDA tensors only (no CPU fallback)")
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    t = t.contiguous()
+    if t.data_ptr() % 16:
+        t = t.clone()
+    return t
+
+
+def _i32(t: torch.Tensor) -> torch.Tensor:
+    t = t.detach()
+    if t.dtype != torch.int32:
+        t = t.to(torch.int32)
+    return t.contiguous()
+
+
+# ---- sampler -----------------------------------------------------------------------------------
+def sample(logits, K, s, tau=1.0, noise=None, seed=0, offset=0, want_lse=False, want_noise=False):
+    """logits [B,N] -> idx [B,K,s] int32 (ascending per row), lse [B,K] | None,
+    sel_key [B,K,s] | None, noise_out [B,K,N] | None."""
+    logits = _f32(logits)
+    B, N = logits.shape
+    dev = logits.device
+    noise = None if noise is None else _f32(noise)
+    if noise is not None and tuple(noise.shape) != (B, K, N):
+        raise ValueError(f"noise must be [B,K,N] = {(B, K, N)}, got {tuple(noise.shape)}")
+    idx = torch.empty(B, K, s, dtype=torch.int32, device=dev)
+    lse = torch.empty(B, K, dtype=torch.float32, device=dev) if want_lse else None
+    sel_key = torch.empty(B, K, s, dtype=torch.float32, device=dev) if want_lse else None
+    noise_out = torch.empty(B, K, N, dtype=torch.float32, device=dev) if want_noise else None
+    lib = _lib.load()
+    check(lib.drb_sample(_p(logits), _p(noise), seed, offset, float(tau), B, K, N, s, _p(idx), _p(lse), _p(sel_key),
+                         _p(noise_out), _stream()), "drb_sample")
+    return idx, lse, sel_key, noise_out
+
+
+def sample_backward(logits, idx, lse, sel_key, g_sel, tau=1.0, noise=None, seed=0, offset=0):
+    logits = _f32(logits)
+    B, N = logits.shape
+    _, K, s = idx.shape
+    noise = None if noise is None else _f32(noise)
+    g_sel = _f32(g_sel)
+    grad = torch.zeros(B, N, dtype=torch.float32, device=logits.device)
+    scratch = torch.empty(B, K, dtype=torch.float32, device=logits.device)
+    lib = _lib.load()
+    check(lib.drb_sample_backward(_p(logits), _p(noise), seed, offset, float(tau), B, K, N, s, _p(idx), _p(lse),
+                                  _p(sel_key), _p(g_sel), _p(scratch), _p(grad), _stream()), "drb_sample_backward")
+    return grad
+
+
+def gather_backward(matches, idx, g_pts, want_grad_matches=True):
+    """g_pts [B,K,s,D] -> g_sel [B,K,s], grad_matches [B,N,D] | None."""
+    matches = _f32(matches)
+    B, N, D = matches.shape
+    _, K, s = idx.shape
+    g_pts = _f32(g_pts)
+    g_sel = torch.empty(B, K, s, dtype=torch.float32, device=matches.device)
+    gm = torch.zeros_like(matches) if want_grad_matches else None
+    lib = _lib.load()
+    check(lib.drb_gather_backward(_p(matches), _p(idx), _p(g_pts), B, K, N, s, D, _p(g_sel), _p(gm), _stream()),
+          "drb_gather_backward")
+    return g_sel, gm
+
+
+# ---- solvers -----------------------------------------------------------------------------------
+def _rows(matches, idx, s, D):
+    """Resolve the (gathered | indexed) calling convention -> (matches, idx, B, K, N)."""
+    matches = _f32(matches)
+    if idx is None:
+        if matches.dim() != 3 or matches.shape[1] != s or matches.shape[2] != D:
+            raise ValueError(f"gathered minimal samples must be [M,{s},{D}], got {tuple(matches.shape)}")
+        return matches, None, 1, matches.shape[0], 0
+    idx = _i32(idx)
+    B, N, _ = matches.shape
+    if idx.shape[0] != B or idx.shape[2] != s:
+        raise ValueError("idx must be [B,K,s]")
+    return matches, idx, B, idx.shape[1], N
+
+
+def solve_e5(matches, idx=None, compact=False):
+    """-> models [B,K,10,3,3], nsol [B,K] int32 (, cmodels [B,K*10,9], cids [B,K*10], ccount [B])."""
+    matches, idx, B, K, N = _rows(matches, idx, 5, 4)
+    dev = matches.device
+    models = torch.empty(B, K, E5_SLOTS, 3, 3, dtype=torch.float32, device=dev)
+    nsol = torch.empty(B, K, dtype=torch.int32, device=dev)
+    cm = cid = cc = None
+    if compact:
+        cm = torch.empty(B, K * E5_SLOTS, 9, dtype=torch.float32, device=dev)
+        cid = torch.empty(B, K * E5_SLOTS, dtype=torch.int32, device=dev)
+        cc = torch.zeros(B, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    check(lib.drb_solve_e5(_p(matches), _p(idx), B, K, N, _p(models), _p(nsol), _p(cm), _p(cid), _p(cc), _stream()),
+          "drb_solve_e5")
+    if compact:
+        return models, nsol, cm, cid, cc
+    return models, nsol
+
+
+def solve_e5_backward(matches, idx, models, sel, g_model):
+    matches, idx, B, K, N = _rows(matches, idx, 5, 4)
+    g_pts = torch.empty(B, K, 5, 4, dtype=torch.float32, device=matches.device)
+    lib = _lib.load()
+    check(lib.drb_solve_e5_backward(_p(matches), _p(idx), B, K, N, _p(_f32(models)), _p(_i32(sel)), _p(_f32(g_model)),
+                                    _p(g_pts), _stream()), "drb_solve_e5_backward")
+    return g_pts
+
+
+def select_closest(models, nsol, gt, sign_invariant=True):
+    """models [B,K,S,3,3], nsol [B,K], gt [B,3,3] -> sel [B,K] int32, chosen [B,K,3,3]."""
+    models = _f32(models)
+    B, K, S = models.shape[:3]
+    sel = torch.empty(B, K, dtype=torch.int32, device=models.device)
+    chosen = torch.empty(B, K, 3, 3, dtype=torch.float32, device=models.device)
+    lib = _lib.load()
+    check(lib.drb_select_closest(_p(models), _p(_i32(nsol)), _p(_f32(gt)), B, K, S, int(bool(sign_invariant)),
+                                 _p(sel), _p(chosen), _stream()), "drb_select_closest")
+    return sel, chosen
+
+
+def solve_f8(matches, idx=None):
+    matches, idx, B, K, N = _rows(matches, idx, 8, 4)
+    models = torch.empty(B, K, 3, 3, dtype=torch.float32, device=matches.device)
+    valid = torch.empty(B, K, dtype=torch.uint8, device=matches.device)
+    lib = _lib.load()
+    check(lib.drb_solve_f8(_p(matches), _p(idx), B, K, N, _p(models), _p(valid), _stream()), "drb_solve_f8")
+    return models, valid
+
+
+def solve_f8_backward(matches, idx, g_model):
+    matches, idx, B, K, N = _rows(matches, idx, 8, 4)
+    g_pts = torch.empty(B, K, 8, 4, dtype=torch.float32, device=matches.device)
+    lib = _lib.load()
+    check(lib.drb_solve_f8_backward(_p(matches), _p(idx), B, K, N, None, _p(_f32(g_model)), _p(g_pts), _stream()),
+          "drb_solve_f8_backward")
+    return g_pts
+
+
+def solve_f7(matches, idx=None):
+    matches, idx, B, K, N = _rows(matches, idx, 7, 4)
+    models = torch.empty(B, K, F7_SLOTS, 3, 3, dtype=torch.float32, device=matches.device)
+    nsol = torch.empty(B, K, dtype=torch.int32, device=matches.device)
+    lib = _lib.load()
+    check(lib.drb_solve_f7(_p(matches), _p(idx), B, K, N, _p(models), _p(nsol), _stream()), "drb_solve_f7")
+    return models, nsol
+
+
+def solve_rigid3(points, idx=None, flag=True):
+    points, idx, B, K, N = _rows(points, idx, 3, 6)
+    models = torch.empty(B, K, 4, 4, dtype=torch.float32, device=points.device)
+    valid = torch.empty(B, K, dtype=torch.uint8, device=points.device)
+    lib = _lib.load()
+    check(lib.drb_solve_rigid3(_p(points), _p(idx), B, K, N, int(bool(flag)), _p(models), _p(valid), _stream()),
+          "drb_solve_rigid3")
+    return models, valid
+
+
+def solve_rigid3_backward(points, idx, g_model, flag=True):
+    points, idx, B, K, N = _rows(points, idx, 3, 6)
+    g_pts = torch.empty(B, K, 3, 6, dtype=torch.float32, device=points.device)
+    lib = _lib.load()
+    check(lib.drb_solve_rigid3_backward(_p(points), _p(idx), B, K, N, int(bool(flag)), None, _p(_f32(g_model)),
+                                        _p(g_pts), _stream()), "drb_solve_rigid3_backward")
+    return g_pts
+
+
+# ---- scoring -----------------------------------------------------------------------------------
+def score_msac(matches, models, thr, count=None, ids=None, want_scores=True):
+    """matches [B,N,4], models [B,M,9|3,3], thr [B] -> scores [B,M] | None, best_packed [B] (int64 view of u64)."""
+    matches = _f32(matches)
+    B, N, _ = matches.shape
+    models = _f32(models).reshape(B, -1, 9)
+    M = models.shape[1]
+    thr = _f32(thr).reshape(B)
+    scores = torch.empty(B, M, dtype=torch.float32, device=matches.device) if want_scores else None
+    best = torch.zeros(B, dtype=torch.int64, device=matches.device)
+    lib = _lib.load()
+    check(lib.drb_score_msac(_p(matches), _p(models), _p(None if count is None else _i32(count)),
+                             _p(None if ids is None else _i32(ids)), _p(thr), B, M, N, _p(scores), _p(best),
+                             _stream()), "drb_score_msac")
+    return scores, best
+
+
+def best_finalize(matches, models_dense, best_packed, thr, want_mask=True):
+    matches = _f32(matches)
+    B, N, _ = matches.shape
+    md = _f32(models_dense).reshape(B, -1, 9)
+    dev = matches.device
+    best_id = torch.empty(B, dtype=torch.int32, device=dev)
+    best_score = torch.empty(B, dtype=torch.float32, device=dev)
+    best_model = torch.empty(B, 3, 3, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, N, dtype=torch.uint8, device=dev) if want_mask else None
+    ninl = torch.empty(B, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    check(lib.drb_best_finalize(_p(matches), _p(md), _p(best_packed), _p(_f32(thr).reshape(B)), B, md.shape[1], N,
+                                _p(best_id), _p(best_score), _p(best_model), _p(mask), _p(ninl), _stream()),
+          "drb_best_finalize")
+    return best_id, best_score, best_model, mask, ninl
+
+
+def episym_forward(pts, models, npts=None, mvalid=None):
+    """pts [B,P,4], models [B,K,3,3] -> row_sum [B,K] = sum_p min(episym, 1)."""
+    pts = _f32(pts)
+    B, P, _ = pts.shape
+    models = _f32(models).reshape(B, -1, 9)
+    K = models.shape[1]
+    out = torch.empty(B, K, dtype=torch.float32, device=pts.device)
+    lib = _lib.load()
+    check(lib.drb_episym_forward(_p(pts), _p(None if npts is None else _i32(npts)), _p(models),
+                                 _p(None if mvalid is None else mvalid.to(torch.uint8).contiguous()), B, K, P, _p(out),
+                                 _stream()), "drb_episym_forward")
+    return out
+
+
+def episym_backward(pts, models, g_row, npts=None, mvalid=None):
+    pts = _f32(pts)
+    B, P, _ = pts.shape
+    models = _f32(models).reshape(B, -1, 9)
+    K = models.shape[1]
+    out = torch.empty(B, K, 3, 3, dtype=torch.float32, device=pts.device)
+    lib = _lib.load()
+    check(lib.drb_episym_backward(_p(pts), _p(None if npts is None else _i32(npts)), _p(models),
+                                  _p(None if mvalid is None else mvalid.to(torch.uint8).contiguous()),
+                                  _p(_f32(g_row)), B, K, P, _p(out), _stream()), "drb_episym_backward")
+    return out
+
+
+def rigid_residual_forward(points, models, threshold=0.03, want_ninl=True):
+    points = _f32(points)
+    B, N, _ = points.shape
+    models = _f32(models).reshape(B, -1, 16)
+    K = models.shape[1]
+    res = torch.empty(B, K, dtype=torch.float32, device=points.device)
+    ninl = torch.empty(B, K, dtype=torch.int32, device=points.device) if want_ninl else None
+    lib = _lib.load()
+    check(lib.drb_rigid_residual_forward(_p(points), _p(models), B, K, N, float(threshold), _p(res), _p(ninl),
+                                         _stream()), "drb_rigid_residual_forward")
+    return res, ninl
+
+
+def rigid_residual_backward(points, models, g_res):
+    points = _f32(points)
+    B, N, _ = points.shape
+    models = _f32(models).reshape(B, -1, 16)
+    K = models.shape[1]
+    out = torch.empty(B, K, 4, 4, dtype=torch.float32, device=points.device)
+    lib = _lib.load()
+    check(lib.drb_rigid_residual_backward(_p(points), _p(models), _p(_f32(g_res)), B, K, N, _p(out), _stream()),
+          "drb_rigid_residual_backward")
+    return out

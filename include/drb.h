@@ -1,0 +1,169 @@
+/* drb.h -- C ABI of the B200 differentiable-RANSAC hot path (libdrb.so).
+ *
+ * The reference (weitong8591/differentiable_ransac) is pure Python and has no
+ * native boundary; these entry points are what a ctypes / cffi binding inside
+ * the reference's plugin classes calls instead of the torch tensor graph.  Each
+ * entry cites the reference interface it replaces.  See INTEGRATION.md for the
+ * reference-side stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates);
+ *     the library never allocates, frees or keeps state between calls;
+ *   - tensors are contiguous row-major fp32 unless stated; B pairs, K hypotheses
+ *     (minimal samples) per pair, N correspondences per pair, s sample size;
+ *   - calls are asynchronous on `stream` (a cudaStream_t passed as void*), never
+ *     synchronise, and are re-entrant;
+ *   - return 0 on success or a negative drb_status; nothing is thrown across
+ *     the boundary.  Launch errors are reported by the call that caused them;
+ *     asynchronous execution errors by drb_last_error().
+ *   - per-hypothesis numerical failure is NOT an error: the slot gets the
+ *     identity model and valid = 0 (mirrors nister.py:400-405).
+ *   - model layout: 3x3 row-major M with x2^T M x1 = 0, x1 = matches[:,0:2],
+ *     x2 = matches[:,2:4] (the convention of every reference estimator).
+ */
+#ifndef DRB_H_
+#define DRB_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    DRB_OK = 0,
+    DRB_ERR_NULL_POINTER = -1,
+    DRB_ERR_BAD_SHAPE = -2,
+    DRB_ERR_UNSUPPORTED = -3,
+    DRB_ERR_CUDA = -4
+} drb_status;
+
+#define DRB_E5_SLOTS 10 /* models per 5-point sample, as the reference (nister.py:400) */
+#define DRB_F7_SLOTS 3  /* real solutions of the 7-point cubic */
+
+int drb_version(void);
+const char* drb_status_string(int status);
+/* cudaGetLastError()/cudaPeekAtLastError() of the calling thread's device, as an int. */
+int drb_last_error(void);
+/* Shared-memory / occupancy facts used by the host mirror and the benchmark. */
+int drb_device_sm_count(void);
+
+/* ---- a1 + a2: Gumbel top-s sampler and minimal-sample gather ------------------------------
+ * Replaces GumbelSoftmaxSampler.sample (samplers/gumbel_sampler.py:25-42) and the gather
+ * ransac.py:64-65.  For every (pair b, hypothesis k): keys[n] = (logits[b,n] + G[b,k,n]) / tau,
+ * the s largest keys are selected and returned as point indices in ASCENDING order (the order
+ * of the reference's boolean-mask gather).  G is read from `noise` ([B,K,N]) when non-null
+ * (parity mode), otherwise generated in-kernel with Philox4x32-10 keyed by (seed, offset).
+ * Optional outputs (nullable): lse[B,K] = logsumexp_n keys (needed by the backward),
+ * sel_key[B,K,s] = keys of the selected points (same order as idx), noise_out[B,K,N] = the
+ * Gumbel noise actually used (lets a test replay a Philox run through the oracle).        */
+int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau,
+               int B, int K, int N, int s,
+               int32_t* idx, float* lse, float* sel_key, float* noise_out, void* stream);
+
+/* Straight-through backward of the sampler (autograd of gumbel_sampler.py:34-38 + ransac.py:64-65).
+ * g_sel[B,K,s] = dL/d ret[b,k,idx[b,k,j]] = sum_c matches[n,c] * dL/d minimal[b,k,j,c].
+ * Adds to grad_logits[B,N] (caller zero-initialises):
+ *   (1/tau) * sum_k y[k,n] (g[k,n] - sum_m y[k,m] g[k,m]),  y = softmax_n(keys).
+ * The noise is re-read (`noise` non-null) or regenerated from (seed, offset); the K x N
+ * soft one-hot is never stored.  `scratch` is B*K floats of caller-owned workspace.          */
+int drb_sample_backward(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau,
+                        int B, int K, int N, int s,
+                        const int32_t* idx, const float* lse, const float* sel_key, const float* g_sel,
+                        float* scratch /* [B,K] */, float* grad_logits, void* stream);
+
+/* ---- a3 / a4: five-point essential matrix ---------------------------------------------------
+ * Replaces EssentialMatrixEstimatorNister.estimate_minimal_model (nister.py:69-408) and
+ * EssentialMatrixEstimator.estimate_minimal_model (stewenius.py:20-80).
+ * Input is either gathered (idx == NULL: `matches` is [B*K,5,4] minimal samples, N ignored) or
+ * indexed (idx[B,K,5] into matches[B,N,4]).  Outputs: models[B,K,10,9] (unit Frobenius norm),
+ * nsol[B,K] real solutions in slots 0..nsol-1 (others = identity).  Optional compact list for
+ * the scorer: cmodels[B,K*10,9], cids[B,K*10] (= k*10+slot), ccount[B] (caller zeroes).     */
+int drb_solve_e5(const float* matches, const int32_t* idx, int B, int K, int N,
+                 float* models, int32_t* nsol, float* cmodels, int32_t* cids, int32_t* ccount, void* stream);
+
+/* Backward of the five-point solver by the implicit-function theorem at the solution
+ * (replaces autograd through nister.py:117-399).  For every (b,k) and the slot `sel[b,k]`
+ * (-1 = no gradient): g_model[B,K,9] = dL/dE  ->  g_pts[B,K,5,4] = dL/d minimal sample.     */
+int drb_solve_e5_backward(const float* matches, const int32_t* idx, int B, int K, int N,
+                          const float* models, const int32_t* sel, const float* g_model,
+                          float* g_pts, void* stream);
+
+/* Train-mode slot selection, ransac.py:87-96: per sample the slot closest to gt[B,9] in
+ * Frobenius norm (sign_invariant != 0: min(||E-gt||, ||E+gt||)).  Writes
+ * sel[B,K] (-1 when nsol == 0) and chosen[B,K,9].                                             */
+int drb_select_closest(const float* models, const int32_t* nsol, const float* gt, int B, int K, int slots,
+                       int sign_invariant, int32_t* sel, float* chosen, void* stream);
+
+/* ---- a5 / a6: fundamental matrix ------------------------------------------------------------
+ * Replaces FundamentalMatrixEstimatorNew.normalize + estimate_non_minimal_model
+ * (fundamental_matrix_estimator.py:177-260): Hartley-normalised s-point (s = 8) null vector,
+ * F = T2^T Fn T1, unit-norm Fn, no rank-2 projection.  models[B,K,9], valid[B,K].          */
+int drb_solve_f8(const float* matches, const int32_t* idx, int B, int K, int N,
+                 float* models, uint8_t* valid, void* stream);
+int drb_solve_f8_backward(const float* matches, const int32_t* idx, int B, int K, int N,
+                          const float* models, const float* g_model, float* g_pts, void* stream);
+/* Correct 7-point (the reference's, fundamental_matrix_estimator.py:262-308, is broken: SURVEY D4).
+ * models[B,K,3,9], nsol[B,K].                                                                 */
+int drb_solve_f7(const float* matches, const int32_t* idx, int B, int K, int N,
+                 float* models, int32_t* nsol, void* stream);
+
+/* ---- a7: rigid 3-point ----------------------------------------------------------------------
+ * Replaces RigidTransformationSVDBasedSolver.estimate_model
+ * (rigid_transformation_SVD_based_solver.py:11-74), both `flag` branches.  points [B,N,6] or
+ * gathered [B*K,3,6]; models[B,K,16] = 4x4 pose row-major; valid[B,K].                      */
+int drb_solve_rigid3(const float* points, const int32_t* idx, int B, int K, int N, int flag,
+                     float* models, uint8_t* valid, void* stream);
+int drb_solve_rigid3_backward(const float* points, const int32_t* idx, int B, int K, int N, int flag,
+                              const float* models, const float* g_model, float* g_pts, void* stream);
+
+/* ---- a9: Sampson / soft-MSAC scoring with fused arg-max -------------------------------------
+ * Replaces MSACScore.score (scorings/msac_score.py:12-55) and the arg-max of ransac.py:114.
+ * models[B,M,9]; count[B] (nullable: all M) = number of leading models to score per pair;
+ * ids[B,M] (nullable: identity) = caller's index of each model, used for the tie-break and
+ * reported in best_id; thr[B] = the (already normalised) inlier threshold per pair;
+ * scores[B,M] (nullable) in the order of `models`.  best_packed[B] (caller zeroes) receives
+ * max over models of (score bits << 32 | ~id): decode with drb_best_finalize.  NaN scores
+ * never win.                                                                     */
+int drb_score_msac(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
+                   const float* thr, int B, int M, int N,
+                   float* scores, unsigned long long* best_packed, void* stream);
+/* Decode best_packed and produce the winner's model, score, id and inlier mask
+ * (d2 < (1.5 thr)^2, msac_score.py:44) -- the only mask ransac.py:116-118 ever uses.
+ * models_dense[B,Md,9] is indexed by best id.  best_id[B], best_score[B], best_model[B,9],
+ * mask[B,N] (uint8), ninl[B].                                                                */
+int drb_best_finalize(const float* matches, const float* models_dense, const unsigned long long* best_packed,
+                      const float* thr, int B, int Md, int N,
+                      int32_t* best_id, float* best_score, float* best_model, uint8_t* mask, int32_t* ninl,
+                      void* stream);
+
+/* ---- a10: symmetric epipolar loss (MatchLoss core) ------------------------------------------
+ * Replaces batch_episym (model_cl.py:13-26) + min(.,1) + mean of loss.py:138-151 over the
+ * GT-inlier subset.  pts[B,P,4] (the inlier correspondences, P may be padded: npts[B] valid),
+ * models[B,K,9], mvalid[B,K] (nullable).  row_sum[B,K] = sum_p min(episym, 1).            */
+int drb_episym_forward(const float* pts, const int32_t* npts, const float* models, const uint8_t* mvalid,
+                       int B, int K, int P, float* row_sum, void* stream);
+/* g_row[B,K] = dL/d row_sum  ->  g_models[B,K,9] (clamped entries contribute zero).          */
+int drb_episym_backward(const float* pts, const int32_t* npts, const float* models, const uint8_t* mvalid,
+                        const float* g_row, int B, int K, int P, float* g_models, void* stream);
+
+/* ---- a8: rigid squared residual -------------------------------------------------------------
+ * Replaces squared_residual (rigid_transformation_SVD_based_solver.py:76-89).
+ * points[B,N,6], models[B,K,16] -> res_sum[B,K] = sum_n ||q - (R p + t)||^2,
+ * ninl[B,K] (nullable) = #(d2 < threshold).                                                  */
+int drb_rigid_residual_forward(const float* points, const float* models, int B, int K, int N, float threshold,
+                               float* res_sum, int32_t* ninl, void* stream);
+/* g_res[B,K] -> g_models[B,K,16] (only the 3x4 [R|t] block is written).                      */
+int drb_rigid_residual_backward(const float* points, const float* models, const float* g_res,
+                                int B, int K, int N, float* g_models, void* stream);
+
+/* ---- a2 backward: scatter minimal-sample gradients ----------------------------------------------
+ * g_pts[B,K,s,D] = dL/d minimal  ->  g_sel[B,K,s] = sum_c matches[n,c] g_pts[...,c] and (nullable)
+ * grad_matches[B,N,D] += g_pts (atomic).                                                      */
+int drb_gather_backward(const float* matches, const int32_t* idx, const float* g_pts,
+                        int B, int K, int N, int s, int D, float* g_sel, float* grad_matches, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRB_H_ */

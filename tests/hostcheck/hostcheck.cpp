@@ -1,0 +1,116 @@
+// TEST INFRASTRUCTURE ONLY.  Compiles the device math headers
+// (differentiable_ransac_b200/csrc/*_math.cuh) for the HOST so the CPU test
+// suite (no GPU in the build container) can run the exact arithmetic of the
+// CUDA kernels against the oracle.  The package never loads this library; the
+// product path is the CUDA library and fails loudly without it.
+#include <cstring>
+#include <vector>
+
+#include "e5_math.cuh"
+#include "e5_backward.cuh"
+#include "f8_math.cuh"
+#include "rigid_math.cuh"
+
+namespace {
+template <class T>
+struct HostMat {
+    T v[10][20];
+    T& operator()(int r, int c) { return v[r][c]; }
+};
+
+template <class T, class RT = T>
+void run_e5(const T* pts, int K, T* models, int* nsol, int polish) {
+    for (int k = 0; k < K; ++k) {
+        T p[5][4];
+        for (int j = 0; j < 5; ++j)
+            for (int c = 0; c < 4; ++c) p[j][c] = pts[(k * 5 + j) * 4 + c];
+        HostMat<T> M;
+        T out[10][9];
+        nsol[k] = drb::e5_solve<T, HostMat<T>, RT>(p, M, out, polish);
+        std::memcpy(models + (size_t)k * 90, out, sizeof(out));
+    }
+}
+}  // namespace
+
+extern "C" {
+void hc_e5_solve_f32(const float* pts, int K, float* models, int* nsol, int polish) {
+    run_e5<float>(pts, K, models, nsol, polish);
+}
+void hc_e5_solve_f32_r64(const float* pts, int K, float* models, int* nsol, int polish) {
+    run_e5<float, double>(pts, K, models, nsol, polish);
+}
+void hc_e5_solve_f64(const double* pts, int K, double* models, int* nsol, int polish) {
+    run_e5<double>(pts, K, models, nsol, polish);
+}
+int hc_e5_backward_f64(const double* pts, const double* E, const double* g, double* gp) {
+    double p[5][4], o[5][4];
+    std::memcpy(p, pts, sizeof(p));
+    bool ok = drb::e5_backward<double, double>(p, E, g, o);
+    std::memcpy(gp, o, sizeof(o));
+    return ok ? 1 : 0;
+}
+int hc_e5_backward_f32(const float* pts, const float* E, const float* g, float* gp) {
+    float p[5][4], o[5][4];
+    std::memcpy(p, pts, sizeof(p));
+    bool ok = drb::e5_backward<float, double>(p, E, g, o);
+    std::memcpy(gp, o, sizeof(o));
+    return ok ? 1 : 0;
+}
+// ---- 8-point / 7-point / rigid ------------------------------------------------------------
+#define HC_F8(NAME, T)                                                                         \
+    void NAME(const T* pts, int K, T* F, int* ok) {                                            \
+        for (int k = 0; k < K; ++k) {                                                          \
+            T p[8][4];                                                                         \
+            std::memcpy(p, pts + (size_t)k * 32, sizeof(p));                                   \
+            ok[k] = drb::f8_solve<T>(p, F + (size_t)k * 9) ? 1 : 0;                            \
+        }                                                                                      \
+    }
+HC_F8(hc_f8_solve_f32, float)
+HC_F8(hc_f8_solve_f64, double)
+#define HC_F8B(NAME, T)                                                                        \
+    void NAME(const T* pts, const T* g, int K, T* gp, int* ok) {                               \
+        for (int k = 0; k < K; ++k) {                                                          \
+            T p[8][4], o[8][4];                                                                \
+            std::memcpy(p, pts + (size_t)k * 32, sizeof(p));                                   \
+            ok[k] = drb::f8_backward<T, double>(p, g + (size_t)k * 9, o) ? 1 : 0;              \
+            std::memcpy(gp + (size_t)k * 32, o, sizeof(o));                                    \
+        }                                                                                      \
+    }
+HC_F8B(hc_f8_backward_f32, float)
+HC_F8B(hc_f8_backward_f64, double)
+#define HC_F7(NAME, T)                                                                         \
+    void NAME(const T* pts, int K, T* F, int* n) {                                             \
+        for (int k = 0; k < K; ++k) {                                                          \
+            T p[7][4], o[3][9];                                                                \
+            std::memcpy(p, pts + (size_t)k * 28, sizeof(p));                                   \
+            n[k] = drb::f7_solve<T>(p, o);                                                     \
+            std::memcpy(F + (size_t)k * 27, o, sizeof(o));                                     \
+        }                                                                                      \
+    }
+HC_F7(hc_f7_solve_f32, float)
+HC_F7(hc_f7_solve_f64, double)
+#define HC_RIGID(NAME, T)                                                                      \
+    void NAME(const T* pts, int K, int flag, T* model, int* ok) {                              \
+        for (int k = 0; k < K; ++k) {                                                          \
+            T p[3][6];                                                                         \
+            std::memcpy(p, pts + (size_t)k * 18, sizeof(p));                                   \
+            ok[k] = drb::rigid3_solve<T>(p, flag, model + (size_t)k * 16) ? 1 : 0;             \
+        }                                                                                      \
+    }
+HC_RIGID(hc_rigid3_solve_f32, float)
+HC_RIGID(hc_rigid3_solve_f64, double)
+#define HC_RIGIDB(NAME, T)                                                                     \
+    void NAME(const T* pts, const T* g, int K, int flag, T* gp, int* ok) {                     \
+        for (int k = 0; k < K; ++k) {                                                          \
+            T p[3][6], o[3][6];                                                                \
+            std::memcpy(p, pts + (size_t)k * 18, sizeof(p));                                   \
+            ok[k] = drb::rigid3_backward<T, double>(p, flag, g + (size_t)k * 16, o) ? 1 : 0;   \
+            std::memcpy(gp + (size_t)k * 18, o, sizeof(o));                                    \
+        }                                                                                      \
+    }
+HC_RIGIDB(hc_rigid3_backward_f32, float)
+HC_RIGIDB(hc_rigid3_backward_f64, double)
+
+int hc_roots_f32(const float* coef, float* roots) { return drb::real_roots_deg10<float>(coef, roots); }
+int hc_roots_f64(const double* coef, double* roots) { return drb::real_roots_deg10<double>(coef, roots); }
+}

@@ -1,0 +1,159 @@
+"""CPU checks of the DEVICE math headers (csrc/*_math.cuh) compiled for the host by
+tests/hostcheck -- the same templates the CUDA kernels instantiate -- against the oracle and
+the reference-generated golden fixtures.  No GPU needed; test infrastructure only."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import hostcheck
+from helpers import match_up_to_sign, trace_constraint_residual, unit
+from oracle import fundamental, nister, rigid
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return hostcheck.load()
+
+
+def vp(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_e5(lib, pts, dt, polish=2):
+    p = np.ascontiguousarray(pts.numpy().astype(dt))
+    K = p.shape[0]
+    out = np.zeros((K, 10, 9), dtype=dt)
+    ns = np.zeros(K, dtype=np.int32)
+    fn = lib.hc_e5_solve_f32 if dt == np.float32 else lib.hc_e5_solve_f64
+    fn(vp(p), K, vp(out), vp(ns), polish)
+    return torch.from_numpy(out).view(K, 10, 3, 3), torch.from_numpy(ns)
+
+
+def test_e5_fp64_finds_every_reference_model(lib, golden):
+    g = golden("nister")
+    E, ns = run_e5(lib, g["pts"], np.float64)
+    ref = g["E64"].view(-1, 10, 3, 3)
+    real = (trace_constraint_residual(g["E64"]) < 1e-8).view(-1, 10)
+    d = match_up_to_sign(E, ref)[real]
+    assert d.max() < 1e-6
+    assert (ns - real.sum(1)).abs().max() <= 1
+
+
+def test_e5_fp32_beats_reference_fp32_noise_floor(lib, golden):
+    g = golden("nister")
+    E, ns = run_e5(lib, g["pts"], np.float32)
+    ref = g["E64"].view(-1, 10, 3, 3)
+    real = (trace_constraint_residual(g["E64"]) < 1e-8).view(-1, 10)
+    d = match_up_to_sign(E, ref)[real]
+    d_ref = match_up_to_sign(g["E32"].view(-1, 10, 3, 3), ref)[real]
+    assert (d < 1e-3).float().mean() > 0.95
+    assert (d < 1e-3).float().mean() >= (d_ref < 1e-3).float().mean()
+    assert d.median() < 1e-5
+
+
+def test_sturm_roots_against_numpy(lib):
+    rng = np.random.default_rng(0)
+    for trial in range(200):
+        n_real = 2 * rng.integers(0, 6)
+        roots = list(rng.uniform(-3, 3, n_real))
+        while len(roots) < 10:
+            re, im = rng.uniform(-2, 2), rng.uniform(0.2, 2)
+            roots += [complex(re, im), complex(re, -im)]
+        c = np.real(np.poly(roots))[::-1].copy()          # ascending
+        c *= rng.uniform(0.1, 10)
+        out = np.zeros(10)
+        n = lib.hc_roots_f64(vp(np.ascontiguousarray(c)), vp(out))
+        want = np.sort(np.real([r for r in roots if abs(np.imag(r)) < 1e-12]))
+        assert n == len(want)
+        assert np.allclose(np.sort(out[:n]), want, atol=1e-7)
+
+
+def test_e5_backward_matches_autograd_of_the_oracle(lib, golden):
+    g = golden("nister")
+    gen = torch.Generator().manual_seed(0)
+    errs = []
+    for k in range(24):
+        pts = g["pts"][k:k + 1].double().clone().requires_grad_(True)
+        E = nister.five_point(pts)
+        real = trace_constraint_residual(E.detach()) < 1e-9
+        for s in range(10):
+            if not real[s]:
+                continue
+            gE = torch.randn(3, 3, dtype=torch.float64, generator=gen)
+            (gr,) = torch.autograd.grad((E[s] * gE).sum(), pts, retain_graph=True)
+            out = np.zeros((5, 4))
+            ok = lib.hc_e5_backward_f64(vp(np.ascontiguousarray(pts.detach().numpy()[0])),
+                                        vp(np.ascontiguousarray(E[s].detach().numpy())),
+                                        vp(np.ascontiguousarray(gE.numpy())), vp(out))
+            assert ok == 1
+            errs.append(np.abs(out - gr[0].numpy()).max() / np.abs(gr[0].numpy()).max())
+    errs = np.array(errs)
+    assert np.median(errs) < 1e-9 and (errs < 1e-4).mean() > 0.97
+
+
+def test_f8_forward_backward(lib, golden):
+    g = golden("f8")
+    pts = np.ascontiguousarray(g["pts"].numpy().astype(np.float32))
+    K = pts.shape[0]
+    F = np.zeros((K, 9), np.float32)
+    ok = np.zeros(K, np.int32)
+    lib.hc_f8_solve_f32(vp(pts), K, vp(F), vp(ok))
+    F = torch.from_numpy(F).view(K, 3, 3).double()
+    R = g["F64"]
+    d = torch.minimum((F - R).flatten(1).norm(dim=1), (F + R).flatten(1).norm(dim=1)) / R.flatten(1).norm(dim=1)
+    assert ok.all() and d.max() < 1e-4
+    p64 = g["pts"][:16].double().clone().requires_grad_(True)
+    Fo = fundamental.eight_point(p64)
+    gF = torch.randn(16, 3, 3, dtype=torch.float64, generator=torch.Generator().manual_seed(1))
+    pn = np.ascontiguousarray(p64.detach().numpy())
+    Fh = np.zeros((16, 9))
+    ok = np.zeros(16, np.int32)
+    lib.hc_f8_solve_f64(vp(pn), 16, vp(Fh), vp(ok))
+    sgn = torch.sign((torch.from_numpy(Fh).view(16, 3, 3) * Fo.detach()).flatten(1).sum(1))
+    (gr,) = torch.autograd.grad((Fo * gF).sum(), p64)
+    gours = np.zeros((16, 8, 4))
+    lib.hc_f8_backward_f64(vp(pn), vp(np.ascontiguousarray((gF * sgn[:, None, None]).numpy())), 16, vp(gours), vp(ok))
+    rel = (torch.from_numpy(gours) - gr).flatten(1).abs().max(1).values / gr.flatten(1).abs().max(1).values
+    assert ok.all() and rel.max() < 1e-7
+
+
+def test_f7_against_oracle(lib, golden):
+    g = golden("f8")
+    pts7 = np.ascontiguousarray(g["pts"][:, :7].numpy().astype(np.float64))
+    K = pts7.shape[0]
+    F7 = np.zeros((K, 3, 9))
+    n7 = np.zeros(K, np.int32)
+    lib.hc_f7_solve_f64(vp(pts7), K, vp(F7), vp(n7))
+    Fo, valid = fundamental.seven_point(torch.from_numpy(pts7))
+    assert (torch.from_numpy(n7) == valid.sum(1)).all()
+    F7 = torch.from_numpy(F7).view(K, 3, 3, 3)
+    for k in range(K):
+        for s in range(n7[k]):
+            cand = Fo[k][valid[k]]
+            d = torch.minimum((cand - F7[k, s]).flatten(1).norm(dim=1), (cand + F7[k, s]).flatten(1).norm(dim=1))
+            assert d.min() < 1e-7
+
+
+@pytest.mark.parametrize("flag", [1, 0])
+def test_rigid_forward_backward(lib, golden, flag):
+    g = golden("rigid")
+    pts = np.ascontiguousarray(g["pts"].numpy().astype(np.float32))
+    K = pts.shape[0]
+    M = np.zeros((K, 16), np.float32)
+    ok = np.zeros(K, np.int32)
+    lib.hc_rigid3_solve_f32(vp(pts), K, flag, vp(M), vp(ok))
+    assert ok.all()
+    assert torch.allclose(torch.from_numpy(M).view(K, 4, 4), g[f"model_{flag}"], atol=5e-4, rtol=1e-4)
+    p64 = g["pts"][:16].double().clone().requires_grad_(True)
+    m, _, _, _ = rigid.estimate(p64, flag=bool(flag))
+    gM = torch.randn(16, 4, 4, dtype=torch.float64, generator=torch.Generator().manual_seed(2))
+    gM[:, 3, :] = 0
+    (gr,) = torch.autograd.grad((m * gM).sum(), p64)
+    gours = np.zeros((16, 3, 6))
+    ok = np.zeros(16, np.int32)
+    lib.hc_rigid3_backward_f64(vp(np.ascontiguousarray(p64.detach().numpy())), vp(np.ascontiguousarray(gM.numpy())),
+                               16, flag, vp(gours), vp(ok))
+    rel = (torch.from_numpy(gours) - gr).flatten(1).abs().max(1).values / gr.flatten(1).abs().max(1).values
+    assert ok.all() and rel.max() < 1e-8

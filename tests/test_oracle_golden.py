@@ -3,7 +3,7 @@ produced by tests/golden/make_golden.py from /root/reference).  CPU only."""
 import torch
 
 from oracle import driver, fundamental, nister, rigid, sampler, scoring, stewenius
-from tests.helpers import match_up_to_sign, trace_constraint_residual, unit
+from helpers import match_up_to_sign, trace_constraint_residual, unit
 
 
 def test_sampler_and_gather(golden):
