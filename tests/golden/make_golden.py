@@ -169,8 +169,41 @@ def main():
         ep = batch_episym(p1, p2, Es)
         loss = torch.min(ep, ep.new_ones(ep.shape)).mean()
         loss.backward()
+        # The driver's slot choice (ransac.py:87-96) compares raw Frobenius norms although the sign of
+        # every E is arbitrary (nister.py:395-399) and complex-root slots are bogus, so
+        # its pick is noise-driven.  Second golden: the SAME reference sampler / estimator / loss and
+        # the same autograd chain, with the harness choosing, per sample, the genuine (real-root) slot
+        # closest to GT up to sign.  Samples without a genuine slot are left out of the mean.
+        smp2 = injected_sampler(Kc_, 5, [n.to(dt) for n in noises], dtype=dt)
+        lgs = lg2.to(dt).clone().requires_grad_(True)
+        ms_ = m2.to(dt).clone().requires_grad_(True)
+        chosen, keep = [], []
+        for c in range(nchunks):
+            ret, _ = smp2.sample(lgs)
+            pts_ = ms_.repeat([Kc_, 1, 1]) * ret.unsqueeze(-1)
+            minimal = pts_[ret != 0].view(Kc_, -1, 4)
+            em = est.estimate_model(minimal).view(Kc_, 10, 3, 3)
+            with torch.no_grad():
+                e64 = em.double()
+                eet = e64 @ e64.transpose(-1, -2)
+                tr = eet.diagonal(dim1=-2, dim2=-1).sum(-1)
+                resid = (2 * eet @ e64 - tr[..., None, None] * e64).flatten(2).norm(dim=-1)
+                genuine = resid < (1e-8 if dt == torch.float64 else 1e-3)
+                gt_ = Egt2.double()
+                dist = torch.minimum((e64 - gt_).flatten(2).norm(dim=-1), (e64 + gt_).flatten(2).norm(dim=-1))
+                dist[~genuine] = float("inf")
+                pick = dist.argmin(dim=1)
+            chosen.append(em[torch.arange(Kc_), pick])
+            keep.append(genuine.any(dim=1))
+        Es2 = torch.cat(chosen)
+        keep = torch.cat(keep)
+        ep2 = batch_episym(m2[inl2][:, :2].to(dt).repeat(Es2.shape[0], 1, 1),
+                           m2[inl2][:, 2:].to(dt).repeat(Es2.shape[0], 1, 1), Es2)
+        loss2 = torch.min(ep2, ep2.new_ones(ep2.shape))[keep].mean()
+        loss2.backward()
         save(f"driver_train_{prec}", matches=m2, logits=lg2, noise=torch.stack(noises), E_gt=Egt2,
-             gt_mask=inl2, models=Es, loss=loss, grad_logits=lgr.grad, grad_matches=mr_.grad)
+             gt_mask=inl2, models=Es, loss=loss, grad_logits=lgr.grad, grad_matches=mr_.grad,
+             sel_models=Es2, sel_keep=keep, sel_loss=loss2, sel_grad_logits=lgs.grad, sel_grad_matches=ms_.grad)
 
     # 8-point training step (cfg3 unit): sampler -> 8pt -> clamped episym mean, grads to logits
     N8, K8 = 1000, 48

@@ -262,23 +262,25 @@ def test_e5_train_step_gradients_vs_reference(drb, golden):
     inl = g64["matches"][g64["gt_mask"]]
     loss = drb.engine.match_loss(chosen, valid, inl[None].to(DEV))[0]
     loss.backward()
-    # which hypotheses picked the same model as the fp64 reference?
-    ref_models = g64["models"]
+    # The reference driver's own slot choice is sign-noise driven, so the comparison is
+    # with the `sel_*` golden: same reference sampler/estimator/loss/autograd, slot = genuine model
+    # closest to GT up to sign (tests/golden/make_golden.py).
+    assert torch.equal(valid[0].cpu(), g64["sel_keep"])
+    ref_models = g64["sel_models"]
     d = torch.minimum((chosen[0].detach().cpu() - ref_models).flatten(1).norm(dim=1),
                       (chosen[0].detach().cpu() + ref_models).flatten(1).norm(dim=1))
     same = d < 1e-3
-    assert same.float().mean() > 0.85
+    assert same.float().mean() >= 0.95
+    gl, rl, rl32 = logits.grad[0].cpu().double(), g64["sel_grad_logits"], g32["sel_grad_logits"].double()
+    gm, rm, rm32 = matches.grad[0].cpu().double(), g64["sel_grad_matches"], g32["sel_grad_matches"].double()
+    err_l, err_m = (gl - rl).norm() / rl.norm(), (gm - rm).norm() / rm.norm()
     if same.all():
-        assert abs(loss.item() - g64["loss"].item()) < 1e-4 * abs(g64["loss"].item())
-        gl, rl = logits.grad[0].cpu().double(), g64["grad_logits"]
-        assert (gl - rl).norm() / rl.norm() < 1e-3
-        gm, rm = matches.grad[0].cpu().double(), g64["grad_matches"]
-        assert (gm - rm).norm() / rm.norm() < 1e-3
-    # and in any case: closer to the fp64 reference than the fp32 reference is to it, within a factor
-    gl, rl, rl32 = logits.grad[0].cpu().double(), g64["grad_logits"], g32["grad_logits"].double()
-    err_ours = (gl - rl).norm() / rl.norm()
-    err_ref32 = (rl32 - rl).norm() / rl.norm()
-    assert err_ours < max(5e-2, 2 * err_ref32)
+        # identical model set: soft loss and gradients within 1e-4 relative of the fp64 reference
+        assert abs(loss.item() - g64["sel_loss"].item()) < 1e-4 * abs(g64["sel_loss"].item())
+        assert err_l < 1e-4 and err_m < 1e-4
+    # in any case: at least as close to the fp64 reference as the fp32 reference itself is
+    assert err_l < max(1e-4, 1.5 * (rl32 - rl).norm() / rl.norm())
+    assert err_m < max(1e-4, 1.5 * (rm32 - rm).norm() / rm.norm())
 
 
 def test_f8_train_step_gradients_vs_reference(drb, golden):
