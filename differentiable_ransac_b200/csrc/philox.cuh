@@ -33,11 +33,23 @@ DRB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
 // 23 random bits -> v in [2^-24, 1 - 2^-24] (both ends exactly representable), then
 // G = -log(-log v).  The clamp keeps the double logarithm finite when the fast
 // log2 rounds -log v to <= 0 next to v = 1.
+DRB_D float uniform_from_bits(uint32_t r) { return ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f; }
+
+#if defined(__CUDACC__)
+// raw SFU log2: every argument here is a normal number, so the denormal pre-scaling that
+// __logf / __log2f wrap around MUFU.LG2 is dead weight
+__device__ __forceinline__ float lg2_approx(float x) {
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+#endif
+
 DRB_D float gumbel_from_bits(uint32_t r) {
-    const float v = ((float)(r >> 9) + 0.5f) * 1.1920928955078125e-07f;
+    const float v = uniform_from_bits(r);
 #if defined(__CUDA_ARCH__)
-    const float e = fmaxf(-__logf(v), 1e-10f);
-    return -__logf(e);
+    const float e = fmaxf(-0.6931471805599453f * lg2_approx(v), 1e-10f);
+    return -0.6931471805599453f * lg2_approx(e);
 #else
     const float e = fmaxf(-logf(v), 1e-10f);
     return -logf(e);

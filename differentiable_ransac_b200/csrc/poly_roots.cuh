@@ -117,58 +117,75 @@ struct SturmChain10 {
         }
     }
 
-    // real roots in (-1, 1]; returns how many were written to out[0..max_out)
-    DRB_HD int roots_unit(T* out, int max_out) const {
-        const int n_lo = count(T(-1));
-        const int n_hi = count(T(1));
-        int nroots = n_lo - n_hi;
-        if (nroots <= 0) return 0;
-        if (nroots > max_out) nroots = max_out;
-        T start = T(-1);
-        int written = 0;
-        for (int r = 0; r < nroots; ++r) {
-            T lo = start, hi = T(1);
-            int clo = n_lo - r;  // by construction exactly r roots lie at or below `start`
-            int chi = n_hi;
-            clo = count(lo);
-            for (int it = 0; it < 48; ++it) {
-                if (clo - chi <= 1) break;
-                const T mid = T(0.5) * (lo + hi);
-                if (!(mid > lo) || !(mid < hi)) break;
-                const int cm = count(mid);
-                if (n_lo - cm >= r + 1) {
-                    hi = mid;
-                    chi = cm;
-                } else {
-                    lo = mid;
-                    clo = cm;
-                }
+    // Safeguarded Newton on p inside a bracket (lo, hi] that holds exactly one simple root.
+    DRB_HD T refine(T lo, T hi) const {
+        T flo, fhi, d;
+        eval(lo, flo, d);
+        eval(hi, fhi, d);
+        T z = T(0.5) * (lo + hi);
+        if ((flo < T(0)) == (fhi < T(0))) return z;  // no sign change (cluster / rounding): keep the midpoint
+        const T tol = T(4) * (sizeof(T) == 4 ? T(6e-8) : T(1.2e-16));
+        for (int it = 0; it < 24; ++it) {
+            T f, df;
+            eval(z, f, df);
+            if ((f < T(0)) == (flo < T(0))) {
+                lo = z;
+            } else {
+                hi = z;
             }
-            // (lo, hi] now holds root r (and possibly a cluster); refine on p itself
-            T flo, fhi, d;
-            eval(lo, flo, d);
-            eval(hi, fhi, d);
-            T z = T(0.5) * (lo + hi);
-            if ((flo < T(0)) != (fhi < T(0))) {
-                for (int it = 0; it < 40; ++it) {
-                    T f, df;
-                    eval(z, f, df);
-                    if ((f < T(0)) == (flo < T(0))) {
-                        lo = z;
-                    } else {
-                        hi = z;
-                    }
-                    T zn = z - f / df;
-                    if (!(zn > lo && zn < hi)) zn = T(0.5) * (lo + hi);
-                    const T dz = t_abs(zn - z);
-                    z = zn;
-                    if (dz <= T(4) * (sizeof(T) == 4 ? T(6e-8) : T(1.2e-16)) * t_max(t_abs(z), T(1e-3))) break;
-                }
-            }
-            out[written++] = z;
-            start = hi;
+            T zn = z - f / df;
+            if (!(zn > lo && zn < hi)) zn = T(0.5) * (lo + hi);
+            const T dz = t_abs(zn - z);
+            z = zn;
+            if (dz <= tol * t_max(t_abs(z), T(1e-3))) break;
         }
-        return written;
+        return z;
+    }
+
+    // Real roots in (-1, 1]; returns how many were written to out[0..max_out).
+    // Phase 1 -- the same work for every thread (no divergence inside a warp): Sturm counts on a
+    // fixed grid of kGrid cells.  Cells holding one root become brackets directly; a cell holding
+    // several is split by Sturm bisection (uncommon).  Phase 2 refines each bracket by Newton.
+    static constexpr int kGrid = 16;
+    DRB_HD int roots_unit(T* out, int max_out) const {
+        int c[kGrid + 1];
+        DRB_UNROLL
+        for (int i = 0; i <= kGrid; ++i) c[i] = count(T(-1) + T(2 * i) / T(kGrid));
+        T blo[10], bhi[10];
+        int nb = 0;
+        DRB_UNROLL
+        for (int i = 0; i < kGrid; ++i) {
+            const int n = c[i] - c[i + 1];
+            if (n <= 0) continue;
+            const T clo_x = T(-1) + T(2 * i) / T(kGrid), chi_x = T(-1) + T(2 * i + 2) / T(kGrid);
+            if (n == 1) {
+                if (nb < max_out) { blo[nb] = clo_x; bhi[nb] = chi_x; ++nb; }
+                continue;
+            }
+            // several roots in this cell: peel them off from the left by bisection on the count
+            T start = clo_x;
+            for (int r = 0; r < n && nb < max_out; ++r) {
+                T lo = start, hi = chi_x;
+                int clo = c[i] - r, chi = c[i + 1];
+                for (int it = 0; it < 40; ++it) {
+                    if (clo - chi <= 1) break;
+                    const T mid = T(0.5) * (lo + hi);
+                    if (!(mid > lo) || !(mid < hi)) break;
+                    const int cm = count(mid);
+                    if (c[i] - cm >= r + 1) {
+                        hi = mid;
+                        chi = cm;
+                    } else {
+                        lo = mid;
+                        clo = cm;
+                    }
+                }
+                blo[nb] = lo; bhi[nb] = hi; ++nb;
+                start = hi;
+            }
+        }
+        for (int r = 0; r < nb; ++r) out[r] = refine(blo[r], bhi[r]);
+        return nb;
     }
 };
 

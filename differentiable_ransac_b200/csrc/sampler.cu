@@ -56,9 +56,103 @@ __device__ __forceinline__ KeyQuad load_keys(const float* __restrict__ logits_b,
             if (n0 + i < N) noise_out_row[n0 + i] = g[i];
     }
     KeyQuad q;
-    DRB_UNROLL
-    for (int i = 0; i < 4; ++i) q.k[i] = (n0 + i < N) ? __fdiv_rn(__fadd_rn(l[i], g[i]), tau) : -INFINITY;
+    if (tau == 1.0f) {  // x / 1 == x exactly: skip the IEEE division (warp-uniform branch)
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) q.k[i] = (n0 + i < N) ? __fadd_rn(l[i], g[i]) : -INFINITY;
+    } else {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) q.k[i] = (n0 + i < N) ? __fdiv_rn(__fadd_rn(l[i], g[i]), tau) : -INFINITY;
+    }
     return q;
+}
+
+// Warp-shared running top-S (element j in lane j, descending).  `cand_v`/`cand_i` are this
+// lane's candidate; every lane whose candidate beats the S-th best is merged in.
+template <int S>
+__device__ __forceinline__ void merge_candidates(float cand_v, int cand_i, float& top_v, int& top_i, float& thr,
+                                                 int lane) {
+    const unsigned FULL = 0xffffffffu;
+    unsigned cand = __ballot_sync(FULL, cand_v > thr);
+    while (cand) {
+        const int src = __ffs(cand) - 1;
+        cand &= cand - 1;
+        const float cv = __shfl_sync(FULL, cand_v, src);
+        if (!(cv > thr)) continue;  // threshold moved since the ballot (warp-uniform)
+        const int ci = __shfl_sync(FULL, cand_i, src);
+        const float up_v = __shfl_up_sync(FULL, top_v, 1);
+        const int up_i = __shfl_up_sync(FULL, top_i, 1);
+        if (cv > top_v) {
+            if (lane > 0 && cv > up_v) {
+                top_v = up_v;
+                top_i = up_i;
+            } else {
+                top_v = cv;
+                top_i = ci;
+            }
+        }
+        thr = __shfl_sync(FULL, top_v, S - 1);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (no injected noise, no log-sum-exp wanted = test mode): the Gumbel-max trick as an
+// exponential race.  key = logit + G, G = -ln(-ln v)  <=>  rank by  log2(v) * exp(-logit)
+// (largest wins), which needs ONE SFU op per element instead of two logarithms and a division;
+// exp(-logit[n]) is tabulated once per CTA in shared memory.  tau > 0 does not change the
+// ranking.  Same Philox stream and the same v as the exact kernel, so both select the same
+// points (up to ties at the last ulp; tests/test_gpu_parity.py::test_sampler_race_equals_exact).
+constexpr int kRaceMaxN = 8192;
+
+template <int S>
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+sample_race_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
+                   int32_t* __restrict__ idx_out) {
+    __shared__ __align__(16) float winv[kRaceMaxN];
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * kSamplerWarps + warp;
+    const float* logits_b = logits + (size_t)b * N;
+    const int n_pad = ((N + 127) / 128) * 128;
+    for (int n = threadIdx.x; n < n_pad; n += blockDim.x)
+        winv[n] = n < N ? __expf(-__ldg(logits_b + n)) : INFINITY;  // lg2(v) < 0: padded entries rank -inf
+    __syncthreads();
+    if (k >= K) return;
+    const long long row = (long long)b * K + k;
+    float top_v = -INFINITY, thr = -INFINITY;
+    int top_i = -1;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+    for (int n0 = lane * 4; n0 < n_pad; n0 += 128) {
+        const Philox4 r = philox4x32_10((uint32_t)(n0 >> 2), (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
+        const float4 w = *reinterpret_cast<const float4*>(winv + n0);
+        float t[4];
+        t[0] = lg2_approx(uniform_from_bits(r.x)) * w.x;
+        t[1] = lg2_approx(uniform_from_bits(r.y)) * w.y;
+        t[2] = lg2_approx(uniform_from_bits(r.z)) * w.z;
+        t[3] = lg2_approx(uniform_from_bits(r.w)) * w.w;
+        // lane-local best of the four first: one ballot per iteration in the common case
+        float bv = t[0];
+        int bi = 0;
+        DRB_UNROLL
+        for (int i = 1; i < 4; ++i)
+            if (t[i] > bv) { bv = t[i]; bi = i; }
+        merge_candidates<S>(bv, n0 + bi, top_v, top_i, thr, lane);
+        // rare: another key of the same lane also beats the (updated) threshold
+        float second = -INFINITY;
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) second = (i == bi) ? second : fmaxf(second, t[i]);
+        if (__any_sync(0xffffffffu, second > thr)) {
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) merge_candidates<S>((i == bi) ? -INFINITY : t[i], n0 + i, top_v, top_i, thr, lane);
+        }
+    }
+    int rank = 0;
+    DRB_UNROLL
+    for (int j = 0; j < S; ++j) {
+        const int oj = __shfl_sync(0xffffffffu, top_i, j);
+        rank += (oj < top_i) ? 1 : 0;
+    }
+    if (lane < S) idx_out[(size_t)row * S + rank] = top_i;
 }
 
 template <int S>
@@ -104,27 +198,20 @@ sample_kernel(const float* __restrict__ logits, const float* __restrict__ noise,
                 run_s = s;
             }
         }
-        DRB_UNROLL
-        for (int i = 0; i < 4; ++i) {
-            unsigned cand = __ballot_sync(FULL, q.k[i] > thr);
-            while (cand) {
-                const int src = __ffs(cand) - 1;
-                cand &= cand - 1;
-                const float cv = __shfl_sync(FULL, q.k[i], src);
-                if (!(cv > thr)) continue;  // threshold moved since the ballot (warp-uniform)
-                const int ci = __shfl_sync(FULL, n0 + i, src);
-                const float up_v = __shfl_up_sync(FULL, top_v, 1);
-                const int up_i = __shfl_up_sync(FULL, top_i, 1);
-                if (cv > top_v) {
-                    if (lane > 0 && cv > up_v) {
-                        top_v = up_v;
-                        top_i = up_i;
-                    } else {
-                        top_v = cv;
-                        top_i = ci;
-                    }
-                }
-                thr = __shfl_sync(FULL, top_v, S - 1);
+        {
+            float bv = q.k[0];
+            int bi = 0;
+            DRB_UNROLL
+            for (int i = 1; i < 4; ++i)
+                if (q.k[i] > bv) { bv = q.k[i]; bi = i; }
+            merge_candidates<S>(bv, n0 + bi, top_v, top_i, thr, lane);
+            float second = -INFINITY;
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) second = (i == bi) ? second : fmaxf(second, q.k[i]);
+            if (__any_sync(FULL, second > thr)) {
+                DRB_UNROLL
+                for (int i = 0; i < 4; ++i)
+                    merge_candidates<S>((i == bi) ? -INFINITY : q.k[i], n0 + i, top_v, top_i, thr, lane);
             }
         }
     }
@@ -224,6 +311,24 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     const long long rows = (long long)B * K;
     const unsigned grid = (unsigned)((rows + kSamplerWarps - 1) / kSamplerWarps);
     const dim3 block(kSamplerWarps * 32);
+    if (!noise && !lse && !sel_key && !noise_out && N <= kRaceMaxN && B <= 65535) {
+        // test mode: only the indices are wanted -> exponential-race fast path
+        const dim3 rgrid((K + kSamplerWarps - 1) / kSamplerWarps, B);
+#define DRB_LAUNCH_RACE(S_)                                                                   \
+    case S_:                                                                                  \
+        sample_race_kernel<S_><<<rgrid, block, 0, st>>>(logits, seed, offset, K, N, idx);     \
+        break;
+        switch (s) {
+            DRB_LAUNCH_RACE(3)
+            DRB_LAUNCH_RACE(5)
+            DRB_LAUNCH_RACE(7)
+            DRB_LAUNCH_RACE(8)
+            default:
+                return DRB_ERR_UNSUPPORTED;
+        }
+#undef DRB_LAUNCH_RACE
+        return check_launch();
+    }
 #define DRB_LAUNCH_SAMPLE(S_)                                                                                   \
     case S_:                                                                                                    \
         sample_kernel<S_><<<grid, block, 0, st>>>(logits, noise, seed, offset, tau, B, K, N, idx, lse, sel_key, \

@@ -12,6 +12,7 @@
 
 #include "../../include/drb.h"
 #include "drb_common.cuh"
+#include "f32x2.cuh"
 #include "tile_pipe.cuh"
 
 namespace drb {
@@ -66,31 +67,60 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     const float inv_thr2 = 1.f / (t * t);
     float acc0 = 0.f, acc1 = 0.f;
 
+    // model coefficients as packed broadcast operands (ptxas folds the splat into the FFMA2
+    // scalar-broadcast operand form, so these cost no extra registers)
+    pk2 mp[9];
+    DRB_UNROLL
+    for (int i = 0; i < 9; ++i) mp[i] = pk2_splat(m[i]);
+    const pk2 neg_inv = pk2_splat(-inv_thr2), one = pk2_splat(1.f);
+    pk2 acc = pk2_splat(0.f);
+
     TilePipe<4, kTile> pipe(tiles, bars, matches + (size_t)b * N * 4, N);
     pipe.prologue();
     for (int tI = 0; tI < pipe.n_tiles; ++tI) {
-        const float4* tile = reinterpret_cast<const float4*>(pipe.acquire(tI));
+        float4* tile = reinterpret_cast<float4*>(const_cast<float*>(pipe.acquire(tI)));
         const int np = pipe.tile_items(tI);
+        const int npairs = np >> 1;
+        // interleave each pair of correspondences in place:
+        // (x1p y1p x2p y2p | x1q y1q x2q y2q) -> (x1p x1q y1p y1q | x2p x2q y2p y2q)
+        for (int i = threadIdx.x; i < npairs; i += kScoreThreads) {
+            const float4 p = tile[2 * i], q = tile[2 * i + 1];
+            tile[2 * i] = make_float4(p.x, q.x, p.y, q.y);
+            tile[2 * i + 1] = make_float4(p.z, q.z, p.w, q.w);
+        }
+        __syncthreads();
         if (active) {
-            int i = 0;
+            const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tile);
 #pragma unroll 2
-            for (; i + 1 < np; i += 2) {
-                const float4 p = tile[i];
-                const float4 q = tile[i + 1];
-                const Sampson a = sampson(m, p.x, p.y, p.z, p.w);
-                const Sampson c = sampson(m, q.x, q.y, q.z, q.w);
-                const float da = __fdividef(a.r * a.r, a.j);
-                const float dc = __fdividef(c.r * c.r, c.j);
-                acc0 += fmaxf(fmaf(-da, inv_thr2, 1.f), 0.f);
-                acc1 += fmaxf(fmaf(-dc, inv_thr2, 1.f), 0.f);
+            for (int i = 0; i < npairs; ++i) {
+                const ulonglong2 a1 = t2[2 * i], a2 = t2[2 * i + 1];
+                const pk2 X1 = a1.x, Y1 = a1.y, X2 = a2.x, Y2 = a2.y;
+                const pk2 E0 = pk2_fma(mp[0], X1, pk2_fma(mp[1], Y1, mp[2]));
+                const pk2 E1 = pk2_fma(mp[3], X1, pk2_fma(mp[4], Y1, mp[5]));
+                const pk2 E2 = pk2_fma(mp[6], X1, pk2_fma(mp[7], Y1, mp[8]));
+                const pk2 F0 = pk2_fma(mp[0], X2, pk2_fma(mp[3], Y2, mp[6]));
+                const pk2 F1 = pk2_fma(mp[1], X2, pk2_fma(mp[4], Y2, mp[7]));
+                const pk2 R = pk2_fma(X2, E0, pk2_fma(Y2, E1, E2));
+                const pk2 J = pk2_fma(E0, E0, pk2_fma(E1, E1, pk2_fma(F0, F0, pk2_mul(F1, F1))));
+                float jl, jh;
+                pk2_split(J, jl, jh);
+                const pk2 U = pk2_mul(pk2_mul(R, R), pk2_make(rcp_approx(jl), rcp_approx(jh)));
+                float tl, th;
+                pk2_split(pk2_fma(U, neg_inv, one), tl, th);
+                acc = pk2_add(acc, pk2_make(fmaxf(tl, 0.f), fmaxf(th, 0.f)));
             }
-            if (i < np) {
-                const float4 p = tile[i];
+            if (np & 1) {  // odd tail of the last tile (never interleaved)
+                const float4 p = tile[np - 1];
                 const Sampson a = sampson(m, p.x, p.y, p.z, p.w);
-                acc0 += fmaxf(fmaf(-__fdividef(a.r * a.r, a.j), inv_thr2, 1.f), 0.f);
+                acc0 += fmaxf(fmaf(-(a.r * a.r) * rcp_approx(a.j), inv_thr2, 1.f), 0.f);
             }
         }
         pipe.release(tI);
+    }
+    {
+        float lo, hi;
+        pk2_split(acc, lo, hi);
+        acc1 = lo + hi;
     }
     const float score = acc0 + acc1;
     if (active && scores) scores[(size_t)b * M + mi] = score;
@@ -198,7 +228,7 @@ episym_kernel(const float* __restrict__ pts, const int32_t* __restrict__ npts, c
                 const float r = fmaf(x2, e0, fmaf(y2, e1, e2));
                 const float a = fmaf(e0, e0, e1 * e1) + eps;
                 const float c = fmaf(f0, f0, f1 * f1) + eps;
-                const float ia = __frcp_rn(a), ic = __frcp_rn(c);
+                const float ia = rcp_approx(a), ic = rcp_approx(c);
                 const float w = ia + ic;
                 const float ys = r * r * w;
                 if (!BWD) {

@@ -72,6 +72,33 @@ def test_sampler_philox_replay_and_statistics(drb):
     assert torch.equal(idx, idx3)                                             # deterministic
 
 
+def test_sampler_race_equals_exact(drb):
+    """Test mode uses the exponential-race fast path (one SFU op per element); it must pick the same
+    points as the exact key = (logit + G) / tau path that the oracle replays, on the same Philox stream."""
+    for s, N, K, regime in ((5, 2000, 1000, "L0"), (8, 2000, 512, "L1"), (3, 4100, 64, "L1"), (7, 333, 100, "L0")):
+        B = 4
+        logits = drb.synth.logits_regime(B, N, regime, seed=s).to(DEV)
+        fast, _, _, _ = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3)
+        exact, _, _, _ = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3, want_lse=True)
+        same_rows = (fast == exact).all(dim=-1).float().mean().item()
+        assert same_rows >= 0.999, (s, N, K, same_rows)
+        assert (fast[..., 1:] > fast[..., :-1]).all()          # ascending, distinct
+        assert int(fast.min()) >= 0 and int(fast.max()) < N
+
+
+def test_sampler_follows_the_weights(drb):
+    """Gumbel-max sampling draws the first pick with probability softmax(logits): empirical
+    inclusion frequencies over many hypotheses follow the weights (fast path)."""
+    B, N, K, s = 1, 64, 20000, 3
+    logits = torch.linspace(-2.0, 2.0, N)[None]
+    idx, _, _, _ = drb.ops.sample(logits.to(DEV), K, s, 1.0, seed=5, offset=0)
+    counts = torch.bincount(idx.flatten().cpu().long(), minlength=N).double()
+    # inclusion probability is monotone in the logit; compare halves and the rank correlation
+    assert counts[N // 2:].sum() > 2.5 * counts[: N // 2].sum()
+    r = torch.corrcoef(torch.stack((counts, torch.softmax(logits[0].double(), 0))))[0, 1]
+    assert r > 0.98
+
+
 # ---- a3 five-point ---------------------------------------------------------------------------------
 def _e5_match_stats(models, nsol, ref64):
     K = ref64.shape[0] // 10
@@ -311,7 +338,8 @@ def test_rigid_train_step_vs_reference(drb, golden):
     noise = g["noise"].reshape(1, 64, -1).to(DEV)
     models, valid = drb.engine.HypothesizeRigid.apply(points, logits, 64, True, 1.0, noise, 0, 0)
     assert valid.all()
-    assert torch.allclose(models[0].detach().cpu(), g["models"], atol=5e-4, rtol=1e-4)
+    # flag=True: the reference's R is I + fp32 SVD noise, times centroids of size ~10
+    assert torch.allclose(models[0].detach().cpu(), g["models"], atol=5e-3, rtol=1e-4)
     res = drb.engine.RigidResidual.apply(points, models)
     assert torch.allclose(res[0].detach().cpu(), g["residuals"], rtol=2e-3)
     loss = res.mean()
@@ -345,7 +373,9 @@ def test_headline_shape_properties(drb):
         s, m = scoring.msac_score(matches[bi], a["best_model"][bi].cpu()[None], float(thr[bi]))
         assert abs(s[0].item() - a["best_score"][bi].item()) < 1e-3 * max(1.0, s[0].item())
         assert abs(int(m.sum()) - int(a["ninl"][bi])) <= 2
-    # noise-free synthetic pairs: the winner is the true essential matrix
+    # noise-free synthetic pairs: the winner is the true essential matrix wherever 1000 draws contain an
+    # all-inlier sample with near certainty (inlier ratio >= 0.4; at 0.2, 0.2^5 * 1000 = 0.3 such samples)
     bm = a["best_model"].cpu()
     err = torch.minimum((bm - E_gt).flatten(1).norm(dim=1), (bm + E_gt).flatten(1).norm(dim=1))
-    assert (err < 1e-2).float().mean() > 0.9
+    easy = torch.arange(B) % 3 != 0
+    assert (err[easy] < 1e-2).float().mean() > 0.9
