@@ -15,13 +15,18 @@ DRB_HD Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
     const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
     DRB_UNROLL
     for (int r = 0; r < 10; ++r) {
+#if defined(__CUDA_ARCH__)
+        uint32_t lo0, hi0, lo1, hi1;
+        asm("{.reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(lo0), "=r"(hi0) : "r"(M0), "r"(c0));
+        asm("{.reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%0, %1}, t;}" : "=r"(lo1), "=r"(hi1) : "r"(M1), "r"(c2));
+#else
         const uint64_t p0 = (uint64_t)M0 * c0;
         const uint64_t p1 = (uint64_t)M1 * c2;
-        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
-        const uint32_t n1 = (uint32_t)p1;
-        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
-        const uint32_t n3 = (uint32_t)p0;
-        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        const uint32_t lo0 = (uint32_t)p0, hi0 = (uint32_t)(p0 >> 32), lo1 = (uint32_t)p1, hi1 = (uint32_t)(p1 >> 32);
+#endif
+        const uint32_t n0 = hi1 ^ c1 ^ k0;
+        const uint32_t n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
         k0 += W0;
         k1 += W1;
     }

@@ -148,41 +148,59 @@ struct SturmChain10 {
     // several is split by Sturm bisection (uncommon).  Phase 2 refines each bracket by Newton.
     static constexpr int kGrid = 16;
     DRB_HD int roots_unit(T* out, int max_out) const {
-        int c[kGrid + 1];
-        DRB_UNROLL
-        for (int i = 0; i <= kGrid; ++i) c[i] = count(T(-1) + T(2 * i) / T(kGrid));
+        // roots per cell, 4 bits each (a cell holds at most 10); rolled loops keep the code small --
+        // this routine is instruction-cache bound when unrolled
+        unsigned long long cells = 0ull;
+        const int c_first = count(T(-1));
+        {
+            int prev = c_first;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+            for (int i = 1; i <= kGrid; ++i) {
+                const int cur = count(T(-1) + T(2 * i) / T(kGrid));
+                int n = prev - cur;
+                n = n < 0 ? 0 : (n > 15 ? 15 : n);
+                cells |= (unsigned long long)n << (4 * (i - 1));
+                prev = cur;
+            }
+        }
         T blo[10], bhi[10];
         int nb = 0;
-        DRB_UNROLL
+        int c_left = c_first;  // Sturm count at the left edge of the current cell
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
         for (int i = 0; i < kGrid; ++i) {
-            const int n = c[i] - c[i + 1];
-            if (n <= 0) continue;
+            const int n = (int)((cells >> (4 * i)) & 15ull);
+            if (n == 0) continue;
             const T clo_x = T(-1) + T(2 * i) / T(kGrid), chi_x = T(-1) + T(2 * i + 2) / T(kGrid);
             if (n == 1) {
                 if (nb < max_out) { blo[nb] = clo_x; bhi[nb] = chi_x; ++nb; }
-                continue;
-            }
-            // several roots in this cell: peel them off from the left by bisection on the count
-            T start = clo_x;
-            for (int r = 0; r < n && nb < max_out; ++r) {
-                T lo = start, hi = chi_x;
-                int clo = c[i] - r, chi = c[i + 1];
-                for (int it = 0; it < 40; ++it) {
-                    if (clo - chi <= 1) break;
-                    const T mid = T(0.5) * (lo + hi);
-                    if (!(mid > lo) || !(mid < hi)) break;
-                    const int cm = count(mid);
-                    if (c[i] - cm >= r + 1) {
-                        hi = mid;
-                        chi = cm;
-                    } else {
-                        lo = mid;
-                        clo = cm;
+            } else {
+                // several roots in this cell: peel them off from the left by bisection on the count
+                T start = clo_x;
+                for (int r = 0; r < n && nb < max_out; ++r) {
+                    T lo = start, hi = chi_x;
+                    int clo = c_left - r, chi = c_left - n;
+                    for (int it = 0; it < 40; ++it) {
+                        if (clo - chi <= 1) break;
+                        const T mid = T(0.5) * (lo + hi);
+                        if (!(mid > lo) || !(mid < hi)) break;
+                        const int cm = count(mid);
+                        if (c_left - cm >= r + 1) {
+                            hi = mid;
+                            chi = cm;
+                        } else {
+                            lo = mid;
+                            clo = cm;
+                        }
                     }
+                    blo[nb] = lo; bhi[nb] = hi; ++nb;
+                    start = hi;
                 }
-                blo[nb] = lo; bhi[nb] = hi; ++nb;
-                start = hi;
             }
+            c_left -= n;
         }
         for (int r = 0; r < nb; ++r) out[r] = refine(blo[r], bhi[r]);
         return nb;
@@ -193,22 +211,26 @@ struct SturmChain10 {
 template <class T>
 DRB_HD int real_roots_deg10(const T* coef, T* roots) {
     int n = 0;
-    {
-        SturmChain10<T> s;
-        s.build(coef);
-        n = s.roots_unit(roots, 10);
-    }
-    {
-        T rev[11];
+    // domain 0: z in (-1, 1] on p;  domain 1: w = 1/z in (-1, 1) on the reversed polynomial.
+    // One rolled loop so that the chain builder / root isolation exist once in the binary.
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int dom = 0; dom < 2; ++dom) {
+        T c[11];
         DRB_UNROLL
-        for (int i = 0; i <= 10; ++i) rev[i] = coef[10 - i];
+        for (int i = 0; i <= 10; ++i) c[i] = dom ? coef[10 - i] : coef[i];
         SturmChain10<T> s;
-        s.build(rev);
+        s.build(c);
         T w[10];
         const int nw = s.roots_unit(w, 10 - n);
         for (int i = 0; i < nw; ++i) {
-            const T aw = t_abs(w[i]);
-            if (aw < T(1) && aw > T(1e-7) && n < 10) roots[n++] = T(1) / w[i];
+            if (dom == 0) {
+                if (n < 10) roots[n++] = w[i];
+            } else {
+                const T aw = t_abs(w[i]);
+                if (aw < T(1) && aw > T(1e-7) && n < 10) roots[n++] = T(1) / w[i];
+            }
         }
     }
     return n;

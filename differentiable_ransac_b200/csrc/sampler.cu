@@ -136,7 +136,24 @@ sample_race_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
         DRB_UNROLL
         for (int i = 1; i < 4; ++i)
             if (t[i] > bv) { bv = t[i]; bi = i; }
-        merge_candidates<S>(bv, n0 + bi, top_v, top_i, thr, lane);
+        if (n0 < 128) {
+            // first sweep: the list is empty, so every lane would be a candidate.  Take the S best
+            // of the 32 lane-maxima by S rounds of warp arg-max instead (straight-line code).
+            float cur = bv;
+            DRB_UNROLL
+            for (int j = 0; j < S; ++j) {
+                float m = cur;
+                DRB_UNROLL
+                for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const int owner = __ffs(__ballot_sync(0xffffffffu, cur == m)) - 1;
+                const int mi = __shfl_sync(0xffffffffu, n0 + bi, owner);
+                if (lane == j) { top_v = m; top_i = mi; }
+                if (lane == owner) cur = -INFINITY;
+            }
+            thr = __shfl_sync(0xffffffffu, top_v, S - 1);
+        } else {
+            merge_candidates<S>(bv, n0 + bi, top_v, top_i, thr, lane);
+        }
         // rare: another key of the same lane also beats the (updated) threshold
         float second = -INFINITY;
         DRB_UNROLL

@@ -17,8 +17,10 @@
 
 namespace drb {
 
-constexpr int kScoreThreads = 128;
-constexpr int kTile = 1024;       // 2-D correspondences (16 B) per stage
+// Small CTAs (2 warps, 16 KB of tiles): ~2200 live CTAs at the headline shape spread evenly over
+// 148 SMs x 14 resident CTAs, instead of 1.24 waves of large ones (profiles/r1_notes.md).
+constexpr int kScoreThreads = 64;
+constexpr int kTile = 512;        // 2-D correspondences (16 B) per stage
 constexpr int kTileRigid = 768;   // 3-D correspondences (24 B) per stage
 
 __device__ __forceinline__ unsigned long long pack_best(float score, int id) {
