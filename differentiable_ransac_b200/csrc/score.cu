@@ -17,10 +17,12 @@
 
 namespace drb {
 
-// Small CTAs (2 warps, 16 KB of tiles): ~2200 live CTAs at the headline shape spread evenly over
-// 148 SMs x 14 resident CTAs, instead of 1.24 waves of large ones (profiles/r1_notes.md).
-constexpr int kScoreThreads = 64;
-constexpr int kTile = 512;        // 2-D correspondences (16 B) per stage
+constexpr int kScoreThreads = 128;   // episym / rigid kernels: models per CTA
+constexpr int kTile = 1024;       // 2-D correspondences (16 B) per stage (episym)
+// MSAC: ONE WARP per CTA, 32 models, 6 KB of tiles -> up to 32 CTAs per SM, so the ~4300 live CTAs of
+// the headline shape are all resident at once (no second wave, no tail); see profiles/r1_notes.md.
+constexpr int kMsacThreads = 32;
+constexpr int kMsacTile = 192;
 constexpr int kTileRigid = 768;   // 3-D correspondences (24 B) per stage
 
 __device__ __forceinline__ unsigned long long pack_best(float score, int id) {
@@ -46,16 +48,18 @@ __device__ __forceinline__ Sampson sampson(const float* m, float x1, float y1, f
     return s;
 }
 
-__global__ void __launch_bounds__(kScoreThreads)
+__global__ void __launch_bounds__(kMsacThreads)
 score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ models,
                   const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
                   int M, int N, float* __restrict__ scores, unsigned long long* __restrict__ best_packed) {
-    __shared__ __align__(128) float tiles[2 * kTile * 4];
+    __shared__ __align__(128) float tiles[2 * kMsacTile * 4];
     __shared__ __align__(8) uint64_t bars[2];
-    __shared__ unsigned long long warp_best[kScoreThreads / 32];
-    const int b = blockIdx.y;
+    __shared__ unsigned long long warp_best[kMsacThreads / 32];
+    // blockIdx.x = pair (fastest in dispatch order), blockIdx.y = model block: the live CTAs of every
+    // pair are dispatched before the empty tail of the worst-case grid
+    const int b = blockIdx.x;
     const int cnt = count ? min(count[b], M) : M;
-    const int m0 = blockIdx.x * kScoreThreads;
+    const int m0 = blockIdx.y * kMsacThreads;
     if (m0 >= cnt) return;  // whole CTA leaves before any barrier
     const int mi = m0 + threadIdx.x;
     const bool active = mi < cnt;
@@ -77,7 +81,7 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     const pk2 neg_inv = pk2_splat(-inv_thr2), one = pk2_splat(1.f);
     pk2 acc = pk2_splat(0.f);
 
-    TilePipe<4, kTile> pipe(tiles, bars, matches + (size_t)b * N * 4, N);
+    TilePipe<4, kMsacTile> pipe(tiles, bars, matches + (size_t)b * N * 4, N);
     pipe.prologue();
     for (int tI = 0; tI < pipe.n_tiles; ++tI) {
         float4* tile = reinterpret_cast<float4*>(const_cast<float*>(pipe.acquire(tI)));
@@ -85,7 +89,7 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
         const int npairs = np >> 1;
         // interleave each pair of correspondences in place:
         // (x1p y1p x2p y2p | x1q y1q x2q y2q) -> (x1p x1q y1p y1q | x2p x2q y2p y2q)
-        for (int i = threadIdx.x; i < npairs; i += kScoreThreads) {
+        for (int i = threadIdx.x; i < npairs; i += kMsacThreads) {
             const float4 p = tile[2 * i], q = tile[2 * i + 1];
             tile[2 * i] = make_float4(p.x, q.x, p.y, q.y);
             tile[2 * i + 1] = make_float4(p.z, q.z, p.w, q.w);
@@ -136,7 +140,7 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     __syncthreads();
     if (threadIdx.x == 0) {
         DRB_UNROLL
-        for (int w = 1; w < kScoreThreads / 32; ++w) key = warp_best[w] > key ? warp_best[w] : key;
+        for (int w = 1; w < kMsacThreads / 32; ++w) key = warp_best[w] > key ? warp_best[w] : key;
         if (key) atomicMax(best_packed + b, key);
     }
 }
@@ -362,10 +366,10 @@ extern "C" int drb_score_msac(const float* matches, const float* models, const i
                               const float* thr, int B, int M, int N, float* scores,
                               unsigned long long* best_packed, void* stream) {
     if (!matches || !models || !thr || !best_packed) return DRB_ERR_NULL_POINTER;
-    if (B <= 0 || M <= 0 || N <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
-    dim3 grid((M + kScoreThreads - 1) / kScoreThreads, B);
-    score_msac_kernel<<<grid, kScoreThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N, scores,
-                                                                        best_packed);
+    if (B <= 0 || M <= 0 || N <= 0 || (M + kMsacThreads - 1) / kMsacThreads > 65535) return DRB_ERR_BAD_SHAPE;
+    dim3 grid(B, (M + kMsacThreads - 1) / kMsacThreads);
+    score_msac_kernel<<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N, scores,
+                                                                       best_packed);
     DRB_CHECK_LAUNCH();
 }
 

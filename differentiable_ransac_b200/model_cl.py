@@ -1,0 +1,119 @@
+"""RANSACLayer / RANSACLayer3D / batch_episym -- host mirror of `model_cl.py:13-26, 160-256, 516-595`.
+
+The nn.Module shells read the reference's `opt` namespace unchanged (`utils.py:7-83`); optional
+engine knobs (`opt.seed`, `opt.adaptive`) default to the reference's behaviour.
+`RANSACLayer.forward_batched` is the B-pairs-at-once entry that replaces the python loop of
+`DeepRansac_CLNet.forward` (`model_cl.py:488-510`)."""
+from __future__ import annotations
+
+import time
+
+import torch
+import torch.nn as nn
+
+from . import engine
+from .estimators.essential_matrix_estimator_nister import EssentialMatrixEstimatorNister
+from .estimators.fundamental_matrix_estimator import FundamentalMatrixEstimatorNew
+from .estimators.rigid_transformation_SVD_based_solver import RigidTransformationSVDBasedSolver
+from .loss import denormalize_pts
+from .ransac import RANSAC, RANSAC3D, normalized_threshold
+from .samplers.gumbel_sampler import GumbelSoftmaxSampler
+from .scorings.msac_score import MSACScore
+
+
+def batch_episym(x1, x2, F):
+    """model_cl.py:13-26: x1, x2 [K,P,2] (the same P points for every model), F [K,3,3] -> [K,P].
+    Unclamped distances; computed with torch ops (the fused, clamped, reduced version that the
+    training loss uses is engine.EpisymLoss)."""
+    one = x1.new_ones(*x1.shape[:2], 1)
+    h1, h2 = torch.cat((x1, one), -1), torch.cat((x2, one), -1)
+    Fx1 = torch.einsum("kij,kpj->kpi", F, h1)
+    Ftx2 = torch.einsum("kji,kpj->kpi", F, h2)
+    r = (h2 * Fx1).sum(-1)
+    return r ** 2 * (1.0 / (Fx1[..., 0] ** 2 + Fx1[..., 1] ** 2 + 1e-15) + 1.0 / (Ftx2[..., 0] ** 2 + Ftx2[..., 1] ** 2 + 1e-15))
+
+
+def _dtype(opt):
+    return {2: torch.float64, 0: torch.float16}.get(getattr(opt, "precision", 1), torch.float32)
+
+
+class RANSACLayer(nn.Module):
+    def __init__(self, opt, **kwargs):
+        super().__init__(**kwargs)
+        self.opt = opt
+        solver = FundamentalMatrixEstimatorNew(opt.device, opt.weighted) if opt.fmat else EssentialMatrixEstimatorNister(opt.device)
+        if opt.sampler in (0, 1):
+            raise NotImplementedError("sampler ids 0/1 cannot run through the reference driver either (SURVEY 2.1 #5)")
+        s = solver.sample_size if opt.sampler == 2 else 8
+        sampler = GumbelSoftmaxSampler(opt.ransac_batch_size, s, device=opt.device, data_type=_dtype(opt),
+                                       seed=getattr(opt, "seed", 0))
+        if opt.fmat:
+            max_iters = 1000 if opt.tr else 5000            # model_cl.py:213-219
+        else:
+            max_iters = 100 if opt.tr else 5000
+        self.estimator = RANSAC(solver, sampler, MSACScore(opt.device), max_iterations=max_iters, fmat=opt.fmat,
+                                train=opt.tr, ransac_batch_size=opt.ransac_batch_size, sampler_id=opt.sampler,
+                                weighted=opt.weighted, threshold=opt.threshold,
+                                adaptive=getattr(opt, "adaptive", True))
+
+    def _points(self, points, im_size1, im_size2):
+        pts = points.clone()
+        if self.opt.fmat:
+            pts[..., 0:2] = denormalize_pts(points[..., 0:2].clone(), im_size1)
+            pts[..., 2:4] = denormalize_pts(points[..., 2:4].clone(), im_size2)
+        return pts
+
+    def forward(self, points, weights, K1, K2, im_size1, im_size2, ground_truth=None):
+        pts = self._points(points, im_size1, im_size2)
+        torch.cuda.synchronize()
+        t0 = time.time()
+        models, _, _, _ = self.estimator(pts, weights.reshape(-1), K1, K2, ground_truth)
+        torch.cuda.synchronize()
+        dt = time.time() - t0
+        Es = torch.cat(list(models.values())) if self.opt.tr else models
+        if Es.dim() == 3:
+            Es = Es[~torch.isnan(Es).flatten(1).any(1)]
+        return Es, dt
+
+    def forward_batched(self, points, weights, K1, K2, im_size1=None, im_size2=None, ground_truth=None, K=None):
+        """points [B,N,4], weights [B,N], K1/K2 [B,3,3] -> list_B[Es_b] (train: [K_b,3,3]; test: [3,3]),
+        with ONE launch per stage for the whole batch."""
+        B = points.shape[0]
+        pts = points
+        if self.opt.fmat:
+            pts = torch.stack([self._points(points[b], im_size1[b], im_size2[b]) for b in range(B)])
+        drv = self.estimator
+        smp = drv.sampler
+        if self.opt.tr:
+            Kt = K or drv._chunks() * drv.ransac_batch_size
+            if smp.num_samples == 8:
+                models, valid = engine.HypothesizeF8.apply(pts, weights, Kt, smp.tau, None, smp.seed, smp._next_offset())
+            else:
+                models, valid = engine.HypothesizeE5.apply(pts, weights, ground_truth.float(), Kt, smp.tau, None,
+                                                           smp.seed, smp._next_offset(), True)
+            return [models[b][valid[b]] for b in range(B)]
+        thr = torch.tensor([normalized_threshold(drv.threshold, K1[b], K2[b], drv.fmat) for b in range(B)],
+                           device=points.device)
+        out = drv.batched_test(pts, weights, thr, K)
+        return [out["best_model"][b] for b in range(B)]
+
+
+class RANSACLayer3D(nn.Module):
+    def __init__(self, opt, **kwargs):
+        super().__init__(**kwargs)
+        self.opt = opt
+        solver = RigidTransformationSVDBasedSolver()
+        sampler = GumbelSoftmaxSampler(opt.ransac_batch_size, 3 if opt.sampler != 3 else 8, device=opt.device,
+                                       data_type=_dtype(opt), seed=getattr(opt, "seed", 0))
+        self.estimator = RANSAC3D(solver, sampler, MSACScore(opt.device), max_iterations=1000, fmat=opt.fmat,
+                                  train=opt.tr, ransac_batch_size=opt.ransac_batch_size, sampler_id=opt.sampler,
+                                  weighted=opt.weighted, threshold=opt.threshold)
+
+    def forward(self, points, weights, ground_truth=None):
+        t0 = time.time()
+        models, residuals, avg_residuals, _, _ = self.estimator(points, weights.reshape(-1), ground_truth)
+        dt = time.time() - t0
+        Es = torch.cat(list(models.values()))
+        loss = torch.cat(list(residuals.values()))
+        avg = sum(avg_residuals.values()) / len(avg_residuals)
+        return Es, loss.mean(), avg, dt

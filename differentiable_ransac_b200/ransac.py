@@ -1,0 +1,158 @@
+"""RANSAC / RANSAC3D -- host mirror of the reference drivers (`ransac.py:6-200`, `:303-450`).
+
+Same constructor, same `__call__` signature and return tuple.  Inside, the reference's
+`while iterations < max_iters` loop of torch ops is replaced by launches of the CUDA path:
+every chunk is one `sample -> solve -> score -> arg-max` pass for `ransac_batch_size`
+hypotheses (test mode), or ONE pass for all chunks at once (train mode, where nothing
+depends on the previous chunk).  `batched_call` does the same for B pairs in one go.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from . import engine, ops
+from .estimators.fundamental_matrix_estimator import normalized_eight_point_torch
+
+
+def normalized_threshold(threshold, K1, K2, fmat):
+    """ransac.py:49-53, including the K1[0,0]-twice quirk."""
+    if fmat:
+        return float(threshold)
+    return float(threshold) / float((K1[0, 0] + K1[1, 1] + K1[0, 0] + K2[1, 1]) / 4)
+
+
+class RANSAC(object):
+    def __init__(self, estimator, sampler, scoring, fmat=False, train=False, ransac_batch_size=64, sampler_id=0,
+                 weighted=0, threshold=1e-3, confidence=0.999, max_iterations=5000, lo=0, lo_iters=64, eps=1e-5,
+                 adaptive=True, final_refit=True):
+        self.estimator, self.sampler, self.scoring = estimator, sampler, scoring
+        self.lo, self.lo_iters = lo, lo_iters
+        self.fmat, self.train = fmat, train
+        self.ransac_batch_size = ransac_batch_size
+        self.sampler_id = sampler_id
+        self.weighted = weighted
+        self.threshold = threshold
+        self.confidence = confidence
+        self.max_iterations = max_iterations
+        self.eps = eps
+        self.adaptive = adaptive          # reference behaviour: early exit by inlier count (one host sync per chunk)
+        self.final_refit = final_refit
+        if sampler_id not in (2, 3):
+            raise NotImplementedError("only the Gumbel samplers (ids 2, 3) run in the reference (SURVEY 2.1 #5)")
+
+    # -- helpers -------------------------------------------------------------------------------
+    @property
+    def sample_size(self):
+        return self.sampler.num_samples
+
+    def _chunks(self):
+        return int(math.ceil(self.max_iterations / self.ransac_batch_size))
+
+    def adaptive_iteration_number(self, inlier_number, point_number, confidence):
+        """ransac.py:202-215."""
+        inlier_ratio = float(inlier_number) / point_number
+        probability = 1.0 - inlier_ratio ** self.estimator.sample_size
+        if probability >= 1.0 - self.eps:
+            return self.max_iterations
+        return max(0.0, math.log10(1.0 - confidence) / math.log10(1 - inlier_ratio ** self.estimator.sample_size + self.eps))
+
+    # -- the driver ------------------------------------------------------------------------------
+    def __call__(self, matches, logits, K1, K2, gt_model):
+        threshold = normalized_threshold(self.threshold, K1, K2, self.fmat)
+        if self.train:
+            return self._train(matches, logits, gt_model)
+        return self._test(matches, logits, threshold)
+
+    def _train(self, matches, logits, gt_model):
+        """ransac.py:78-108: every chunk's chosen models, NaN-free, keyed by the iteration count."""
+        rbs = self.ransac_batch_size
+        K = self._chunks() * rbs
+        noise = self.sampler.injected_noise
+        if noise is not None:
+            noise = noise.reshape(1, -1, noise.shape[-1])
+        seed, off = self.sampler.seed, self.sampler._next_offset()
+        m, lg = matches[None], logits[None]
+        if self.sample_size == 8:
+            models, valid = engine.HypothesizeF8.apply(m, lg, K, self.sampler.tau, noise, seed, off)
+        elif self.sample_size == 5:
+            models, valid = engine.HypothesizeE5.apply(m, lg, gt_model[None].float(), K, self.sampler.tau, noise, seed,
+                                                       off, True)
+        else:
+            raise NotImplementedError("train mode supports the 5-point and the 8-point samplers")
+        out = {}
+        for c in range(self._chunks()):
+            sl = slice(c * rbs, (c + 1) * rbs)
+            out[c * rbs] = models[0, sl][valid[0, sl]]
+        return out, [], 0, K
+
+    def _test(self, matches, logits, threshold):
+        rbs = self.ransac_batch_size
+        dev = matches.device
+        thr = torch.tensor([threshold], device=dev, dtype=torch.float32)
+        N = matches.shape[0]
+        m, lg = matches[None].float(), logits[None].float()
+        best = None
+        iterations, max_iters = 0, self.max_iterations
+        noise = self.sampler.injected_noise
+        chunk = 0
+        while iterations < max_iters:
+            nz = None
+            if noise is not None:
+                nz = noise.reshape(-1, rbs, noise.shape[-1])[chunk][None]
+            run = engine.ransac_e5_test if self.sample_size == 5 else engine.ransac_f8_test
+            if self.sample_size not in (5, 8):
+                raise NotImplementedError("test mode supports the 5-point and the 8-point samplers")
+            out = run(m, lg, rbs, thr, self.sampler.tau, nz, self.sampler.seed, self.sampler._next_offset())
+            if best is None or bool(out["best_score"][0] > best["best_score"][0]):     # ransac.py:116
+                best = out
+                if self.adaptive:
+                    max_iters = min(self.max_iterations,
+                                    self.adaptive_iteration_number(int(out["ninl"][0]), N, self.confidence))
+            iterations += rbs
+            chunk += 1
+        best_model, best_mask, best_score = best["best_model"][0], best["mask"][0], best["best_score"][0]
+        if self.final_refit and self.fmat and int(best_mask.sum()) >= 8:
+            # ransac.py:148-176: non-minimal 8-point on the inliers, kept only if it scores higher
+            cand = normalized_eight_point_torch(matches[best_mask][None])
+            sc, _ = ops.score_msac(m, cand.reshape(1, 1, 9), thr)
+            if bool(sc[0, 0] > best_score):
+                best_model, best_score = cand[0], sc[0, 0]
+        # The essential-matrix refit of the reference is pymagsac's C++ optimiser or, without it, a
+        # 5-point solve on ALL points (nister.py:51-65): outside the hot path.
+        return best_model.to(matches.dtype), best_mask, best_score, iterations
+
+    # -- B pairs at once (replaces the python loop of model_cl.py:488-510) ---------------------------
+    def batched_test(self, matches, logits, thresholds, K=None):
+        """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict for K hypotheses per pair
+        (default: max_iterations, no early exit)."""
+        K = K or self.max_iterations
+        run = engine.ransac_e5_test if self.sample_size == 5 else engine.ransac_f8_test
+        return run(matches, logits, K, thresholds, self.sampler.tau, None, self.sampler.seed, self.sampler._next_offset())
+
+
+class RANSAC3D(RANSAC):
+    """`ransac.py:303-450`.  Only the train branch of the reference runs (its test branch reads
+    undefined variables), so that is the branch provided."""
+
+    def __call__(self, matches, logits, gt_model, valid=False):
+        if valid or not self.train:
+            raise NotImplementedError("RANSAC3D test mode is broken in the reference (ransac.py:384-396)")
+        rbs = self.ransac_batch_size
+        chunks = self._chunks()
+        K = chunks * rbs
+        noise = self.sampler.injected_noise
+        if noise is not None:
+            noise = noise.reshape(1, -1, noise.shape[-1])
+        models, ok = engine.HypothesizeRigid.apply(matches[None], logits[None], K, True, self.sampler.tau, noise,
+                                                   self.sampler.seed, self.sampler._next_offset())
+        res = engine.RigidResidual.apply(matches[None], models)[0]
+        N = matches.shape[0]
+        out_m, out_r, out_mean = {}, {}, {}
+        for c in range(chunks):
+            sl = slice(c * rbs, (c + 1) * rbs)
+            out_m[c * rbs] = models[0, sl][ok[0, sl]]
+            out_r[c * rbs] = res[sl]
+            out_mean[c * rbs] = res[sl].sum() / (rbs * N)
+        return out_m, out_r, out_mean, 0, K
