@@ -1,0 +1,7 @@
+"""Drop-in `loss`: PoseLoss / ClassificationLoss stay the reference's; MatchLoss is the fused CUDA one."""
+from _bootstrap import load_reference_module
+
+_ref = load_reference_module("loss")
+globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("__")})
+
+from differentiable_ransac_b200.loss import MatchLoss  # noqa: E402,F401
