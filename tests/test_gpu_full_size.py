@@ -1,0 +1,112 @@
+"""BASELINE.json configs 3-5 at FULL size, through size-independent properties (determinism,
+linearity of the backward, finiteness, agreement with the oracle on a slice the CPU can afford)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_gpu():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+
+
+def test_cfg3_fundamental_training_step_full_size():
+    """F-8PC, 64 pairs x 2000 hyps x 2000 corrs, forward + backward with the epipolar loss."""
+    from differentiable_ransac_b200 import engine, synth
+    from oracle import fundamental, scoring
+    B, K, N = 64, 2000, 2000
+    ms, inls = [], []
+    for b in range(B):
+        pm, _, _, inl = synth.pixel_pair(N, (0.3, 0.5, 0.7)[b % 3], seed=100 + b)
+        ms.append(pm / 640.0)          # keep coordinates O(1) as datasets.py:74-79 does
+        inls.append(inl)
+    matches = torch.stack(ms).to(DEV)
+    logits = synth.logits_regime(B, N, "L1", seed=1).to(DEV)
+    P = max(int(i.sum()) for i in inls)
+    pts = torch.zeros(B, P, 4)
+    npts = torch.zeros(B, dtype=torch.int32)
+    for b in range(B):
+        pts[b, : int(inls[b].sum())] = ms[b][inls[b]]
+        npts[b] = int(inls[b].sum())
+    pts, npts = pts.to(DEV), npts.to(DEV)
+
+    def step(scale=1.0):
+        m = matches.clone().requires_grad_(True)
+        lg = logits.clone().requires_grad_(True)
+        models, valid = engine.HypothesizeF8.apply(m, lg, K, 1.0, None, 9, 0)
+        loss = engine.match_loss(models, valid, pts, npts).mean() * scale
+        loss.backward()
+        return loss.detach(), lg.grad, m.grad, models.detach(), valid
+
+    l1, gl1, gm1, models, valid = step()
+    l2, gl2, gm2, _, _ = step(2.0)
+    assert valid.float().mean() > 0.999 and torch.isfinite(gl1).all() and torch.isfinite(gm1).all()
+    assert torch.allclose(l2, 2 * l1, rtol=1e-6)
+    # same models, same per-thread sums; only the order of the atomic accumulation differs
+    assert torch.allclose(gl2, 2 * gl1, rtol=1e-3, atol=1e-7 * float(gl1.abs().max()) + 1e-12)
+    assert gl1.abs().sum() > 0
+    # oracle on a slice: the models of pair 0, first 32 hypotheses, and their loss rows
+    idx, _, _, _ = __import__("differentiable_ransac_b200").ops.sample(logits, K, 8, 1.0, seed=9, offset=0, want_lse=True)
+    sub = matches[0].cpu()[idx[0, :32].cpu().long()]
+    Fo = fundamental.eight_point(sub.double())
+    Fm = models[0, :32].cpu().double()
+    d = torch.minimum((Fm - Fo).flatten(1).norm(dim=1), (Fm + Fo).flatten(1).norm(dim=1)) / Fo.flatten(1).norm(dim=1)
+    assert d.max() < 1e-3
+    inl0 = ms[0][inls[0]]
+    want = scoring.match_loss(Fm.float(), inl0[:, :2], inl0[:, 2:], torch.ones(inl0.shape[0], dtype=torch.bool))
+    got = engine.match_loss(models[:1, :32], valid[:1, :32], pts[:1], npts[:1])[0]
+    assert abs(float(got) - float(want)) < 1e-3 * float(want)
+
+
+def test_cfg4_rigid_full_size():
+    """Rigid 3-point, 16 pairs x 1000 hyps x 50 000 corrs (the reference needs 5.3 GB per pair here)."""
+    from differentiable_ransac_b200 import engine, synth
+    B, K, N = 16, 1000, 50000
+    pts = torch.stack([synth.rigid_pair(N, 0.7, seed=200 + b)[0] for b in range(B)]).to(DEV)
+    logits = synth.logits_regime(B, N, "L1", seed=2).to(DEV).requires_grad_(True)
+    torch.cuda.reset_peak_memory_stats()
+    base = torch.cuda.memory_allocated()
+    for flag in (True, False):
+        models, valid = engine.HypothesizeRigid.apply(pts, logits, K, flag, 1.0, None, 3, 0)
+        res = engine.RigidResidual.apply(pts, models)
+        assert valid.float().mean() > 0.99 and torch.isfinite(res).all()
+        # three models against a direct evaluation
+        for b, k in ((0, 0), (7, 123), (15, 999)):
+            M = models[b, k].detach().double().cpu()
+            p = pts[b].double().cpu()
+            want = ((p[:, 3:] - (p[:, :3] @ M[:3, :3].T + M[:3, 3])) ** 2).sum()
+            assert abs(float(res[b, k]) - float(want)) < 1e-4 * float(want)
+        if flag:
+            res.mean().backward()
+            assert torch.isfinite(logits.grad).all() and logits.grad.abs().sum() > 0
+    assert torch.cuda.max_memory_allocated() - base < 64 * 1024 * 1024      # nothing of size K x N exists
+
+
+def test_cfg5_essential_training_step_full_size():
+    """5PC training, 32 pairs per GPU (cfg5 = 256 pairs over 8 GPUs) x 1000 hyps x 2000 corrs."""
+    from differentiable_ransac_b200 import engine, synth
+    B, K, N = 32, 1000, 2000
+    matches, E_gt, inl = synth.relative_pose_batch(B, N, seed=300, noise=2e-4)
+    logits = synth.logits_regime(B, N, "L0", seed=4)
+    P = int(inl.sum(1).max())
+    pts = torch.zeros(B, P, 4)
+    npts = inl.sum(1).int()
+    for b in range(B):
+        pts[b, : int(npts[b])] = matches[b][inl[b]]
+    m = matches.to(DEV).requires_grad_(True)
+    lg = logits.to(DEV).requires_grad_(True)
+    chosen, valid = engine.HypothesizeE5.apply(m, lg, E_gt.to(DEV), K, 1.0, None, 5, 0, True)
+    loss = engine.match_loss(chosen, valid, pts.to(DEV), npts.to(DEV)).mean()
+    loss.backward()
+    assert valid.float().mean() > 0.9 and torch.isfinite(lg.grad).all() and torch.isfinite(m.grad).all()
+    # every chosen model is a genuine essential matrix fitting its own minimal sample
+    c = chosen.detach()[valid]
+    EEt = c @ c.transpose(-1, -2)
+    resid = (2 * EEt @ c - EEt.diagonal(dim1=-2, dim2=-1).sum(-1)[:, None, None] * c).flatten(1).norm(dim=1)
+    assert (resid < 1e-3).float().mean() > 0.97
+    # the gradient pushes weight towards inliers: d loss / d logit is lower on inliers on average
+    g = lg.grad.cpu()
+    assert g[inl].mean() < g[~inl].mean()
