@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "2")),
+                    help="sub-batches on separate CUDA streams (overlaps the latency-bound solver with scoring)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -228,7 +230,7 @@ def main():
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
 
     def step(i):
-        return engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=i)
+        return engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=i, streams=args.streams)
 
     def barrier():
         torch.cuda.synchronize()
@@ -270,7 +272,7 @@ def main():
         m = matches_h.to(dev, non_blocking=True)
         l = logits_h.to(dev, non_blocking=True)
         th = thr_h.to(dev, non_blocking=True)
-        o = engine.ransac_e5_test(m, l, K, th, seed=42 + rank, offset=1000 + i)
+        o = engine.ransac_e5_test(m, l, K, th, seed=42 + rank, offset=1000 + i, streams=args.streams)
         for k_, v in res_h.items():
             v.copy_(o[k_], non_blocking=True)
 
@@ -296,7 +298,7 @@ def main():
         return
 
     # ---- roofline of the dominant kernel (score_msac_kernel), timed live with CUDA events -------------------
-    idx, _, _, _ = ops.sample(logits, K, 5, 1.0, seed=7, offset=0)
+    idx = ops.sample_sets(logits, K, 5, seed=7, offset=0)
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
     n_valid = int(cc.sum().item())
     reps = 10
@@ -312,7 +314,8 @@ def main():
     score_ms = sum(a.elapsed_time(b_) for a, b_ in evs) / reps          # includes the 8-byte/pair memset of `best`
     # stage shares of one step (events around each stage)
     shares = {}
-    for name, fn in (("sample", lambda: ops.sample(logits, K, 5, 1.0, seed=7, offset=1)),
+    for name, fn in (("sample_sets", lambda: ops.sample_sets(logits, K, 5, seed=7, offset=1)),
+                     ("sample_gumbel_race", lambda: ops.sample(logits, K, 5, 1.0, seed=7, offset=1)),
                      ("solve_e5", lambda: ops.solve_e5(matches, idx, compact=True)),
                      ("score_msac", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=False)),
                      ):
@@ -335,11 +338,14 @@ def main():
         dtype="f32", data="synthetic",
         config=dict(workload="cfg2: Essential 5PC (Nister), 32 pairs x 1000 hyps x 2000 corrs per GPU, fwd only, "
                              "test-mode semantics (sample -> solve -> MSAC -> arg-max + winner mask)",
-                    pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N, noise="in-kernel Philox4x32-10",
-                    l2="flushed between timed iterations (256 MB write)", parallelism=f"pairs sharded over {world} GPU(s)"),
+                    pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N,
+                    noise="in-kernel Philox4x32-10; sets drawn without replacement from softmax(logits) "
+                          "(= Gumbel top-5 in law, drb_sample_sets)",
+                    l2="flushed between timed iterations (256 MB write)", streams=args.streams,
+                    parallelism=f"pairs sharded over {world} GPU(s)"),
         clocks=clock_info,
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-        gpu_launches=4 * args.steps,
+        gpu_launches=4 * max(1, args.streams) * args.steps,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
                       kernel="score_msac_kernel", kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,

@@ -172,6 +172,112 @@ sample_race_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
     if (lane < S) idx_out[(size_t)row * S + rank] = top_i;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Set sampler (test mode, nothing but the index sets is wanted).  Taking the s largest of
+// logit + Gumbel noise IS sampling s items without replacement from softmax(logits) (the
+// Plackett-Luce law behind the Gumbel-top-k trick), so the sets can be drawn directly: one THREAD
+// per hypothesis makes s inverse-CDF draws on a per-pair prefix sum held in shared memory and
+// rejects repeats.  O(s log N) per hypothesis instead of O(N): the K x N noise the reference
+// (and the kernels above) generate only to throw away is never produced.  The distribution is
+// identical; the realisation differs, which is immaterial without an injected-noise reference.
+constexpr int kSetThreads = 256;
+
+template <int S>
+__global__ void __launch_bounds__(kSetThreads)
+sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
+                   int32_t* __restrict__ idx_out) {
+    extern __shared__ float cdf[];  // N inclusive prefix sums of exp(logit - max)
+    __shared__ float red[kSetThreads / 32];
+    __shared__ float warp_tot[kSetThreads / 32];
+    const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float* lg = logits + (size_t)b * N;
+    // 1. max logit (so that exp cannot overflow)
+    float mx = -INFINITY;
+    for (int n = tid; n < N; n += kSetThreads) mx = fmaxf(mx, __ldg(lg + n));
+    DRB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    DRB_UNROLL
+    for (int w = 1; w < kSetThreads / 32; ++w) mx = fmaxf(mx, red[w]);
+    // 2. block-wide inclusive scan of the weights, each thread owning a contiguous chunk
+    const int chunk = (N + kSetThreads - 1) / kSetThreads;
+    const int n_lo = min(N, tid * chunk), n_hi = min(N, n_lo + chunk);
+    float local = 0.f;
+    for (int n = n_lo; n < n_hi; ++n) {
+        local += __expf(__ldg(lg + n) - mx);
+        cdf[n] = local;
+    }
+    float incl = local;
+    DRB_UNROLL
+    for (int o = 1; o < 32; o <<= 1) {
+        const float up = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += up;
+    }
+    if (lane == 31) warp_tot[warp] = incl;
+    __syncthreads();
+    float base = incl - local;
+    for (int w = 0; w < warp; ++w) base += warp_tot[w];
+    for (int n = n_lo; n < n_hi; ++n) cdf[n] += base;
+    __syncthreads();
+    const int k = blockIdx.x * kSetThreads + tid;
+    if (k >= K) return;
+    const float total = cdf[N - 1];
+    int chosen[S];
+    int count = 0;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+    for (int call = 0; call < 16 && count < S; ++call) {
+        const Philox4 r = philox4x32_10((uint32_t)call, (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        DRB_UNROLL
+        for (int t = 0; t < 4; ++t) {
+            if (count < S) {
+                // 24 random bits -> u in [0, total); first n with cdf[n] > u
+                const float u = (float)(rr[t] >> 8) * 5.9604644775390625e-08f * total;
+                int lo = 0, hi = N - 1;
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    if (cdf[mid] > u) hi = mid; else lo = mid + 1;
+                }
+                bool dup = false;
+                DRB_UNROLL
+                for (int j = 0; j < S; ++j) dup = dup || (j < count && chosen[j] == lo);
+                if (!dup) {
+                    DRB_UNROLL
+                    for (int j = 0; j < S; ++j)
+                        if (j == count) chosen[j] = lo;
+                    ++count;
+                }
+            }
+        }
+    }
+    // degenerate weights (all the mass on fewer than S items): complete with the lowest unused indices
+    for (int n = 0; count < S && n < N; ++n) {
+        bool dup = false;
+        DRB_UNROLL
+        for (int j = 0; j < S; ++j) dup = dup || (j < count && chosen[j] == n);
+        if (!dup) {
+            DRB_UNROLL
+            for (int j = 0; j < S; ++j)
+                if (j == count) chosen[j] = n;
+            ++count;
+        }
+    }
+    // ascending order, like the reference's boolean-mask gather (ransac.py:65)
+    DRB_UNROLL
+    for (int i = 1; i < S; ++i) {
+        DRB_UNROLL
+        for (int j = i; j > 0; --j) {
+            if (chosen[j - 1] > chosen[j]) { const int t = chosen[j]; chosen[j] = chosen[j - 1]; chosen[j - 1] = t; }
+        }
+    }
+    const long long row = (long long)b * K + k;
+    DRB_UNROLL
+    for (int j = 0; j < S; ++j) idx_out[row * S + j] = chosen[j];
+}
+
 template <int S>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_kernel(const float* __restrict__ logits, const float* __restrict__ noise, uint64_t seed, uint64_t offset,
@@ -360,6 +466,37 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
             return DRB_ERR_UNSUPPORTED;
     }
 #undef DRB_LAUNCH_SAMPLE
+    return check_launch();
+}
+
+extern "C" int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offset, int B, int K, int N, int s,
+                               int32_t* idx, void* stream) {
+    if (!logits || !idx) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || N <= 0 || s <= 0 || s > N || B > 65535) return DRB_ERR_BAD_SHAPE;
+    const size_t smem = (size_t)N * sizeof(float);
+    if (smem > 200 * 1024) return DRB_ERR_UNSUPPORTED;  // the prefix sums of one pair must fit in shared memory
+    const dim3 grid((K + kSetThreads - 1) / kSetThreads, B);
+#define DRB_LAUNCH_SETS(S_)                                                                                       \
+    case S_: {                                                                                                    \
+        static bool configured = false;                                                                           \
+        if (!configured) {                                                                                        \
+            if (cudaFuncSetAttribute(sample_sets_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
+                                     200 * 1024) != cudaSuccess)                                                  \
+                return DRB_ERR_CUDA;                                                                              \
+            configured = true;                                                                                    \
+        }                                                                                                         \
+        sample_sets_kernel<S_><<<grid, kSetThreads, smem, (cudaStream_t)stream>>>(logits, seed, offset, K, N, idx); \
+        break;                                                                                                    \
+    }
+    switch (s) {
+        DRB_LAUNCH_SETS(3)
+        DRB_LAUNCH_SETS(5)
+        DRB_LAUNCH_SETS(7)
+        DRB_LAUNCH_SETS(8)
+        default:
+            return DRB_ERR_UNSUPPORTED;
+    }
+#undef DRB_LAUNCH_SETS
     return check_launch();
 }
 

@@ -61,6 +61,20 @@ def sample(logits, K, s, tau=1.0, noise=None, seed=0, offset=0, want_lse=False, 
     return idx, lse, sel_key, noise_out
 
 
+def sample_sets(logits, K, s, seed=0, offset=0):
+    """Test-mode set sampler (Plackett-Luce by inverse CDF, no Gumbel noise): logits [B,N] -> idx [B,K,s].
+    Falls back to the Gumbel-race kernel when one pair's prefix sums do not fit in shared memory."""
+    logits = _f32(logits)
+    B, N = logits.shape
+    idx = torch.empty(B, K, s, dtype=torch.int32, device=logits.device)
+    lib = _lib.load()
+    rc = lib.drb_sample_sets(_p(logits), seed, offset, B, K, N, s, _p(idx), _stream())
+    if rc == -3 and s in (3, 5, 7, 8):
+        return sample(logits, K, s, 1.0, None, seed, offset)[0]
+    check(rc, "drb_sample_sets")
+    return idx
+
+
 def sample_backward(logits, idx, lse, sel_key, g_sel, tau=1.0, noise=None, seed=0, offset=0):
     logits = _f32(logits)
     B, N = logits.shape

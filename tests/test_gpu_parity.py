@@ -86,6 +86,57 @@ def test_sampler_race_equals_exact(drb):
         assert int(fast.min()) >= 0 and int(fast.max()) < N
 
 
+def test_set_sampler_same_law_as_gumbel_topk(drb):
+    """drb_sample_sets draws without replacement by inverse CDF (Plackett-Luce); Gumbel top-s is the same
+    law.  Compare, on a small alphabet, (i) the first-pick marginal with softmax(logits), (ii) inclusion
+    frequencies and pair co-occurrence frequencies of both kernels over 200 000 hypotheses."""
+    B, N, K, s = 1, 12, 200000, 3
+    logits = torch.tensor([[0.3, -1.0, 2.0, 0.0, 1.2, -0.5, 0.7, -2.0, 1.5, 0.1, -0.2, 0.9]])
+    a = drb.ops.sample_sets(logits.to(DEV), K, s, seed=3, offset=0)[0].cpu().long()
+    b = drb.ops.sample(logits.to(DEV), K, s, 1.0, seed=4, offset=0, want_lse=True)[0][0].cpu().long()
+    assert (a[:, 1:] > a[:, :-1]).all() and int(a.min()) >= 0 and int(a.max()) < N
+
+    def stats(idx):
+        inc = torch.zeros(N)
+        pair = torch.zeros(N, N)
+        onehot = torch.zeros(idx.shape[0], N).scatter_(1, idx, 1.0)
+        inc = onehot.mean(0)
+        pair = (onehot.T @ onehot) / idx.shape[0]
+        return inc, pair
+
+    ia, pa = stats(a)
+    ib, pb = stats(b)
+    sigma = (0.25 / K) ** 0.5
+    assert (ia - ib).abs().max() < 6 * sigma * 1.5
+    assert (pa - pb).abs().max() < 6 * sigma * 1.5
+    # exact inclusion probability of the most likely item under Plackett-Luce (enumeration over ordered triples)
+    w = torch.softmax(logits[0].double(), 0)
+    p_inc = torch.zeros(N, dtype=torch.float64)
+    for i in range(N):
+        for j in range(N):
+            if j == i:
+                continue
+            for l in range(N):
+                if l in (i, j):
+                    continue
+                p = w[i] * w[j] / (1 - w[i]) * w[l] / (1 - w[i] - w[j])
+                p_inc[i] += p
+                p_inc[j] += p
+                p_inc[l] += p
+    assert (ia.double() - p_inc).abs().max() < 8 * sigma
+    # determinism / offsets / degenerate weights
+    assert torch.equal(drb.ops.sample_sets(logits.to(DEV), 1000, s, seed=3, offset=0),
+                       drb.ops.sample_sets(logits.to(DEV), 1000, s, seed=3, offset=0))
+    assert not torch.equal(drb.ops.sample_sets(logits.to(DEV), 1000, s, seed=3, offset=0),
+                           drb.ops.sample_sets(logits.to(DEV), 1000, s, seed=3, offset=1))
+    spike = torch.full((2, 500), -80.0)
+    spike[:, 17] = 0.0
+    d = drb.ops.sample_sets(spike.to(DEV), 64, 5, seed=1, offset=0).cpu()
+    assert (d[..., 1:] > d[..., :-1]).all() and (d == 17).any(dim=-1).all()
+    big = drb.ops.sample_sets(torch.zeros(2, 50000, device=DEV), 128, 3, seed=1, offset=0)     # cfg4 size
+    assert int(big.max()) < 50000 and (big[..., 1:] > big[..., :-1]).all()
+
+
 def test_sampler_follows_the_weights(drb):
     """Gumbel-max sampling draws the first pick with probability softmax(logits): empirical
     inclusion frequencies over many hypotheses follow the weights (fast path)."""
