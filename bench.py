@@ -201,8 +201,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "2")),
-                    help="sub-batches on separate CUDA streams (overlaps the latency-bound solver with scoring)")
+    ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "1")),
+                    help="sub-batches on separate CUDA streams (measured: 1 is fastest, profiles/r1_notes.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -263,30 +263,50 @@ def main():
     value = world * B * K * args.steps / (ms_total / 1e3)
 
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
-    h2d = matches_h.numel() * 4 + logits_h.numel() * 4 + thr_h.numel() * 4
-    res_h = dict(best_model=torch.empty(B, 3, 3).pin_memory(), best_id=torch.empty(B, dtype=torch.int32).pin_memory(),
-                 best_score=torch.empty(B).pin_memory(), ninl=torch.empty(B, dtype=torch.int32).pin_memory())
-    d2h = sum(v.numel() * v.element_size() for v in res_h.values())
+    # Every step copies ITS inputs from pinned host memory (one packed buffer: matches | logits | thr) and
+    # reads ITS results back (one packed buffer: model | id | score | #inliers).  Two slots: the copy-in of
+    # step i+1 runs on a copy stream while step i computes -- steady-state service throughput.  Inputs come
+    # from the host every step, so no L2 flush is inserted here (and it could not be excluded from the
+    # timed region once copies and compute overlap).
+    n_in = B * N * 4 + B * N + B
+    host_in = torch.cat((matches_h.flatten(), logits_h.flatten(), thr_h.flatten())).pin_memory()
+    h2d = host_in.numel() * 4
+    n_out = B * 9 + 3 * B
+    host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(2)]
+    d2h = n_out * 4
+    dev_in = [torch.empty(n_in, dtype=torch.float32, device=dev) for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    main_stream = torch.cuda.current_stream()
 
-    def step_e2e(i):
-        m = matches_h.to(dev, non_blocking=True)
-        l = logits_h.to(dev, non_blocking=True)
-        th = thr_h.to(dev, non_blocking=True)
-        o = engine.ransac_e5_test(m, l, K, th, seed=42 + rank, offset=1000 + i, streams=args.streams)
-        for k_, v in res_h.items():
-            v.copy_(o[k_], non_blocking=True)
+    def run_e2e(n_steps, first):
+        for s_ in range(2):
+            consumed[s_].record(main_stream)
+        for i in range(n_steps):
+            slot = i & 1
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[slot])
+                dev_in[slot].copy_(host_in, non_blocking=True)
+                copied[slot].record(copy_stream)
+            main_stream.wait_event(copied[slot])
+            buf = dev_in[slot]
+            m = buf[: B * N * 4].view(B, N, 4)
+            l = buf[B * N * 4: B * N * 5].view(B, N)
+            th = buf[B * N * 5:]
+            o = engine.ransac_e5_test(m, l, K, th, seed=42 + rank, offset=first + i, streams=args.streams)
+            consumed[slot].record(main_stream)
+            packed = torch.cat((o["best_model"].flatten(), o["best_id"].float(), o["best_score"], o["ninl"].float()))
+            host_out[slot].copy_(packed, non_blocking=True)
 
-    for i in range(warmup):
-        step_e2e(i)
+    run_e2e(warmup, 1000)
     barrier()
-    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
-        flush.fill_(float(i))
-        ev2[i][0].record()
-        step_e2e(warmup + i)
-        ev2[i][1].record()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(main_stream)
+    run_e2e(args.steps, 2000)
+    e1.record(main_stream)
     barrier()
-    t2 = torch.tensor([sum(a.elapsed_time(b) for a, b in ev2)], dtype=torch.float64, device=dev)
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B * K * args.steps / (float(t2.item()) / 1e3)
@@ -341,7 +361,11 @@ def main():
                     pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N,
                     noise="in-kernel Philox4x32-10; sets drawn without replacement from softmax(logits) "
                           "(= Gumbel top-5 in law, drb_sample_sets)",
-                    l2="flushed between timed iterations (256 MB write)", streams=args.streams,
+                    l2="flushed between timed iterations (256 MB write) for `value`; e2e re-copies its inputs "
+                       "from the host every step instead",
+                    e2e_mode="two slots: the packed H2D of step i+1 overlaps the compute of step i; one packed "
+                             "D2H of (model, id, score, #inliers) per step",
+                    streams=args.streams,
                     parallelism=f"pairs sharded over {world} GPU(s)"),
         clocks=clock_info,
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),

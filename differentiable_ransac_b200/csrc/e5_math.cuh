@@ -283,11 +283,19 @@ DRB_HD void e5_polish(const T (*N)[9], T& x, T& y, T& z, int iters) {
     }
 }
 
-// Full solver.  pts[j] = (x1, y1, x2, y2).  models[s][9] row-major, unit
-// Frobenius norm; returns the number of real solutions n (slots >= n are set to
-// the identity).  `M` is the 10 x 20 scratch.
-template <class T, class Mat, class RT = T>
-DRB_HD int e5_solve(const T (*pts)[4], Mat& M, T (*models)[9], int polish_iters = 2) {
+// Plain-array sink for e5_solve's models (host harness, and anything that wants [10][9]).
+template <class T>
+struct ArrayModelSink {
+    T (*m)[9];
+    DRB_HD void operator()(int slot, int i, T v) { m[slot][i] = v; }
+};
+
+// Full solver.  pts[j] = (x1, y1, x2, y2).  `models(slot, i, v)` receives the row-major, unit
+// Frobenius norm solutions in slots 0..n-1 (n = return value = number of real roots; slots >= n
+// are NOT written: the caller pads with the identity).  `M` is the 10 x 20 scratch; it is dead
+// once the z-polynomials have been read out of it, so a sink may alias its storage.
+template <class T, class Mat, class RT, class Sink>
+DRB_HD int e5_solve(const T (*pts)[4], Mat& M, Sink& models, int polish_iters = 2) {
     T N[4][9];
     {
         T rows[5][9];
@@ -389,12 +397,8 @@ DRB_HD int e5_solve(const T (*pts)[4], Mat& M, T (*models)[9], int polish_iters 
         if (!(n2 > T(0)) || !(n2 < T(1e37))) continue;
         const T inv = t_rsqrt(n2);
         DRB_UNROLL
-        for (int i = 0; i < 9; ++i) models[nout][i] = E[i] * inv;
+        for (int i = 0; i < 9; ++i) models(nout, i, E[i] * inv);
         ++nout;
-    }
-    for (int s = nout; s < 10; ++s) {
-        DRB_UNROLL
-        for (int i = 0; i < 9; ++i) models[s][i] = (i == 0 || i == 4 || i == 8) ? T(1) : T(0);
     }
     return nout;
 }

@@ -124,8 +124,11 @@ struct SturmChain10 {
         eval(hi, fhi, d);
         T z = T(0.5) * (lo + hi);
         if ((flo < T(0)) == (fhi < T(0))) return z;  // no sign change (cluster / rounding): keep the midpoint
-        const T tol = T(4) * (sizeof(T) == 4 ? T(6e-8) : T(1.2e-16));
-        for (int it = 0; it < 24; ++it) {
+        // fp32: the caller polishes every root by Gauss-Newton on the original constraints, so a root
+        // good to ~1e-4 is enough here and the (warp-divergent) loop stays short; fp64 goes to rounding.
+        const T tol = sizeof(T) == 4 ? T(1e-4) : T(4.8e-16);
+        const int max_it = sizeof(T) == 4 ? 8 : 24;
+        for (int it = 0; it < max_it; ++it) {
             T f, df;
             eval(z, f, df);
             if ((f < T(0)) == (flo < T(0))) {

@@ -19,6 +19,12 @@ struct SmemMat {
     __device__ __forceinline__ float& operator()(int r, int c) { return base[(r * 20 + c) * kE5Threads]; }
 };
 
+struct SmemSink {
+    float* base;  // same column as SmemMat: element e (= slot * 9 + i, e < 90 <= 200) at base[e * kE5Threads]
+    __device__ __forceinline__ void operator()(int slot, int i, float v) { base[(slot * 9 + i) * kE5Threads] = v; }
+    __device__ __forceinline__ float get(int e) const { return base[e * kE5Threads]; }
+};
+
 __device__ __forceinline__ void load_minimal5(const float* __restrict__ matches, const int32_t* __restrict__ idx,
                                               long long row, int b, int N, float (*p)[4]) {
     DRB_UNROLL
@@ -46,15 +52,28 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
     float p[5][4];
     load_minimal5(matches, idx, row, b, N, p);
     SmemMat M{smem + threadIdx.x};
-    float(*out)[9] = reinterpret_cast<float(*)[9]>(models + (size_t)row * 90);
-    const int n = e5_solve<float, SmemMat>(p, M, out, 2);
+    // The solutions are staged in this thread's own scratch column (dead once the z-polynomials have
+    // been read out), so the dense and the compact copies below read shared memory, not the global
+    // memory that was just written.
+    SmemSink sink{smem + threadIdx.x};
+    const int n = e5_solve<float, SmemMat, float, SmemSink>(p, M, sink, 2);
     nsol[row] = n;
+    // reserve the compact-list slots early so the atomic's round trip overlaps the dense write
+    int pos = 0;
+    if (cmodels != nullptr && n > 0) pos = atomicAdd(ccount + b, n);
+    float2* dense = reinterpret_cast<float2*>(models + (size_t)row * 90);   // 360 B per row: 8-byte aligned
+    DRB_UNROLL
+    for (int e = 0; e < 45; ++e) {
+        const int e0 = 2 * e, e1 = 2 * e + 1;
+        const float v0 = (e0 / 9 < n) ? sink.get(e0) : (((e0 % 9) % 4 == 0) ? 1.f : 0.f);
+        const float v1 = (e1 / 9 < n) ? sink.get(e1) : (((e1 % 9) % 4 == 0) ? 1.f : 0.f);
+        dense[e] = make_float2(v0, v1);
+    }
     if (cmodels != nullptr && n > 0) {
-        const int pos = atomicAdd(ccount + b, n);
         float* dst = cmodels + ((size_t)b * K * 10 + pos) * 9;
         for (int s = 0; s < n; ++s) {
             DRB_UNROLL
-            for (int i = 0; i < 9; ++i) dst[s * 9 + i] = out[s][i];
+            for (int i = 0; i < 9; ++i) dst[s * 9 + i] = sink.get(s * 9 + i);
             cids[(size_t)b * K * 10 + pos + s] = k * 10 + s;
         }
     }

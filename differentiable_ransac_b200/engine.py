@@ -65,15 +65,16 @@ def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
             main.wait_stream(st)
         return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
     idx = _draw(logits, K, 5, tau, noise, seed, offset, sampler)
-    models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
-    scores, best = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=want_scores)
-    B = matches.shape[0]
+    best0, cc0 = ops.zeroed_counters(B, matches.device)
+    models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True, ccount=cc0)
+    scores, best = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=want_scores, best=best0)
     best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, models.reshape(B, -1, 9), best, thr)
-    out = dict(best_model=best_model, best_id=best_id, best_hyp=torch.div(best_id, ops.E5_SLOTS, rounding_mode="floor"),
-               best_slot=best_id % ops.E5_SLOTS, best_score=best_score, mask=mask.bool(), ninl=ninl, idx=idx,
-               models=models, nsol=nsol)
+    # best_id = hypothesis * 10 + slot; mask is 0/1 bytes, reinterpreted (not copied) as bool
+    out = dict(best_model=best_model, best_id=best_id, best_score=best_score, mask=mask.view(torch.bool), ninl=ninl,
+               idx=idx, models=models, nsol=nsol)
     if want_scores:
-        out.update(scores=scores, cids=cid, ccount=cc)
+        out.update(scores=scores, cids=cid, ccount=cc,
+                   best_hyp=torch.div(best_id, ops.E5_SLOTS, rounding_mode="floor"), best_slot=best_id % ops.E5_SLOTS)
     return out
 
 

@@ -118,7 +118,14 @@ def _rows(matches, idx, s, D):
     return matches, idx, B, idx.shape[1], N
 
 
-def solve_e5(matches, idx=None, compact=False):
+def zeroed_counters(B, device):
+    """One fill for both zero-initialised scratch arrays of the test pipeline:
+    best_packed [B] (u64 as int64) and ccount [B] int32."""
+    z = torch.zeros(2 * B, dtype=torch.int64, device=device)
+    return z[:B], z[B:].view(torch.int32)[:B]
+
+
+def solve_e5(matches, idx=None, compact=False, ccount=None):
     """-> models [B,K,10,3,3], nsol [B,K] int32 (, cmodels [B,K*10,9], cids [B,K*10], ccount [B])."""
     matches, idx, B, K, N = _rows(matches, idx, 5, 4)
     dev = matches.device
@@ -128,7 +135,7 @@ def solve_e5(matches, idx=None, compact=False):
     if compact:
         cm = torch.empty(B, K * E5_SLOTS, 9, dtype=torch.float32, device=dev)
         cid = torch.empty(B, K * E5_SLOTS, dtype=torch.int32, device=dev)
-        cc = torch.zeros(B, dtype=torch.int32, device=dev)
+        cc = ccount if ccount is not None else torch.zeros(B, dtype=torch.int32, device=dev)
     lib = _lib.load()
     check(lib.drb_solve_e5(_p(matches), _p(idx), B, K, N, _p(models), _p(nsol), _p(cm), _p(cid), _p(cc), _stream()),
           "drb_solve_e5")
@@ -205,15 +212,17 @@ def solve_rigid3_backward(points, idx, g_model, flag=True):
 
 
 # ---- scoring -----------------------------------------------------------------------------------
-def score_msac(matches, models, thr, count=None, ids=None, want_scores=True):
-    """matches [B,N,4], models [B,M,9|3,3], thr [B] -> scores [B,M] | None, best_packed [B] (int64 view of u64)."""
+def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None):
+    """matches [B,N,4], models [B,M,9|3,3], thr [B] -> scores [B,M] | None, best_packed [B] (int64 view of u64).
+    `best` may be a caller-zeroed [B] int64 buffer."""
     matches = _f32(matches)
     B, N, _ = matches.shape
     models = _f32(models).reshape(B, -1, 9)
     M = models.shape[1]
     thr = _f32(thr).reshape(B)
     scores = torch.empty(B, M, dtype=torch.float32, device=matches.device) if want_scores else None
-    best = torch.zeros(B, dtype=torch.int64, device=matches.device)
+    if best is None:
+        best = torch.zeros(B, dtype=torch.int64, device=matches.device)
     lib = _lib.load()
     check(lib.drb_score_msac(_p(matches), _p(models), _p(None if count is None else _i32(count)),
                              _p(None if ids is None else _i32(ids)), _p(thr), B, M, N, _p(scores), _p(best),

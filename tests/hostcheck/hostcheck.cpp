@@ -26,7 +26,10 @@ void run_e5(const T* pts, int K, T* models, int* nsol, int polish) {
             for (int c = 0; c < 4; ++c) p[j][c] = pts[(k * 5 + j) * 4 + c];
         HostMat<T> M;
         T out[10][9];
-        nsol[k] = drb::e5_solve<T, HostMat<T>, RT>(p, M, out, polish);
+        for (int s = 0; s < 10; ++s)
+            for (int i = 0; i < 9; ++i) out[s][i] = (i % 4 == 0) ? T(1) : T(0);   // identity padding
+        drb::ArrayModelSink<T> sink{out};
+        nsol[k] = drb::e5_solve<T, HostMat<T>, RT, drb::ArrayModelSink<T>>(p, M, sink, polish);
         std::memcpy(models + (size_t)k * 90, out, sizeof(out));
     }
 }
