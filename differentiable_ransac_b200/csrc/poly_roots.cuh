@@ -80,31 +80,40 @@ struct SturmChain10 {
         a[0] = b[0] = m[0] = T(0);
     }
 
-    // number of sign changes of the chain at z
+    // shift the sign bit of v into the low end of `mask` (one funnel shift on the device)
+    DRB_HD static uint32_t push_sign(uint32_t mask, float v) {
+#if defined(__CUDA_ARCH__)
+        return __funnelshift_l(__float_as_uint(v), mask, 1);
+#else
+        return (mask << 1) | (uint32_t)(v < 0.f || (v == 0.f && 1.f / v < 0.f));
+#endif
+    }
+    DRB_HD static uint32_t push_sign(uint32_t mask, double v) {
+        return (mask << 1) | (uint32_t)(v < 0.0 || (v == 0.0 && 1.0 / v < 0.0));
+    }
+
+    // Number of sign changes of the chain f_10, f_9, ..., f_0 at z.  The eleven sign bits are collected
+    // in one word and adjacent bits compared at the end (an exact zero counts as positive: measure-zero
+    // event, and the grid / bisection points never coincide with a root of a chain member in practice).
     DRB_HD int count(T z) const {
         T s_next = c;
         T s_cur = l1 * z + l0;
-        int changes = 0;
-        int last = (s_next > T(0)) - (s_next < T(0));
-        {
-            const int sg = (s_cur > T(0)) - (s_cur < T(0));
-            if (sg != 0) {
-                if (last != 0 && sg != last) ++changes;
-                last = sg;
-            }
-        }
+        uint32_t mask = push_sign(push_sign(0u, s_next), s_cur);
         DRB_UNROLL
         for (int i = 9; i >= 1; --i) {
             const T s_prev = (a[i] * z + b[i]) * s_cur - m[i] * s_next;
             s_next = s_cur;
             s_cur = s_prev;
-            const int sg = (s_cur > T(0)) - (s_cur < T(0));
-            if (sg != 0) {
-                if (last != 0 && sg != last) ++changes;
-                last = sg;
-            }
+            mask = push_sign(mask, s_cur);
         }
-        return changes;
+        const uint32_t flips = (mask ^ (mask >> 1)) & 0x3ffu;  // 11 values -> 10 adjacent pairs
+#if defined(__CUDA_ARCH__)
+        return __popc(flips);
+#else
+        int n = 0;
+        for (uint32_t f = flips; f; f &= f - 1) ++n;
+        return n;
+#endif
     }
 
     DRB_HD void eval(T z, T& f, T& df) const {
