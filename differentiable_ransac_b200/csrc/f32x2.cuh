@@ -28,6 +28,19 @@ __device__ __forceinline__ pk2 pk2_mul(pk2 a, pk2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
     return d;
 }
+// `volatile` twins: the compiler keeps volatile asm statements in program order, which lets a
+// hand-written sequence put instructions that share a source operand next to each other (the
+// register-file operand-reuse cache only helps adjacent instructions; score.cu).
+__device__ __forceinline__ pk2 pk2_fma_v(pk2 a, pk2 b, pk2 c) {
+    pk2 d;
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ pk2 pk2_mul_v(pk2 a, pk2 b) {
+    pk2 d;
+    asm volatile("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
 __device__ __forceinline__ pk2 pk2_add(pk2 a, pk2 b) {
     pk2 d;
     asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
