@@ -45,6 +45,16 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def load_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
+            t = json.load(f)[kernel]
+        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
 
@@ -370,7 +380,8 @@ def main():
         clocks=clock_info,
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=4 * max(1, args.streams) * args.steps,
-        roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+        roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                      traffic=load_traffic("score_msac_kernel"),
                       kernel="score_msac_kernel", kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,
                       note="FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops",
