@@ -169,6 +169,35 @@ def cpu_reference_throughput(max_seconds=12.0, max_pairs=8, K=None, N=None):
                        f"host has {cores} cores)")
 
 
+def auc_parity(dev, pairs=12, N=1000, K=192):
+    """AUC@5/10/20 of the poses recovered from the winning E, CUDA path vs the CPU oracle of the reference,
+    same synthetic pairs and the same injected Gumbel noise (bounded sample: ~5 s of CPU work)."""
+    from differentiable_ransac_b200 import engine, synth
+    from oracle import driver, pose_eval
+
+    thr = WORKLOAD["threshold_px"] / WORKLOAD["focal"]
+    data = [synth.relative_pose_pair(N, (0.35, 0.5, 0.65)[b % 3], seed=900 + b, noise=4e-4, return_pose=True)
+            for b in range(pairs)]
+    matches = torch.stack([d[0] for d in data])
+    logits = synth.logits_regime(pairs, N, "L0", seed=12)
+    noise = synth.gumbel_noise((pairs, K, N), seed=13)
+    ours = engine.ransac_e5_test(matches.to(dev), logits.to(dev), K, torch.full((pairs,), thr, device=dev),
+                                 noise=noise.to(dev), want_scores=True)
+    e_ours, e_ref, same = [], [], 0
+    for b in range(pairs):
+        _, _, _, R, t = data[b]
+        ref = driver.test_loop(matches[b], logits[b], [noise[b]], thr)
+        same += int(int(ours["best_hyp"][b]) == ref["best_idx"] // 10)
+        e_ours.append(max(pose_eval.pose_error_deg(ours["best_model"][b].cpu().numpy(), matches[b].numpy(), R, t,
+                                                   ours["mask"][b].cpu().numpy())))
+        e_ref.append(max(pose_eval.pose_error_deg(ref["best_model"].numpy(), matches[b].numpy(), R, t,
+                                                  ref["best_mask"].numpy())))
+    a, r = pose_eval.auc(e_ours), pose_eval.auc(e_ref)
+    return dict(auc5_10_20_ours=a, auc5_10_20_cpu_reference=r, same_best_hypothesis=f"{same}/{pairs}",
+                sample=f"{pairs} synthetic pairs x {K} hyps x {N} corrs, identical injected Gumbel noise, "
+                       "pose from cv2.recoverPose, AUC as cv_utils.py:528-546")
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -390,6 +419,7 @@ def main():
     )
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_throughput()
+        line["accuracy"] = auc_parity(dev)
     print(json.dumps(line))
     if dist is not None:
         dist.barrier()

@@ -43,11 +43,13 @@ def relative_pose_pair(
     noise: float = 0.0,
     small_motion: bool = True,
     dtype=torch.float32,
+    return_pose: bool = False,
 ):
     """One image pair in normalised camera coordinates.
 
     Returns (matches[N,4] = [x1,y1,x2,y2], E_gt[3,3] with x2^T E x1 = 0 and
-    ||E||_F = 1, inlier_mask[N] bool).
+    ||E||_F = 1, inlier_mask[N] bool) and, with `return_pose`, also (R[3,3], t[3])
+    with X2 = R X1 + t.
     """
     gen = torch.Generator().manual_seed(seed)
     if small_motion:
@@ -76,6 +78,8 @@ def relative_pose_pair(
     E = skew(t) @ rot
     E = E / E.norm()
     matches = torch.cat((x1, x2), dim=1).to(dtype)
+    if return_pose:
+        return matches, E.to(dtype), inl, rot, t
     return matches, E.to(dtype), inl
 
 

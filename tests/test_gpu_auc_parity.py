@@ -1,0 +1,41 @@
+"""AUC@5/10/20 parity (BASELINE.json: "AUC@10 parity"): the CUDA pipeline and the CPU oracle of the
+reference run RANSAC on the same synthetic pairs with the same injected Gumbel noise; the poses are
+recovered from the winning essential matrices and scored with the reference's AUC."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def test_auc_parity_with_the_cpu_reference_algorithm():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from differentiable_ransac_b200 import engine, synth
+    from oracle import driver, pose_eval
+    B, N, K = 24, 1000, 192
+    thr = 0.75 / 800.0
+    pairs = [synth.relative_pose_pair(N, (0.35, 0.5, 0.65)[b % 3], seed=900 + b, noise=4e-4, return_pose=True)
+             for b in range(B)]
+    matches = torch.stack([p[0] for p in pairs])
+    logits = synth.logits_regime(B, N, "L0", seed=12)
+    noise = synth.gumbel_noise((B, K, N), seed=13)
+    ours = engine.ransac_e5_test(matches.to(DEV), logits.to(DEV), K, torch.full((B,), thr, device=DEV),
+                                 noise=noise.to(DEV), want_scores=True)
+    e_ours, e_ref, same_hyp = [], [], 0
+    for b in range(B):
+        _, _, inl, R, t = pairs[b]
+        ref = driver.test_loop(matches[b], logits[b], [noise[b]], thr)
+        same_hyp += int(int(ours["best_hyp"][b]) == ref["best_idx"] // 10)
+        e_ours.append(max(pose_eval.pose_error_deg(ours["best_model"][b].cpu().numpy(), matches[b].numpy(), R, t,
+                                                   ours["mask"][b].cpu().numpy())))
+        e_ref.append(max(pose_eval.pose_error_deg(ref["best_model"].numpy(), matches[b].numpy(), R, t,
+                                                  ref["best_mask"].numpy())))
+    auc_ours, auc_ref = pose_eval.auc(e_ours), pose_eval.auc(e_ref)
+    # identical samples -> the same winning hypothesis on (nearly) every pair, hence the same AUC
+    assert same_hyp >= B - 2, (same_hyp, B)
+    for a, r in zip(auc_ours, auc_ref):
+        assert abs(a - r) <= 1.0 / B + 1e-6, (auc_ours, auc_ref)          # at most one pair changes a 5-degree bin
+    assert auc_ours[1] >= auc_ref[1] - 1.0 / B
+    assert np.median(np.abs(np.array(e_ours) - np.array(e_ref))) < 0.2      # degrees
