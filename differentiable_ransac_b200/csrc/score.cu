@@ -48,38 +48,14 @@ __device__ __forceinline__ Sampson sampson(const float* m, float x1, float y1, f
     return s;
 }
 
-// Everything of the Sampson / MSAC term that is only needed when the point can score at all:
-// f = M^T x2, J = e0^2 + e1^2 + f0^2 + f1^2, t = max(0, 1 - r^2 / (J thr^2)) for two points at once.
-__device__ __forceinline__ pk2 msac_tail(const pk2* mp, pk2 X2, pk2 Y2, pk2 E0, pk2 E1, pk2 R2, pk2 neg_inv, pk2 one) {
-    const pk2 u0 = pk2_fma_v(mp[3], Y2, mp[6]);
-    const pk2 u1 = pk2_fma_v(mp[4], Y2, mp[7]);
-    const pk2 F0 = pk2_fma_v(mp[0], X2, u0);
-    const pk2 F1 = pk2_fma_v(mp[1], X2, u1);
-    const pk2 j0 = pk2_mul_v(F1, F1);
-    const pk2 j1 = pk2_fma_v(F0, F0, j0);
-    const pk2 j2 = pk2_fma_v(E1, E1, j1);
-    const pk2 J = pk2_fma_v(E0, E0, j2);
-    float jl, jh, tl, th;
-    pk2_split(J, jl, jh);
-    const pk2 U = pk2_mul(R2, pk2_make(rcp_approx(jl), rcp_approx(jh)));
-    pk2_split(pk2_fma(U, neg_inv, one), tl, th);
-    return pk2_make(fmaxf(tl, 0.f), fmaxf(th, 0.f));
-}
-
-// MODE 0: compiler-scheduled packed loop.  MODE 1: hand-grouped packed loop.  MODE 2 (default): MODE 1 plus
-// an exact early-out -- J <= ||M||_F^2 (|x1h|^2 + |x2h|^2), so a point with r^2 >= thr^2 ||M||_F^2 (|x1h|^2 +
-// |x2h|^2) contributes exactly 0 and its denominator is never formed.  The branch is warp-wide (vote), the
-// scores are bit-identical to MODE 1.
-template <int MODE>
+template <bool SCHED>
 __global__ void __launch_bounds__(kMsacThreads)
 score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ models,
                   const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
                   int M, int N, float* __restrict__ scores, unsigned long long* __restrict__ best_packed) {
     __shared__ __align__(128) float tiles[2 * kMsacTile * 4];
-    __shared__ __align__(8) float2 pnorm[kMsacTile / 2];   // |x1h|^2 + |x2h|^2 of the two points of each pair
     __shared__ __align__(8) uint64_t bars[2];
     __shared__ unsigned long long warp_best[kMsacThreads / 32];
-    constexpr bool SCHED = MODE >= 1;
     // blockIdx.x = pair (fastest in dispatch order), blockIdx.y = model block: the live CTAs of every
     // pair are dispatched before the empty tail of the worst-case grid
     const int b = blockIdx.x;
@@ -105,11 +81,6 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     for (int i = 0; i < 9; ++i) mp[i] = pk2_splat(m[i]);
     const pk2 neg_inv = pk2_splat(-inv_thr2), one = pk2_splat(1.f);
     pk2 acc = pk2_splat(0.f), accB = pk2_splat(0.f);
-    float fn2 = 0.f;
-    DRB_UNROLL
-    for (int i = 0; i < 9; ++i) fn2 = fmaf(m[i], m[i], fn2);
-    // 0.1 % slack covers the rounding of the bound itself; NaN models make `need` false and score 0 either way
-    const pk2 neg_bound = pk2_splat(-1.001f * t * t * fn2);
 
     TilePipe<4, kMsacTile> pipe(tiles, bars, matches + (size_t)b * N * 4, N);
     pipe.prologue();
@@ -123,37 +94,9 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
             const float4 p = tile[2 * i], q = tile[2 * i + 1];
             tile[2 * i] = make_float4(p.x, q.x, p.y, q.y);
             tile[2 * i + 1] = make_float4(p.z, q.z, p.w, q.w);
-            if (MODE == 2)
-                pnorm[i] = make_float2(fmaf(p.x, p.x, fmaf(p.y, p.y, fmaf(p.z, p.z, fmaf(p.w, p.w, 2.f)))),
-                                       fmaf(q.x, q.x, fmaf(q.y, q.y, fmaf(q.z, q.z, fmaf(q.w, q.w, 2.f)))));
         }
         __syncthreads();
-        if (MODE == 2) {
-            // every lane runs the loop (the votes are warp-wide); lanes without a model never vote "need"
-            const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tile);
-            const pk2* pn = reinterpret_cast<const pk2*>(pnorm);
-            for (int i = 0; i < npairs; ++i) {
-                const ulonglong2 a1 = t2[2 * i], a2 = t2[2 * i + 1];
-                const pk2 X1 = a1.x, Y1 = a1.y, X2 = a2.x, Y2 = a2.y;
-                const pk2 t0 = pk2_fma_v(mp[1], Y1, mp[2]);
-                const pk2 t1 = pk2_fma_v(mp[4], Y1, mp[5]);
-                const pk2 t2_ = pk2_fma_v(mp[7], Y1, mp[8]);
-                const pk2 E0 = pk2_fma_v(mp[0], X1, t0);
-                const pk2 E1 = pk2_fma_v(mp[3], X1, t1);
-                const pk2 E2 = pk2_fma_v(mp[6], X1, t2_);
-                const pk2 r0 = pk2_fma_v(Y2, E1, E2);
-                const pk2 R = pk2_fma_v(X2, E0, r0);
-                const pk2 R2 = pk2_mul_v(R, R);
-                const pk2 D = pk2_fma(neg_bound, pn[i], R2);          // r^2 - bound: negative <=> may score
-                const bool need = active && (long long)(D | (D << 32)) < 0;   // sign bit of either half
-                if (__any_sync(0xffffffffu, need)) acc = pk2_add(acc, msac_tail(mp, X2, Y2, E0, E1, R2, neg_inv, one));
-            }
-            if (active && (np & 1)) {
-                const float4 p = tile[np - 1];
-                const Sampson a = sampson(m, p.x, p.y, p.z, p.w);
-                acc0 += fmaxf(fmaf(-(a.r * a.r) * rcp_approx(a.j), inv_thr2, 1.f), 0.f);
-            }
-        } else if (active && SCHED) {
+        if (active && SCHED) {
             // Hand-ordered variant: two point-pairs (A, B) per trip, packed ops pinned in program order so
             // that instructions sharing a source (Y1 three times, X1 three times, Y2 twice, X2 twice) are
             // adjacent and the operand-reuse cache can serve them; groups of A and B alternate so that a
@@ -504,18 +447,17 @@ extern "C" int drb_score_msac(const float* matches, const float* models, const i
     if (!matches || !models || !thr || !best_packed) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || M <= 0 || N <= 0 || (M + kMsacThreads - 1) / kMsacThreads > 65535) return DRB_ERR_BAD_SHAPE;
     dim3 grid(B, (M + kMsacThreads - 1) / kMsacThreads);
-    // DRB_MSAC_MODE = 0 | 1 | 2 selects the inner loop (see score_msac_kernel); kept for A/B measurements
-    static const int mode = []() {
-        const char* e = getenv("DRB_MSAC_MODE");
-        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    // DRB_MSAC_SCHED=0 selects the compiler-scheduled inner loop (kept for A/B measurements)
+    static const bool sched = []() {
+        const char* e = getenv("DRB_MSAC_SCHED");
+        return e == nullptr || e[0] != '0';
     }();
-    cudaStream_t st = (cudaStream_t)stream;
-    if (mode == 2)
-        score_msac_kernel<2><<<grid, kMsacThreads, 0, st>>>(matches, models, count, ids, thr, M, N, scores, best_packed);
-    else if (mode == 1)
-        score_msac_kernel<1><<<grid, kMsacThreads, 0, st>>>(matches, models, count, ids, thr, M, N, scores, best_packed);
+    if (sched)
+        score_msac_kernel<true><<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N,
+                                                                                 scores, best_packed);
     else
-        score_msac_kernel<0><<<grid, kMsacThreads, 0, st>>>(matches, models, count, ids, thr, M, N, scores, best_packed);
+        score_msac_kernel<false><<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N,
+                                                                                  scores, best_packed);
     DRB_CHECK_LAUNCH();
 }
 
