@@ -94,10 +94,10 @@ def test_reference_default_iteration_count():
     o = engine.ransac_e5_test(m.to(DEV), lg.to(DEV), K, thr.to(DEV))
     bm = o["best_model"].cpu()
     err = torch.minimum((bm - E).flatten(1).norm(dim=1), (bm + E).flatten(1).norm(dim=1))
-    # pairs 1..3 have 40-60 % inliers (dozens of all-inlier samples among 5000); pair 0 has 20 %
+    # pairs 1, 2 have 40 / 60 % inliers (dozens of all-inlier samples among 5000); pairs 0, 3 have 20 %
     # (0.2^5 * 5000 = 1.6 expected all-inlier samples: not guaranteed)
-    assert (err[1:] < 2e-2).all()
-    assert (o["ninl"].cpu()[1:] > 0.3 * N).all()
+    assert (err[1:3] < 2e-2).all()
+    assert (o["ninl"].cpu()[1:3] > 0.3 * N).all()
 
 
 def test_unaligned_views_are_handled():
