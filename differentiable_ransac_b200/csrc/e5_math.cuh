@@ -290,24 +290,29 @@ struct ArrayModelSink {
     DRB_HD void operator()(int slot, int i, T v) { m[slot][i] = v; }
 };
 
-// Full solver.  pts[j] = (x1, y1, x2, y2).  `models(slot, i, v)` receives the row-major, unit
-// Frobenius norm solutions in slots 0..n-1 (n = return value = number of real roots; slots >= n
-// are NOT written: the caller pads with the identity).  `M` is the 10 x 20 scratch; it is dead
-// once the z-polynomials have been read out of it, so a sink may alias its storage.
-template <class T, class Mat, class RT, class Sink>
-DRB_HD int e5_solve(const T (*pts)[4], Mat& M, Sink& models, int polish_iters = 2) {
+// The per-sample data every root of the sample needs: the null-space basis, the three z-polynomial
+// equations cx_i x + cy_i y + cq_i = 0 (ascending powers) and their determinant polynomial P.
+// 86 scalars: the device kernel parks them in the thread's scratch column so that ANY lane of the warp
+// can turn one of this sample's root brackets into a model (solver_e5.cu).
+template <class T>
+struct E5Sample {
     T N[4][9];
+    T cx[3][4], cy[3][4], cq[3][5];
+    T P[11];
+};
+static constexpr int kE5SampleScalars = 36 + 12 + 12 + 15 + 11;
+
+// Stage 1: points -> E5Sample.  `M` is the 10 x 20 scratch; it is dead when this returns.
+template <class T, class Mat>
+DRB_HD bool e5_prepare(const T (*pts)[4], Mat& M, E5Sample<T>& S) {
     {
         T rows[5][9];
         DRB_UNROLL
         for (int j = 0; j < 5; ++j) epipolar_row(pts[j][0], pts[j][1], pts[j][2], pts[j][3], rows[j]);
-        null_space_rows<T, 5>(rows, N);
+        null_space_rows<T, 5>(rows, S.N);
     }
-    e5_constraints<T, Mat>(N, M);
+    e5_constraints<T, Mat>(S.N, M);
     bool ok = e5_eliminate<T, Mat>(M);
-
-    // z-polynomials, ascending powers:  cx_i x + cy_i y + cq_i = 0,  i = 0..2
-    T cx[3][4], cy[3][4], cq[3][5];
     DRB_UNROLL
     for (int i = 0; i < 3; ++i) {
         T ra[10], rb[10];
@@ -316,15 +321,14 @@ DRB_HD int e5_solve(const T (*pts)[4], Mat& M, Sink& models, int polish_iters = 
             ra[c] = M(4 + 2 * i, 10 + c);
             rb[c] = M(5 + 2 * i, 10 + c);
         }
-        cx[i][0] = ra[2]; cx[i][1] = ra[1] - rb[2]; cx[i][2] = ra[0] - rb[1]; cx[i][3] = -rb[0];
-        cy[i][0] = ra[5]; cy[i][1] = ra[4] - rb[5]; cy[i][2] = ra[3] - rb[4]; cy[i][3] = -rb[3];
-        cq[i][0] = ra[9]; cq[i][1] = ra[8] - rb[9]; cq[i][2] = ra[7] - rb[8]; cq[i][3] = ra[6] - rb[7];
-        cq[i][4] = -rb[6];
+        S.cx[i][0] = ra[2]; S.cx[i][1] = ra[1] - rb[2]; S.cx[i][2] = ra[0] - rb[1]; S.cx[i][3] = -rb[0];
+        S.cy[i][0] = ra[5]; S.cy[i][1] = ra[4] - rb[5]; S.cy[i][2] = ra[3] - rb[4]; S.cy[i][3] = -rb[3];
+        S.cq[i][0] = ra[9]; S.cq[i][1] = ra[8] - rb[9]; S.cq[i][2] = ra[7] - rb[8]; S.cq[i][3] = ra[6] - rb[7];
+        S.cq[i][4] = -rb[6];
     }
-    // determinant polynomial (degree 10)
-    T P[11];
+    // determinant polynomial (degree 10) of [cx | cy | cq]
     DRB_UNROLL
-    for (int i = 0; i <= 10; ++i) P[i] = T(0);
+    for (int i = 0; i <= 10; ++i) S.P[i] = T(0);
     DRB_UNROLL
     for (int t = 0; t < 3; ++t) {
         const int r = (t == 0) ? 1 : 0;
@@ -336,68 +340,79 @@ DRB_HD int e5_solve(const T (*pts)[4], Mat& M, Sink& models, int polish_iters = 
         DRB_UNROLL
         for (int i = 0; i < 4; ++i) {
             DRB_UNROLL
-            for (int j = 0; j < 4; ++j) mn[i + j] += cx[r][i] * cy[s][j] - cx[s][i] * cy[r][j];
+            for (int j = 0; j < 4; ++j) mn[i + j] += S.cx[r][i] * S.cy[s][j] - S.cx[s][i] * S.cy[r][j];
         }
         DRB_UNROLL
         for (int i = 0; i < 7; ++i) {
             DRB_UNROLL
-            for (int j = 0; j < 5; ++j) P[i + j] += sign * mn[i] * cq[t][j];
+            for (int j = 0; j < 5; ++j) S.P[i + j] += sign * mn[i] * S.cq[t][j];
         }
     }
-    {
-        bool finite = true;
-        DRB_UNROLL
-        for (int i = 0; i <= 10; ++i) finite = finite && (P[i] == P[i]) && (t_abs(P[i]) < T(1e30));
-        ok = ok && finite;
-    }
-    T roots[10];
-    int n = 0;
-    if (ok) {
-        RT Pr[11], rr[10];
-        DRB_UNROLL
-        for (int i = 0; i <= 10; ++i) Pr[i] = RT(P[i]);
-        n = real_roots_deg10<RT>(Pr, rr);
-        for (int i = 0; i < n; ++i) roots[i] = T(rr[i]);
-    }
+    DRB_UNROLL
+    for (int i = 0; i <= 10; ++i) ok = ok && (S.P[i] == S.P[i]) && (t_abs(S.P[i]) < T(1e30));
+    return ok;
+}
 
+// Stage 3: one root z of P -> (x, y) from the best-conditioned pair of the three equations -> Gauss-Newton
+// polish -> unit-norm E.  Returns false when the root has to be dropped.
+template <class T>
+DRB_HD bool e5_model_from_root(const E5Sample<T>& S, T z, int polish_iters, T* E) {
+    T vx[3], vy[3], vq[3];
+    DRB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        vx[i] = ((S.cx[i][3] * z + S.cx[i][2]) * z + S.cx[i][1]) * z + S.cx[i][0];
+        vy[i] = ((S.cy[i][3] * z + S.cy[i][2]) * z + S.cy[i][1]) * z + S.cy[i][0];
+        vq[i] = (((S.cq[i][4] * z + S.cq[i][3]) * z + S.cq[i][2]) * z + S.cq[i][1]) * z + S.cq[i][0];
+    }
+    const T d01 = vx[0] * vy[1] - vx[1] * vy[0];
+    const T d02 = vx[0] * vy[2] - vx[2] * vy[0];
+    const T d12 = vx[1] * vy[2] - vx[2] * vy[1];
+    T x, y;
+    if (t_abs(d01) >= t_abs(d02) && t_abs(d01) >= t_abs(d12)) {
+        x = (vq[1] * vy[0] - vq[0] * vy[1]) / d01;
+        y = (vq[0] * vx[1] - vq[1] * vx[0]) / d01;
+    } else if (t_abs(d02) >= t_abs(d12)) {
+        x = (vq[2] * vy[0] - vq[0] * vy[2]) / d02;
+        y = (vq[0] * vx[2] - vq[2] * vx[0]) / d02;
+    } else {
+        x = (vq[2] * vy[1] - vq[1] * vy[2]) / d12;
+        y = (vq[1] * vx[2] - vq[2] * vx[1]) / d12;
+    }
+    if (!(x == x) || !(y == y) || t_abs(x) > T(1e18) || t_abs(y) > T(1e18)) return false;
+    e5_polish<T>(S.N, x, y, z, polish_iters);
+    T n2 = T(0);
+    DRB_UNROLL
+    for (int i = 0; i < 9; ++i) {
+        E[i] = x * S.N[0][i] + y * S.N[1][i] + z * S.N[2][i] + S.N[3][i];
+        n2 += E[i] * E[i];
+    }
+    if (!(n2 > T(0)) || !(n2 < T(1e37))) return false;
+    const T inv = t_rsqrt(n2);
+    DRB_UNROLL
+    for (int i = 0; i < 9; ++i) E[i] *= inv;
+    return true;
+}
+
+// Full solver, serial composition of the three stages (host harness; the device kernel runs stage 3
+// warp-cooperatively instead).  `models(slot, i, v)` receives the row-major unit-norm solutions in slots
+// 0..n-1 (n = return value; slots >= n are NOT written: the caller pads with the identity).
+template <class T, class Mat, class RT, class Sink>
+DRB_HD int e5_solve(const T (*pts)[4], Mat& M, Sink& models, int polish_iters = 2) {
+    E5Sample<T> S;
+    if (!e5_prepare<T, Mat>(pts, M, S)) return 0;
+    RT Pr[11], blo[10], bhi[10];
+    DRB_UNROLL
+    for (int i = 0; i <= 10; ++i) Pr[i] = RT(S.P[i]);
+    int n0 = 0;
+    const int nb = isolate_deg10<RT>(Pr, blo, bhi, n0);
     int nout = 0;
-    for (int ri = 0; ri < n; ++ri) {
-        T z = roots[ri];
-        T vx[3], vy[3], vq[3];
-        DRB_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            vx[i] = ((cx[i][3] * z + cx[i][2]) * z + cx[i][1]) * z + cx[i][0];
-            vy[i] = ((cy[i][3] * z + cy[i][2]) * z + cy[i][1]) * z + cy[i][0];
-            vq[i] = (((cq[i][4] * z + cq[i][3]) * z + cq[i][2]) * z + cq[i][1]) * z + cq[i][0];
-        }
-        // best-conditioned pair of the three equations
-        const T d01 = vx[0] * vy[1] - vx[1] * vy[0];
-        const T d02 = vx[0] * vy[2] - vx[2] * vy[0];
-        const T d12 = vx[1] * vy[2] - vx[2] * vy[1];
-        T x, y;
-        if (t_abs(d01) >= t_abs(d02) && t_abs(d01) >= t_abs(d12)) {
-            x = (vq[1] * vy[0] - vq[0] * vy[1]) / d01;
-            y = (vq[0] * vx[1] - vq[1] * vx[0]) / d01;
-        } else if (t_abs(d02) >= t_abs(d12)) {
-            x = (vq[2] * vy[0] - vq[0] * vy[2]) / d02;
-            y = (vq[0] * vx[2] - vq[2] * vx[0]) / d02;
-        } else {
-            x = (vq[2] * vy[1] - vq[1] * vy[2]) / d12;
-            y = (vq[1] * vx[2] - vq[2] * vx[1]) / d12;
-        }
-        if (!(x == x) || !(y == y) || t_abs(x) > T(1e18) || t_abs(y) > T(1e18)) continue;
-        e5_polish<T>(N, x, y, z, polish_iters);
+    for (int r = 0; r < nb; ++r) {
+        RT zr;
+        if (!root_from_bracket<RT>(Pr, r >= n0, blo[r], bhi[r], zr)) continue;
         T E[9];
-        T n2 = T(0);
+        if (!e5_model_from_root<T>(S, T(zr), polish_iters, E)) continue;
         DRB_UNROLL
-        for (int i = 0; i < 9; ++i) {
-            E[i] = x * N[0][i] + y * N[1][i] + z * N[2][i] + N[3][i];
-            n2 += E[i] * E[i];
-        }
-        if (!(n2 > T(0)) || !(n2 < T(1e37))) continue;
-        const T inv = t_rsqrt(n2);
-        DRB_UNROLL
-        for (int i = 0; i < 9; ++i) models(nout, i, E[i] * inv);
+        for (int i = 0; i < 9; ++i) models(nout, i, E[i]);
         ++nout;
     }
     return nout;

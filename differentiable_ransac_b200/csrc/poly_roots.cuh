@@ -14,6 +14,47 @@
 
 namespace drb {
 
+// p(z) and p'(z) by Horner; p has 11 ascending coefficients.
+template <class T>
+DRB_HD void poly10_eval(const T* p, T z, T& f, T& df) {
+    f = p[10];
+    df = T(0);
+    DRB_UNROLL
+    for (int i = 9; i >= 0; --i) {
+        df = df * z + f;
+        f = f * z + p[i];
+    }
+}
+
+// Safeguarded Newton on p inside a bracket (lo, hi] that holds exactly one simple root.
+template <class T>
+DRB_HD T refine_bracket(const T* p, T lo, T hi) {
+    T flo, fhi, d;
+    poly10_eval(p, lo, flo, d);
+    poly10_eval(p, hi, fhi, d);
+    T z = T(0.5) * (lo + hi);
+    if ((flo < T(0)) == (fhi < T(0))) return z;  // no sign change (cluster / rounding): keep the midpoint
+    // fp32: the caller polishes every root by Gauss-Newton on the original constraints, so a root
+    // good to ~1e-4 is enough here and the loop stays short; fp64 goes to rounding.
+    const T tol = sizeof(T) == 4 ? T(1e-4) : T(4.8e-16);
+    const int max_it = sizeof(T) == 4 ? 8 : 24;
+    for (int it = 0; it < max_it; ++it) {
+        T f, df;
+        poly10_eval(p, z, f, df);
+        if ((f < T(0)) == (flo < T(0))) {
+            lo = z;
+        } else {
+            hi = z;
+        }
+        T zn = z - f / df;
+        if (!(zn > lo && zn < hi)) zn = T(0.5) * (lo + hi);
+        const T dz = t_abs(zn - z);
+        z = zn;
+        if (dz <= tol * t_max(t_abs(z), T(1e-3))) break;
+    }
+    return z;
+}
+
 template <class T>
 struct SturmChain10 {
     // f_{i-1} = (a[i] z + b[i]) f_i - m[i] f_{i+1},  i = 1..9  (every f_i positively rescaled)
@@ -116,43 +157,10 @@ struct SturmChain10 {
 #endif
     }
 
-    DRB_HD void eval(T z, T& f, T& df) const {
-        f = p[10];
-        df = T(0);
-        DRB_UNROLL
-        for (int i = 9; i >= 0; --i) {
-            df = df * z + f;
-            f = f * z + p[i];
-        }
-    }
+    DRB_HD void eval(T z, T& f, T& df) const { poly10_eval<T>(p, z, f, df); }
 
     // Safeguarded Newton on p inside a bracket (lo, hi] that holds exactly one simple root.
-    DRB_HD T refine(T lo, T hi) const {
-        T flo, fhi, d;
-        eval(lo, flo, d);
-        eval(hi, fhi, d);
-        T z = T(0.5) * (lo + hi);
-        if ((flo < T(0)) == (fhi < T(0))) return z;  // no sign change (cluster / rounding): keep the midpoint
-        // fp32: the caller polishes every root by Gauss-Newton on the original constraints, so a root
-        // good to ~1e-4 is enough here and the (warp-divergent) loop stays short; fp64 goes to rounding.
-        const T tol = sizeof(T) == 4 ? T(1e-4) : T(4.8e-16);
-        const int max_it = sizeof(T) == 4 ? 8 : 24;
-        for (int it = 0; it < max_it; ++it) {
-            T f, df;
-            eval(z, f, df);
-            if ((f < T(0)) == (flo < T(0))) {
-                lo = z;
-            } else {
-                hi = z;
-            }
-            T zn = z - f / df;
-            if (!(zn > lo && zn < hi)) zn = T(0.5) * (lo + hi);
-            const T dz = t_abs(zn - z);
-            z = zn;
-            if (dz <= tol * t_max(t_abs(z), T(1e-3))) break;
-        }
-        return z;
-    }
+    DRB_HD T refine(T lo, T hi) const { return refine_bracket<T>(p, lo, hi); }
 
     // Real roots in (-1, 1]; returns how many were written to out[0..max_out).
     // Phase 1 -- the same work for every thread (no divergence inside a warp): Sturm counts on a
@@ -160,6 +168,14 @@ struct SturmChain10 {
     // several is split by Sturm bisection (uncommon).  Phase 2 refines each bracket by Newton.
     static constexpr int kGrid = 16;
     DRB_HD int roots_unit(T* out, int max_out) const {
+        T blo[10], bhi[10];
+        const int nb = brackets_unit(blo, bhi, max_out);
+        for (int r = 0; r < nb; ++r) out[r] = refine(blo[r], bhi[r]);
+        return nb;
+    }
+
+    // Phase 1 only: brackets (blo[r], bhi[r]], each holding one real root (or a cluster).
+    DRB_HD int brackets_unit(T* blo, T* bhi, int max_out) const {
         // roots per cell, 4 bits each (a cell holds at most 10); rolled loops keep the code small --
         // this routine is instruction-cache bound when unrolled
         unsigned long long cells = 0ull;
@@ -177,7 +193,6 @@ struct SturmChain10 {
                 prev = cur;
             }
         }
-        T blo[10], bhi[10];
         int nb = 0;
         int c_left = c_first;  // Sturm count at the left edge of the current cell
 #if defined(__CUDA_ARCH__)
@@ -214,10 +229,51 @@ struct SturmChain10 {
             }
             c_left -= n;
         }
-        for (int r = 0; r < nb; ++r) out[r] = refine(blo[r], bhi[r]);
         return nb;
     }
 };
+
+// Root isolation only, both domains: brackets 0..n0-1 are intervals of z on p (|z| <= 1), brackets n0..nb-1
+// are intervals of w = 1/z on the reversed polynomial.  Returns nb (<= 10) and n0.
+template <class T>
+DRB_HD int isolate_deg10(const T* coef, T* blo, T* bhi, int& n0) {
+    int nb = 0;
+    n0 = 0;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
+    for (int dom = 0; dom < 2; ++dom) {
+        T c[11];
+        DRB_UNROLL
+        for (int i = 0; i <= 10; ++i) c[i] = dom ? coef[10 - i] : coef[i];
+        SturmChain10<T> s;
+        s.build(c);
+        nb += s.brackets_unit(blo + nb, bhi + nb, 10 - nb);
+        if (dom == 0) n0 = nb;
+    }
+    return nb;
+}
+
+// Refine bracket r of isolate_deg10 into a root z of the ORIGINAL polynomial; false if it must be dropped.
+template <class T>
+DRB_HD bool root_from_bracket(const T* coef, bool reversed, T lo, T hi, T& z) {
+    T c[11];
+    T sc = T(0);
+    DRB_UNROLL
+    for (int i = 0; i <= 10; ++i) sc = t_max(sc, t_abs(coef[i]));
+    const T inv = sc > T(0) ? T(1) / sc : T(1);
+    DRB_UNROLL
+    for (int i = 0; i <= 10; ++i) c[i] = (reversed ? coef[10 - i] : coef[i]) * inv;
+    const T w = refine_bracket<T>(c, lo, hi);
+    if (!reversed) {
+        z = w;
+        return true;
+    }
+    const T aw = t_abs(w);
+    if (!(aw < T(1)) || !(aw > T(1e-7))) return false;
+    z = T(1) / w;
+    return true;
+}
 
 // All real roots of sum_i coef[i] z^i (degree <= 10).  Returns the count (<= 10).
 template <class T>

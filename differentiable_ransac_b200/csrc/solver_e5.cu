@@ -1,6 +1,6 @@
-// Five-point essential-matrix kernels: one hypothesis per thread, the 10 x 20
-// constraint matrix of every thread resident in shared memory (column-interleaved,
-// bank-conflict free), everything else in registers.  See e5_math.cuh for the math
+// Five-point essential-matrix kernels: one hypothesis per thread for the per-sample stages (the
+// 10 x 20 constraint matrix of every thread resident in shared memory, column-interleaved and
+// bank-conflict free), one ROOT per lane for the per-root stage.  See e5_math.cuh for the math
 // and the reference lines it replaces.
 #include <cuda_runtime.h>
 
@@ -40,24 +40,159 @@ __device__ __forceinline__ void load_minimal5(const float* __restrict__ matches,
     }
 }
 
+// Layout of a thread's scratch column (200 floats, element e at base[e * kE5Threads]) after stage 1:
+//   [0, 90)    solutions of this sample, slot * 9 + i            (aliases rows 0-4 of the dead 10 x 20 matrix)
+//   [90, 176)  E5Sample: N[4][9], cx[3][4], cy[3][4], cq[3][5], P[11]
+//   [176, 186) bracket lower ends,  [186, 196) bracket upper ends
+//   196 number of brackets, 197 number of brackets of the |z| <= 1 domain, 198 valid-slot bit mask
+constexpr int kColSample = 90, kColLo = 176, kColHi = 186, kColNb = 196, kColN0 = 197, kColMask = 198;
+
+__device__ __forceinline__ void park_sample(float* col, const E5Sample<float>& S) {
+    int e = kColSample;
+    DRB_UNROLL
+    for (int a = 0; a < 4; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 9; ++i) col[(e++) * kE5Threads] = S.N[a][i];
+    }
+    DRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) col[(e++) * kE5Threads] = S.cx[a][i];
+    }
+    DRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) col[(e++) * kE5Threads] = S.cy[a][i];
+    }
+    DRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 5; ++i) col[(e++) * kE5Threads] = S.cq[a][i];
+    }
+    DRB_UNROLL
+    for (int i = 0; i < 11; ++i) col[(e++) * kE5Threads] = S.P[i];
+}
+
+__device__ __forceinline__ void fetch_sample(const float* col, E5Sample<float>& S) {
+    int e = kColSample;
+    DRB_UNROLL
+    for (int a = 0; a < 4; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 9; ++i) S.N[a][i] = col[(e++) * kE5Threads];
+    }
+    DRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) S.cx[a][i] = col[(e++) * kE5Threads];
+    }
+    DRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) S.cy[a][i] = col[(e++) * kE5Threads];
+    }
+    DRB_UNROLL
+    for (int a = 0; a < 3; ++a) {
+        DRB_UNROLL
+        for (int i = 0; i < 5; ++i) S.cq[a][i] = col[(e++) * kE5Threads];
+    }
+    DRB_UNROLL
+    for (int i = 0; i < 11; ++i) S.P[i] = col[(e++) * kE5Threads];
+}
+
+// Stage 1 + 2 (null space, constraints, elimination, z-polynomials, root isolation) run one sample per
+// thread.  Stage 3 (Newton refinement of a bracket, back-substitution, Gauss-Newton polish, normalisation)
+// is a per-ROOT job and samples have 0..10 roots, so leaving it per-thread means a warp runs as long as its
+// busiest lane (measured: 7.7 of 32 lanes active).  Instead the warp pools its brackets: every lane parks its
+// sample in shared memory, the brackets of all 32 samples are numbered consecutively, and lane l works on
+// items l, l + 32, ... whoever they belong to.
 __global__ void __launch_bounds__(kE5Threads)
 solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
                 float* __restrict__ models, int32_t* __restrict__ nsol, float* __restrict__ cmodels,
                 int32_t* __restrict__ cids, int32_t* __restrict__ ccount) {
     extern __shared__ float smem[];
+    __shared__ int wprefix[kE5Threads / 32][33];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long row = (long long)blockIdx.x * kE5Threads + threadIdx.x;
-    if (row >= (long long)B * K) return;
-    const int b = (int)(row / K);
-    const int k = (int)(row % K);
-    float p[5][4];
-    load_minimal5(matches, idx, row, b, N, p);
-    SmemMat M{smem + threadIdx.x};
-    // The solutions are staged in this thread's own scratch column (dead once the z-polynomials have
-    // been read out), so the dense and the compact copies below read shared memory, not the global
-    // memory that was just written.
-    SmemSink sink{smem + threadIdx.x};
-    const int n = e5_solve<float, SmemMat, float, SmemSink>(p, M, sink, 2);
+    const bool alive = row < (long long)B * K;
+    const int b = alive ? (int)(row / K) : 0;
+    const int k = alive ? (int)(row % K) : 0;
+    float* col = smem + threadIdx.x;
+
+    // ---- stages 1 + 2: this thread's own sample ------------------------------------------------------
+    int nb = 0, n0 = 0;
+    {
+        E5Sample<float> S;
+        float blo[10], bhi[10];
+        bool ok = false;
+        if (alive) {
+            float p[5][4];
+            load_minimal5(matches, idx, row, b, N, p);
+            SmemMat M{col};
+            ok = e5_prepare<float, SmemMat>(p, M, S);
+        }
+        if (ok) nb = isolate_deg10<float>(S.P, blo, bhi, n0);
+        if (nb > 0) {
+            park_sample(col, S);
+            for (int r = 0; r < nb; ++r) {
+                col[(kColLo + r) * kE5Threads] = blo[r];
+                col[(kColHi + r) * kE5Threads] = bhi[r];
+            }
+        }
+        col[kColN0 * kE5Threads] = __int_as_float(n0);
+        col[kColMask * kE5Threads] = __int_as_float(0);
+    }
+    // ---- pool the brackets of the warp ---------------------------------------------------------------
+    int incl = nb;
+    DRB_UNROLL
+    for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += up;
+    }
+    wprefix[warp][lane + 1] = incl;
+    if (lane == 0) wprefix[warp][0] = 0;
+    __syncwarp();
+    const int total = wprefix[warp][32];
+    // ---- stage 3: one bracket per lane per trip ----------------------------------------------------------
+    for (int it = lane; it < total; it += 32) {
+        int lo = 0, hi = 32;                      // owner = largest L with wprefix[L] <= it
+        DRB_UNROLL
+        for (int s_ = 0; s_ < 5; ++s_) {
+            const int mid = (lo + hi) >> 1;
+            if (wprefix[warp][mid] <= it) lo = mid; else hi = mid;
+        }
+        const int owner = lo;
+        const int j = it - wprefix[warp][owner];
+        float* ocol = smem + (warp * 32 + owner);
+        E5Sample<float> S;
+        fetch_sample(ocol, S);
+        const bool reversed = j >= __float_as_int(ocol[kColN0 * kE5Threads]);
+        float z, E[9];
+        bool valid = root_from_bracket<float>(S.P, reversed, ocol[(kColLo + j) * kE5Threads],
+                                              ocol[(kColHi + j) * kE5Threads], z);
+        valid = valid && e5_model_from_root<float>(S, z, 2, E);
+        if (valid) {
+            DRB_UNROLL
+            for (int i = 0; i < 9; ++i) ocol[(j * 9 + i) * kE5Threads] = E[i];
+            atomicOr(reinterpret_cast<int*>(ocol + kColMask * kE5Threads), 1 << j);
+        }
+    }
+    __syncwarp();
+    if (!alive) return;
+    // ---- epilogue: each thread owns its sample again --------------------------------------------------
+    const int vmask = __float_as_int(col[kColMask * kE5Threads]);
+    int n = 0;
+    for (int j = 0; j < nb; ++j) {                 // close the (rare) holes left by dropped roots
+        if (vmask & (1 << j)) {
+            if (j != n) {
+                DRB_UNROLL
+                for (int i = 0; i < 9; ++i) col[(n * 9 + i) * kE5Threads] = col[(j * 9 + i) * kE5Threads];
+            }
+            ++n;
+        }
+    }
     nsol[row] = n;
+    SmemSink sink{col};
     // reserve the compact-list slots early so the atomic's round trip overlaps the dense write
     int pos = 0;
     if (cmodels != nullptr && n > 0) pos = atomicAdd(ccount + b, n);
