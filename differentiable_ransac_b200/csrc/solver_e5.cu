@@ -12,17 +12,21 @@
 namespace drb {
 
 constexpr int kE5Threads = 64;
-constexpr int kE5SmemBytes = kE5Threads * 200 * sizeof(float);
+// Scratch columns are interleaved with an ODD stride: element e of thread t lives at smem[e * 65 + t], so both
+// "same element, consecutive threads" (the solver) and "same thread, consecutive elements" (the coalesced
+// copy-out) hit 32 different banks.
+constexpr int kE5Stride = kE5Threads + 1;
+constexpr int kE5SmemBytes = kE5Stride * 200 * sizeof(float);
 
 struct SmemMat {
-    float* base;  // smem + tid ; element (r, c) at base[(r * 20 + c) * kE5Threads]
-    __device__ __forceinline__ float& operator()(int r, int c) { return base[(r * 20 + c) * kE5Threads]; }
+    float* base;  // smem + tid ; element (r, c) at base[(r * 20 + c) * kE5Stride]
+    __device__ __forceinline__ float& operator()(int r, int c) { return base[(r * 20 + c) * kE5Stride]; }
 };
 
 struct SmemSink {
-    float* base;  // same column as SmemMat: element e (= slot * 9 + i, e < 90 <= 200) at base[e * kE5Threads]
-    __device__ __forceinline__ void operator()(int slot, int i, float v) { base[(slot * 9 + i) * kE5Threads] = v; }
-    __device__ __forceinline__ float get(int e) const { return base[e * kE5Threads]; }
+    float* base;  // same column as SmemMat: element e (= slot * 9 + i, e < 90 <= 200) at base[e * kE5Stride]
+    __device__ __forceinline__ void operator()(int slot, int i, float v) { base[(slot * 9 + i) * kE5Stride] = v; }
+    __device__ __forceinline__ float get(int e) const { return base[e * kE5Stride]; }
 };
 
 __device__ __forceinline__ void load_minimal5(const float* __restrict__ matches, const int32_t* __restrict__ idx,
@@ -40,7 +44,7 @@ __device__ __forceinline__ void load_minimal5(const float* __restrict__ matches,
     }
 }
 
-// Layout of a thread's scratch column (200 floats, element e at base[e * kE5Threads]) after stage 1:
+// Layout of a thread's scratch column (200 floats, element e at base[e * kE5Stride]) after stage 1:
 //   [0, 90)    solutions of this sample, slot * 9 + i            (aliases rows 0-4 of the dead 10 x 20 matrix)
 //   [90, 176)  E5Sample: N[4][9], cx[3][4], cy[3][4], cq[3][5], P[11]
 //   [176, 186) bracket lower ends,  [186, 196) bracket upper ends
@@ -52,25 +56,25 @@ __device__ __forceinline__ void park_sample(float* col, const E5Sample<float>& S
     DRB_UNROLL
     for (int a = 0; a < 4; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 9; ++i) col[(e++) * kE5Threads] = S.N[a][i];
+        for (int i = 0; i < 9; ++i) col[(e++) * kE5Stride] = S.N[a][i];
     }
     DRB_UNROLL
     for (int a = 0; a < 3; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 4; ++i) col[(e++) * kE5Threads] = S.cx[a][i];
+        for (int i = 0; i < 4; ++i) col[(e++) * kE5Stride] = S.cx[a][i];
     }
     DRB_UNROLL
     for (int a = 0; a < 3; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 4; ++i) col[(e++) * kE5Threads] = S.cy[a][i];
+        for (int i = 0; i < 4; ++i) col[(e++) * kE5Stride] = S.cy[a][i];
     }
     DRB_UNROLL
     for (int a = 0; a < 3; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 5; ++i) col[(e++) * kE5Threads] = S.cq[a][i];
+        for (int i = 0; i < 5; ++i) col[(e++) * kE5Stride] = S.cq[a][i];
     }
     DRB_UNROLL
-    for (int i = 0; i < 11; ++i) col[(e++) * kE5Threads] = S.P[i];
+    for (int i = 0; i < 11; ++i) col[(e++) * kE5Stride] = S.P[i];
 }
 
 __device__ __forceinline__ void fetch_sample(const float* col, E5Sample<float>& S) {
@@ -78,25 +82,25 @@ __device__ __forceinline__ void fetch_sample(const float* col, E5Sample<float>& 
     DRB_UNROLL
     for (int a = 0; a < 4; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 9; ++i) S.N[a][i] = col[(e++) * kE5Threads];
+        for (int i = 0; i < 9; ++i) S.N[a][i] = col[(e++) * kE5Stride];
     }
     DRB_UNROLL
     for (int a = 0; a < 3; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 4; ++i) S.cx[a][i] = col[(e++) * kE5Threads];
+        for (int i = 0; i < 4; ++i) S.cx[a][i] = col[(e++) * kE5Stride];
     }
     DRB_UNROLL
     for (int a = 0; a < 3; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 4; ++i) S.cy[a][i] = col[(e++) * kE5Threads];
+        for (int i = 0; i < 4; ++i) S.cy[a][i] = col[(e++) * kE5Stride];
     }
     DRB_UNROLL
     for (int a = 0; a < 3; ++a) {
         DRB_UNROLL
-        for (int i = 0; i < 5; ++i) S.cq[a][i] = col[(e++) * kE5Threads];
+        for (int i = 0; i < 5; ++i) S.cq[a][i] = col[(e++) * kE5Stride];
     }
     DRB_UNROLL
-    for (int i = 0; i < 11; ++i) S.P[i] = col[(e++) * kE5Threads];
+    for (int i = 0; i < 11; ++i) S.P[i] = col[(e++) * kE5Stride];
 }
 
 // Stage 1 + 2 (null space, constraints, elimination, z-polynomials, root isolation) run one sample per
@@ -135,12 +139,12 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
         if (nb > 0) {
             park_sample(col, S);
             for (int r = 0; r < nb; ++r) {
-                col[(kColLo + r) * kE5Threads] = blo[r];
-                col[(kColHi + r) * kE5Threads] = bhi[r];
+                col[(kColLo + r) * kE5Stride] = blo[r];
+                col[(kColHi + r) * kE5Stride] = bhi[r];
             }
         }
-        col[kColN0 * kE5Threads] = __int_as_float(n0);
-        col[kColMask * kE5Threads] = __int_as_float(0);
+        col[kColN0 * kE5Stride] = __int_as_float(n0);
+        col[kColMask * kE5Stride] = __int_as_float(0);
     }
     // ---- pool the brackets of the warp ---------------------------------------------------------------
     int incl = nb;
@@ -166,49 +170,59 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
         float* ocol = smem + (warp * 32 + owner);
         E5Sample<float> S;
         fetch_sample(ocol, S);
-        const bool reversed = j >= __float_as_int(ocol[kColN0 * kE5Threads]);
+        const bool reversed = j >= __float_as_int(ocol[kColN0 * kE5Stride]);
         float z, E[9];
-        bool valid = root_from_bracket<float>(S.P, reversed, ocol[(kColLo + j) * kE5Threads],
-                                              ocol[(kColHi + j) * kE5Threads], z);
+        bool valid = root_from_bracket<float>(S.P, reversed, ocol[(kColLo + j) * kE5Stride],
+                                              ocol[(kColHi + j) * kE5Stride], z);
         valid = valid && e5_model_from_root<float>(S, z, 2, E);
         if (valid) {
             DRB_UNROLL
-            for (int i = 0; i < 9; ++i) ocol[(j * 9 + i) * kE5Threads] = E[i];
-            atomicOr(reinterpret_cast<int*>(ocol + kColMask * kE5Threads), 1 << j);
+            for (int i = 0; i < 9; ++i) ocol[(j * 9 + i) * kE5Stride] = E[i];
+            atomicOr(reinterpret_cast<int*>(ocol + kColMask * kE5Stride), 1 << j);
         }
     }
     __syncwarp();
-    if (!alive) return;
-    // ---- epilogue: each thread owns its sample again --------------------------------------------------
-    const int vmask = __float_as_int(col[kColMask * kE5Threads]);
+    // ---- each thread owns its sample again: close the (rare) holes left by dropped roots ----------------
     int n = 0;
-    for (int j = 0; j < nb; ++j) {                 // close the (rare) holes left by dropped roots
-        if (vmask & (1 << j)) {
-            if (j != n) {
-                DRB_UNROLL
-                for (int i = 0; i < 9; ++i) col[(n * 9 + i) * kE5Threads] = col[(j * 9 + i) * kE5Threads];
+    {
+        const int vmask = __float_as_int(col[kColMask * kE5Stride]);
+        for (int j = 0; j < nb; ++j) {
+            if (vmask & (1 << j)) {
+                if (j != n) {
+                    DRB_UNROLL
+                    for (int i = 0; i < 9; ++i) col[(n * 9 + i) * kE5Stride] = col[(j * 9 + i) * kE5Stride];
+                }
+                ++n;
             }
-            ++n;
         }
     }
-    nsol[row] = n;
-    SmemSink sink{col};
-    // reserve the compact-list slots early so the atomic's round trip overlaps the dense write
+    if (alive) nsol[row] = n;
+    col[kColNb * kE5Stride] = __int_as_float(n);
+    // compact-list range of this sample: reserved now, its round trip overlaps the dense copy-out below
     int pos = 0;
-    if (cmodels != nullptr && n > 0) pos = atomicAdd(ccount + b, n);
-    float2* dense = reinterpret_cast<float2*>(models + (size_t)row * 90);   // 360 B per row: 8-byte aligned
-    DRB_UNROLL
-    for (int e = 0; e < 45; ++e) {
-        const int e0 = 2 * e, e1 = 2 * e + 1;
-        const float v0 = (e0 / 9 < n) ? sink.get(e0) : (((e0 % 9) % 4 == 0) ? 1.f : 0.f);
-        const float v1 = (e1 / 9 < n) ? sink.get(e1) : (((e1 % 9) % 4 == 0) ? 1.f : 0.f);
-        dense[e] = make_float2(v0, v1);
+    if (alive && cmodels != nullptr && n > 0) pos = atomicAdd(ccount + b, n);
+    __syncthreads();
+    // ---- dense copy-out, coalesced: the CTA's 64 rows x 90 floats are contiguous in global memory ---------
+    {
+        const long long row0 = (long long)blockIdx.x * kE5Threads;
+        const long long rows_here = min((long long)kE5Threads, (long long)B * K - row0);
+        float2* dense = reinterpret_cast<float2*>(models + (size_t)row0 * 90);
+        const int n_pairs = (int)rows_here * 45;
+        for (int g = threadIdx.x; g < n_pairs; g += kE5Threads) {
+            const int owner = g / 45, e0 = (g - owner * 45) * 2, e1 = e0 + 1;
+            const float* oc = smem + owner;
+            const int on = __float_as_int(oc[kColNb * kE5Stride]);
+            const float v0 = (e0 / 9 < on) ? oc[e0 * kE5Stride] : (((e0 % 9) % 4 == 0) ? 1.f : 0.f);
+            const float v1 = (e1 / 9 < on) ? oc[e1 * kE5Stride] : (((e1 % 9) % 4 == 0) ? 1.f : 0.f);
+            dense[g] = make_float2(v0, v1);
+        }
     }
-    if (cmodels != nullptr && n > 0) {
+    // ---- compact list: each sample's models are contiguous (36 n bytes), written by their owner -----------
+    if (alive && cmodels != nullptr && n > 0) {
         float* dst = cmodels + ((size_t)b * K * 10 + pos) * 9;
         for (int s = 0; s < n; ++s) {
             DRB_UNROLL
-            for (int i = 0; i < 9; ++i) dst[s * 9 + i] = sink.get(s * 9 + i);
+            for (int i = 0; i < 9; ++i) dst[s * 9 + i] = col[(s * 9 + i) * kE5Stride];
             cids[(size_t)b * K * 10 + pos + s] = k * 10 + s;
         }
     }
