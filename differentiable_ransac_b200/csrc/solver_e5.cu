@@ -198,9 +198,27 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
     }
     if (alive) nsol[row] = n;
     col[kColNb * kE5Stride] = __int_as_float(n);
-    // compact-list range of this sample: reserved now, its round trip overlaps the dense copy-out below
+    // Compact-list range of this sample.  One atomic per (warp, pair) instead of one per sample: rows are
+    // consecutive, so the lanes of a pair form a contiguous group; the group leader reserves the group's total
+    // and every lane adds its exclusive prefix.  (32 000 same-address atomics were 8 % of the stall samples.)
     int pos = 0;
-    if (alive && cmodels != nullptr && n > 0) pos = atomicAdd(ccount + b, n);
+    if (cmodels != nullptr) {
+        const int key = alive ? b : -1;
+        const unsigned grp = __match_any_sync(FULL, key);
+        int inc = n;
+        DRB_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
+        }
+        const int first = __ffs(grp) - 1, last = 31 - __clz(grp);
+        const int before_group = __shfl_sync(FULL, inc - n, first);
+        const int group_total = __shfl_sync(FULL, inc, last) - before_group;
+        int base = 0;
+        if (lane == first && alive && group_total > 0) base = atomicAdd(ccount + b, group_total);
+        base = __shfl_sync(FULL, base, first);
+        pos = base + (inc - n) - before_group;
+    }
     __syncthreads();
     // ---- dense copy-out, coalesced: the CTA's 64 rows x 90 floats are contiguous in global memory ---------
     {
