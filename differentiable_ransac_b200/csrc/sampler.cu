@@ -18,6 +18,12 @@ namespace drb {
 
 constexpr int kSamplerWarps = 8;
 
+__device__ __forceinline__ float rcp_fast(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 struct KeyQuad {
     float k[4];
 };
@@ -278,6 +284,97 @@ sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
     for (int j = 0; j < S; ++j) idx_out[row * S + j] = chosen[j];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Training forward, in-kernel noise, tau = 1: indices + log-sum-exp + selected keys, with the race
+// formulation for the ranking (rank by log2(u) * exp(-(l - lmax))) and
+//   sum_n exp(l_n + g_n) = exp(lmax) * sum_n w_n / e_n,   w = exp(l - lmax),  e = -ln u,
+// for the normaliser: one log2 and one reciprocal per element instead of two logs, an IEEE add and
+// an online softmax.  Draws the SAME noise as sample_kernel (same Philox counters, same clamp), so
+// the backward (which regenerates it) and the exact kernel agree with it to rounding.
+constexpr int kTrainMaxN = 6016;   // two float tables of N entries in static shared memory (< 48 KB)
+
+template <int S>
+__global__ void __launch_bounds__(kSamplerWarps * 32)
+sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
+                    int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out) {
+    __shared__ __align__(16) float wtab[kTrainMaxN];     // exp(l - lmax)
+    __shared__ __align__(16) float winv[kTrainMaxN];     // exp(lmax - l)
+    __shared__ float red[kSamplerWarps];
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int b = blockIdx.y;
+    const int k = blockIdx.x * kSamplerWarps + warp;
+    const float* logits_b = logits + (size_t)b * N;
+    const int n_pad = ((N + 127) / 128) * 128;
+    float mx = -INFINITY;
+    for (int n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, __ldg(logits_b + n));
+    DRB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(FULL, mx, o));
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    mx = red[0];
+    DRB_UNROLL
+    for (int w = 1; w < kSamplerWarps; ++w) mx = fmaxf(mx, red[w]);
+    for (int n = threadIdx.x; n < n_pad; n += blockDim.x) {
+        const float d = n < N ? __ldg(logits_b + n) - mx : -INFINITY;
+        wtab[n] = __expf(d);                 // 0 for the padding
+        winv[n] = __expf(-d);                // +inf for the padding: log2(u) * inf = -inf never ranks
+    }
+    __syncthreads();
+    if (k >= K) return;
+    const long long row = (long long)b * K + k;
+    float top_v = -INFINITY, thr = -INFINITY, zacc = 0.f;
+    int top_i = -1;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+    for (int n0 = lane * 4; n0 < n_pad; n0 += 128) {
+        const Philox4 r = philox4x32_10((uint32_t)(n0 >> 2), (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
+        const float4 wi = *reinterpret_cast<const float4*>(winv + n0);
+        const float4 ww = *reinterpret_cast<const float4*>(wtab + n0);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        const float wiv[4] = {wi.x, wi.y, wi.z, wi.w}, wwv[4] = {ww.x, ww.y, ww.z, ww.w};
+        float t[4];
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) {
+            const float lg = fminf(lg2_approx(uniform_from_bits(rr[i])), -1.4426950408889634e-10f);
+            t[i] = lg * wiv[i];
+            zacc = fmaf(wwv[i], rcp_fast(lg), zacc);       // sum of w / log2(u)  (negative)
+        }
+        float bv = t[0];
+        int bi = 0;
+        DRB_UNROLL
+        for (int i = 1; i < 4; ++i)
+            if (t[i] > bv) { bv = t[i]; bi = i; }
+        merge_candidates<S>(bv, n0 + bi, top_v, top_i, thr, lane);
+        float second = -INFINITY;
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) second = (i == bi) ? second : fmaxf(second, t[i]);
+        if (__any_sync(FULL, second > thr)) {
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) merge_candidates<S>((i == bi) ? -INFINITY : t[i], n0 + i, top_v, top_i, thr, lane);
+        }
+    }
+    DRB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) zacc += __shfl_xor_sync(FULL, zacc, o);
+    // Z = sum w / e = -(1 / ln 2) * zacc ;  lse = lmax + ln Z
+    if (lane == 0) lse_out[row] = mx + __logf(-1.4426950408889634f * zacc);
+    int rank = 0;
+    DRB_UNROLL
+    for (int j = 0; j < S; ++j) {
+        const int oj = __shfl_sync(FULL, top_i, j);
+        rank += (oj < top_i) ? 1 : 0;
+    }
+    if (lane < S) {
+        idx_out[(size_t)row * S + rank] = top_i;
+        // key of the selected point, from the same draw: l + g with g = -ln(e)
+        const Philox4 r = philox4x32_10((uint32_t)(top_i >> 2), (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        uint32_t bits = rr[0];
+        DRB_UNROLL
+        for (int i = 1; i < 4; ++i) bits = ((top_i & 3) == i) ? rr[i] : bits;
+        sel_key_out[(size_t)row * S + rank] = __ldg(logits_b + top_i) + gumbel_from_bits(bits);
+    }
+}
+
 template <int S>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_kernel(const float* __restrict__ logits, const float* __restrict__ noise, uint64_t seed, uint64_t offset,
@@ -404,6 +501,30 @@ sample_bwd_dense_kernel(const float* __restrict__ logits, const float* __restric
     const float* logits_b = logits + (size_t)b * N;
     const bool vec = (N % 4 == 0);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    if (noise == nullptr && tau == 1.0f) {
+        // Fast path (in-kernel noise, tau = 1):  y[k,n] = exp(l_n + g - lse_k) = exp(l_n - c) * exp(c - lse_k) / e,
+        // e = -ln u the exponential behind the Gumbel draw; c = the largest of this thread's four logits, so the
+        // per-element work is one log2 and one reciprocal instead of two logs and an exp.
+        float l4[4], w4[4];
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) l4[i] = (n0 + i < N) ? __ldg(logits_b + n0 + i) : -INFINITY;
+        const float c0 = fmaxf(fmaxf(l4[0], l4[1]), fmaxf(l4[2], l4[3]));
+        DRB_UNROLL
+        for (int i = 0; i < 4; ++i) w4[i] = (n0 + i < N) ? __expf(l4[i] - c0) : 0.f;
+        const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+        for (int k = k_begin; k < k_end; ++k) {
+            const size_t row = (size_t)b * K + k;
+            const Philox4 r = philox4x32_10((uint32_t)(n0 >> 2), (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
+            // exp(c - lse_k) * c_k / ln 2, with the sign of 1 / log2(u) (< 0) folded in
+            const float skc = -1.4426950408889634f * __expf(c0 - __ldg(lse + row)) * __ldg(ck + row);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const float lg = fminf(lg2_approx(uniform_from_bits(rr[i])), -1.4426950408889634e-10f);  // e >= 1e-10
+                acc[i] = fmaf(w4[i] * rcp_fast(lg), skc, acc[i]);
+            }
+        }
+    } else
     for (int k = k_begin; k < k_end; ++k) {
         const size_t row = (size_t)b * K + k;
         const float* noise_row = noise ? noise + row * N : nullptr;
@@ -434,6 +555,24 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     const long long rows = (long long)B * K;
     const unsigned grid = (unsigned)((rows + kSamplerWarps - 1) / kSamplerWarps);
     const dim3 block(kSamplerWarps * 32);
+    if (!noise && lse && sel_key && !noise_out && tau == 1.0f && N <= kTrainMaxN && B <= 65535) {
+        // training forward with in-kernel noise at tau = 1
+        const dim3 tgrid((K + kSamplerWarps - 1) / kSamplerWarps, B);
+#define DRB_LAUNCH_TRAIN(S_)                                                                                 \
+    case S_:                                                                                                 \
+        sample_train_kernel<S_><<<tgrid, block, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key);      \
+        break;
+        switch (s) {
+            DRB_LAUNCH_TRAIN(3)
+            DRB_LAUNCH_TRAIN(5)
+            DRB_LAUNCH_TRAIN(7)
+            DRB_LAUNCH_TRAIN(8)
+            default:
+                return DRB_ERR_UNSUPPORTED;
+        }
+#undef DRB_LAUNCH_TRAIN
+        return check_launch();
+    }
     if (!noise && !lse && !sel_key && !noise_out && N <= kRaceMaxN && B <= 65535) {
         // test mode: only the indices are wanted -> exponential-race fast path
         const dim3 rgrid((K + kSamplerWarps - 1) / kSamplerWarps, B);

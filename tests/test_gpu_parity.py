@@ -79,11 +79,24 @@ def test_sampler_race_equals_exact(drb):
         B = 4
         logits = drb.synth.logits_regime(B, N, regime, seed=s).to(DEV)
         fast, _, _, _ = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3)
-        exact, _, _, _ = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3, want_lse=True)
+        # want_noise forces the exact-key kernel (the one the oracle replays)
+        exact, lse_x, key_x, noise = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3, want_lse=True,
+                                                    want_noise=True)
         same_rows = (fast == exact).all(dim=-1).float().mean().item()
         assert same_rows >= 0.999, (s, N, K, same_rows)
         assert (fast[..., 1:] > fast[..., :-1]).all()          # ascending, distinct
         assert int(fast.min()) >= 0 and int(fast.max()) < N
+        # training fast path (tau = 1, in-kernel noise): same draw, same sets, same normaliser and keys
+        tr, lse_t, key_t, _ = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3, want_lse=True)
+        rows = (tr == exact).all(dim=-1)
+        assert rows.float().mean().item() >= 0.999
+        assert torch.allclose(lse_t, lse_x, rtol=2e-5, atol=2e-5)
+        assert torch.allclose(key_t[rows], key_x[rows], rtol=1e-5, atol=1e-5)
+        # ... and the backward's fast path (noise regenerated) against the generic one (noise re-read)
+        g_sel = torch.randn(B, K, s, device=DEV)
+        g_fast = drb.ops.sample_backward(logits, exact, lse_x, key_x, g_sel, 1.0, None, 11, 3)
+        g_gen = drb.ops.sample_backward(logits, exact, lse_x, key_x, g_sel, 1.0, noise, 11, 3)
+        assert (g_fast - g_gen).norm() <= 1e-4 * g_gen.norm()
 
 
 def test_set_sampler_same_law_as_gumbel_topk(drb):
