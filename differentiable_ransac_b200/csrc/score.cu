@@ -224,130 +224,6 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     }
 }
 
-// Two MODELS per thread (64 models per one-warp CTA).  Every correspondence operand of the packed sequence is
-// then used by two adjacent instructions (model A, model B), which is what the register-file operand-reuse
-// cache needs; the FMA pipe is register-read bound here (profiles/r1_notes.md).
-__global__ void __launch_bounds__(kMsacThreads)
-score_msac2_kernel(const float* __restrict__ matches, const float* __restrict__ models,
-                   const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
-                   int M, int N, float* __restrict__ scores, unsigned long long* __restrict__ best_packed) {
-    __shared__ __align__(128) float tiles[2 * kMsacTile * 4];
-    __shared__ __align__(8) uint64_t bars[2];
-    const int b = blockIdx.x;
-    const int cnt = count ? min(count[b], M) : M;
-    const int m0 = blockIdx.y * (2 * kMsacThreads);
-    if (m0 >= cnt) return;
-    const int miA = m0 + threadIdx.x, miB = m0 + kMsacThreads + threadIdx.x;
-    const bool actA = miA < cnt, actB = miB < cnt;
-    pk2 a[9], c[9];   // model A / model B coefficients as scalar-broadcast packed operands
-    {
-        const float* sa = models + ((size_t)b * M + (actA ? miA : m0)) * 9;
-        const float* sb = models + ((size_t)b * M + (actB ? miB : m0)) * 9;
-        DRB_UNROLL
-        for (int i = 0; i < 9; ++i) {
-            a[i] = pk2_splat(__ldg(sa + i));
-            c[i] = pk2_splat(__ldg(sb + i));
-        }
-    }
-    const float t = 1.5f * __ldg(thr + b);
-    const float inv_thr2 = 1.f / (t * t);
-    const pk2 neg_inv = pk2_splat(-inv_thr2), one = pk2_splat(1.f);
-    pk2 accA = pk2_splat(0.f), accB = pk2_splat(0.f);
-    float tailA = 0.f, tailB = 0.f;
-
-    TilePipe<4, kMsacTile> pipe(tiles, bars, matches + (size_t)b * N * 4, N);
-    pipe.prologue();
-    for (int tI = 0; tI < pipe.n_tiles; ++tI) {
-        float4* tile = reinterpret_cast<float4*>(const_cast<float*>(pipe.acquire(tI)));
-        const int np = pipe.tile_items(tI);
-        const int npairs = np >> 1;
-        for (int i = threadIdx.x; i < npairs; i += kMsacThreads) {
-            const float4 p = tile[2 * i], q = tile[2 * i + 1];
-            tile[2 * i] = make_float4(p.x, q.x, p.y, q.y);
-            tile[2 * i + 1] = make_float4(p.z, q.z, p.w, q.w);
-        }
-        __syncthreads();
-        const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tile);
-#pragma unroll 1
-        for (int i = 0; i < npairs; ++i) {
-            const ulonglong2 l1 = t2[2 * i], l2 = t2[2 * i + 1];
-            const pk2 X1 = l1.x, Y1 = l1.y, X2 = l2.x, Y2 = l2.y;
-            const pk2 At0 = pk2_fma_v(a[1], Y1, a[2]);
-            const pk2 Bt0 = pk2_fma_v(c[1], Y1, c[2]);
-            const pk2 At1 = pk2_fma_v(a[4], Y1, a[5]);
-            const pk2 Bt1 = pk2_fma_v(c[4], Y1, c[5]);
-            const pk2 At2 = pk2_fma_v(a[7], Y1, a[8]);
-            const pk2 Bt2 = pk2_fma_v(c[7], Y1, c[8]);
-            const pk2 AE0 = pk2_fma_v(a[0], X1, At0);
-            const pk2 BE0 = pk2_fma_v(c[0], X1, Bt0);
-            const pk2 AE1 = pk2_fma_v(a[3], X1, At1);
-            const pk2 BE1 = pk2_fma_v(c[3], X1, Bt1);
-            const pk2 AE2 = pk2_fma_v(a[6], X1, At2);
-            const pk2 BE2 = pk2_fma_v(c[6], X1, Bt2);
-            const pk2 Au0 = pk2_fma_v(a[3], Y2, a[6]);
-            const pk2 Bu0 = pk2_fma_v(c[3], Y2, c[6]);
-            const pk2 Au1 = pk2_fma_v(a[4], Y2, a[7]);
-            const pk2 Bu1 = pk2_fma_v(c[4], Y2, c[7]);
-            const pk2 Ar0 = pk2_fma_v(Y2, AE1, AE2);
-            const pk2 Br0 = pk2_fma_v(Y2, BE1, BE2);
-            const pk2 AF0 = pk2_fma_v(a[0], X2, Au0);
-            const pk2 BF0 = pk2_fma_v(c[0], X2, Bu0);
-            const pk2 AF1 = pk2_fma_v(a[1], X2, Au1);
-            const pk2 BF1 = pk2_fma_v(c[1], X2, Bu1);
-            const pk2 AR = pk2_fma_v(X2, AE0, Ar0);
-            const pk2 BR = pk2_fma_v(X2, BE0, Br0);
-            const pk2 Aj0 = pk2_mul_v(AF1, AF1);
-            const pk2 Bj0 = pk2_mul_v(BF1, BF1);
-            const pk2 Aj1 = pk2_fma_v(AF0, AF0, Aj0);
-            const pk2 Bj1 = pk2_fma_v(BF0, BF0, Bj0);
-            const pk2 Aj2 = pk2_fma_v(AE1, AE1, Aj1);
-            const pk2 Bj2 = pk2_fma_v(BE1, BE1, Bj1);
-            const pk2 AJ = pk2_fma_v(AE0, AE0, Aj2);
-            const pk2 BJ = pk2_fma_v(BE0, BE0, Bj2);
-            const pk2 AR2 = pk2_mul_v(AR, AR);
-            const pk2 BR2 = pk2_mul_v(BR, BR);
-            float ajl, ajh, bjl, bjh;
-            pk2_split(AJ, ajl, ajh);
-            pk2_split(BJ, bjl, bjh);
-            const pk2 AU = pk2_mul(AR2, pk2_make(rcp_approx(ajl), rcp_approx(ajh)));
-            const pk2 BU = pk2_mul(BR2, pk2_make(rcp_approx(bjl), rcp_approx(bjh)));
-            float atl, ath, btl, bth;
-            pk2_split(pk2_fma(AU, neg_inv, one), atl, ath);
-            pk2_split(pk2_fma(BU, neg_inv, one), btl, bth);
-            accA = pk2_add(accA, pk2_make(fmaxf(atl, 0.f), fmaxf(ath, 0.f)));
-            accB = pk2_add(accB, pk2_make(fmaxf(btl, 0.f), fmaxf(bth, 0.f)));
-        }
-        if (np & 1) {  // odd tail of the last tile (never interleaved)
-            const float4 p = tile[np - 1];
-            float ma[9], mb[9], dummy;
-            DRB_UNROLL
-            for (int i = 0; i < 9; ++i) { pk2_split(a[i], ma[i], dummy); pk2_split(c[i], mb[i], dummy); }
-            const Sampson sa = sampson(ma, p.x, p.y, p.z, p.w), sb = sampson(mb, p.x, p.y, p.z, p.w);
-            tailA += fmaxf(fmaf(-(sa.r * sa.r) * rcp_approx(sa.j), inv_thr2, 1.f), 0.f);
-            tailB += fmaxf(fmaf(-(sb.r * sb.r) * rcp_approx(sb.j), inv_thr2, 1.f), 0.f);
-        }
-        pipe.release(tI);
-    }
-    float lo, hi;
-    pk2_split(accA, lo, hi);
-    const float scoreA = tailA + lo + hi;
-    pk2_split(accB, lo, hi);
-    const float scoreB = tailB + lo + hi;
-    if (scores) {
-        if (actA) scores[(size_t)b * M + miA] = scoreA;
-        if (actB) scores[(size_t)b * M + miB] = scoreB;
-    }
-    const unsigned long long kA = actA ? pack_best(scoreA, ids ? ids[(size_t)b * M + miA] : miA) : 0ull;
-    const unsigned long long kB = actB ? pack_best(scoreB, ids ? ids[(size_t)b * M + miB] : miB) : 0ull;
-    unsigned long long key = kA > kB ? kA : kB;
-    DRB_UNROLL
-    for (int o = 16; o > 0; o >>= 1) {
-        const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
-        key = other > key ? other : key;
-    }
-    if (threadIdx.x == 0 && key) atomicMax(best_packed + b, key);
-}
-
 // One CTA per pair: decode the packed arg-max and emit the winner's inlier mask.
 __global__ void __launch_bounds__(256)
 best_finalize_kernel(const float* __restrict__ matches, const float* __restrict__ models_dense,
@@ -571,18 +447,12 @@ extern "C" int drb_score_msac(const float* matches, const float* models, const i
     if (!matches || !models || !thr || !best_packed) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || M <= 0 || N <= 0 || (M + kMsacThreads - 1) / kMsacThreads > 65535) return DRB_ERR_BAD_SHAPE;
     dim3 grid(B, (M + kMsacThreads - 1) / kMsacThreads);
-    // DRB_MSAC_MODE: 2 (default) = two models per thread, 1 = one model per thread with the hand-grouped packed
-    // sequence, 0 = compiler-scheduled packed loop.  Kept selectable for A/B measurements.
-    static const int mode = []() {
-        const char* e = getenv("DRB_MSAC_MODE");
-        return (e != nullptr && e[0] >= '0' && e[0] <= '2') ? e[0] - '0' : 2;
+    // DRB_MSAC_SCHED=0 selects the compiler-scheduled inner loop (kept for A/B measurements)
+    static const bool sched = []() {
+        const char* e = getenv("DRB_MSAC_SCHED");
+        return e == nullptr || e[0] != '0';
     }();
-    const bool sched = mode >= 1;
-    if (mode == 2) {
-        dim3 grid2(B, (M + 2 * kMsacThreads - 1) / (2 * kMsacThreads));
-        score_msac2_kernel<<<grid2, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N,
-                                                                             scores, best_packed);
-    } else if (sched)
+    if (sched)
         score_msac_kernel<true><<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N,
                                                                                  scores, best_packed);
     else
