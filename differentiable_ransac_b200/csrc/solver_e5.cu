@@ -23,12 +23,6 @@ struct SmemMat {
     __device__ __forceinline__ float& operator()(int r, int c) { return base[(r * 20 + c) * kE5Stride]; }
 };
 
-struct SmemSink {
-    float* base;  // same column as SmemMat: element e (= slot * 9 + i, e < 90 <= 200) at base[e * kE5Stride]
-    __device__ __forceinline__ void operator()(int slot, int i, float v) { base[(slot * 9 + i) * kE5Stride] = v; }
-    __device__ __forceinline__ float get(int e) const { return base[e * kE5Stride]; }
-};
-
 __device__ __forceinline__ void load_minimal5(const float* __restrict__ matches, const int32_t* __restrict__ idx,
                                               long long row, int b, int N, float (*p)[4]) {
     DRB_UNROLL

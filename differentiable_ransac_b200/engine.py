@@ -91,6 +91,25 @@ def ransac_f8_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     return out
 
 
+def ransac_f7_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False,
+                   sampler="sets"):
+    """Fundamental matrix from 7-point samples (`-fmat 1 -sam 2` in the reference, whose own 7-point is broken:
+    SURVEY D4).  Up to three models per sample; slots without a real root are NaN for the scorer, which never
+    lets a NaN score win."""
+    idx = _draw(logits, K, 7, tau, noise, seed, offset, sampler)
+    models, nsol = ops.solve_f7(matches, idx)                                   # [B,K,3,3,3], [B,K]
+    B = matches.shape[0]
+    live = torch.arange(ops.F7_SLOTS, device=models.device)[None, None, :] < nsol[..., None]
+    scored = torch.where(live[..., None, None], models, torch.full_like(models, float("nan"))).reshape(B, -1, 9)
+    scores, best = ops.score_msac(matches, scored, thr, want_scores=want_scores)
+    best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, models.reshape(B, -1, 9), best, thr)
+    out = dict(best_model=best_model, best_id=best_id, best_score=best_score, mask=mask.view(torch.bool), ninl=ninl,
+               idx=idx, models=models, nsol=nsol)
+    if want_scores:
+        out.update(scores=scores, best_hyp=torch.div(best_id, ops.F7_SLOTS, rounding_mode="floor"))
+    return out
+
+
 # ---- train mode --------------------------------------------------------------------------------
 class _HypothesizeBase(torch.autograd.Function):
     """sample -> minimal solve (-> slot selection); backward: solver IFT adjoint ->

@@ -101,9 +101,9 @@ class RANSAC(object):
             nz = None
             if noise is not None:
                 nz = noise.reshape(-1, rbs, noise.shape[-1])[chunk][None]
-            run = engine.ransac_e5_test if self.sample_size == 5 else engine.ransac_f8_test
-            if self.sample_size not in (5, 8):
-                raise NotImplementedError("test mode supports the 5-point and the 8-point samplers")
+            run = {5: engine.ransac_e5_test, 7: engine.ransac_f7_test, 8: engine.ransac_f8_test}.get(self.sample_size)
+            if run is None:
+                raise NotImplementedError("test mode supports the 5-, 7- and 8-point samplers")
             out = run(m, lg, rbs, thr, self.sampler.tau, nz, self.sampler.seed, self.sampler._next_offset())
             if best is None or bool(out["best_score"][0] > best["best_score"][0]):     # ransac.py:116
                 best = out
@@ -128,7 +128,7 @@ class RANSAC(object):
         """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict for K hypotheses per pair
         (default: max_iterations, no early exit)."""
         K = K or self.max_iterations
-        run = engine.ransac_e5_test if self.sample_size == 5 else engine.ransac_f8_test
+        run = {5: engine.ransac_e5_test, 7: engine.ransac_f7_test, 8: engine.ransac_f8_test}[self.sample_size]
         return run(matches, logits, K, thresholds, self.sampler.tau, None, self.sampler.seed, self.sampler._next_offset())
 
 

@@ -190,3 +190,20 @@ def test_fundamental_layer_test_mode_with_refit():
     F, _ = layer(pn.to(DEV), logits.to(DEV), Kc, Kc, im.to(DEV), im.to(DEV))
     Fu, Fg = unit(F.cpu()), unit(F_gt)
     assert min((Fu - Fg).norm(), (Fu + Fg).norm()) < 5e-2
+
+
+def test_fundamental_seven_point_test_mode():
+    """`-fmat 1 -sam 2`: 7-point samples (up to three models each) through the driver."""
+    from differentiable_ransac_b200 import synth
+    from differentiable_ransac_b200.model_cl import RANSACLayer
+    pm, F_gt, Kc, inl = synth.pixel_pair(2000, 0.6, seed=6)
+    im = torch.tensor([480.0, 640.0])
+    pn = pm.clone()
+    pn[:, 0:2] = (pm[:, 0:2] - torch.stack((im[1] / 2, im[0] / 2))) / max(im)
+    pn[:, 2:4] = (pm[:, 2:4] - torch.stack((im[1] / 2, im[0] / 2))) / max(im)
+    layer = RANSACLayer(_opt(fmat=1, sampler=2, ransac_batch_size=256))
+    assert layer.estimator.sampler.num_samples == 7
+    layer.estimator.max_iterations = 1024
+    F, _ = layer(pn.to(DEV), torch.rand(2000).to(DEV), Kc, Kc, im.to(DEV), im.to(DEV))
+    Fu, Fg = unit(F.cpu()), unit(F_gt)
+    assert min((Fu - Fg).norm(), (Fu + Fg).norm()) < 5e-2
