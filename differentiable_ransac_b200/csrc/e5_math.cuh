@@ -302,15 +302,11 @@ struct E5Sample {
 };
 static constexpr int kE5SampleScalars = 36 + 12 + 12 + 15 + 11;
 
-// Stage 1: points -> E5Sample.  `M` is the 10 x 20 scratch; it is dead when this returns.
+// Stage 1b: S.N (a basis of the 4-dimensional space E lives in) -> the rest of E5Sample.  `M` is the
+// 10 x 20 scratch; it is dead when this returns.  Shared by the minimal solver (null space of the 5 x 9
+// system) and the non-minimal refit (the 4 smallest eigenvectors of A^T A, refit_math.cuh).
 template <class T, class Mat>
-DRB_HD bool e5_prepare(const T (*pts)[4], Mat& M, E5Sample<T>& S) {
-    {
-        T rows[5][9];
-        DRB_UNROLL
-        for (int j = 0; j < 5; ++j) epipolar_row(pts[j][0], pts[j][1], pts[j][2], pts[j][3], rows[j]);
-        null_space_rows<T, 5>(rows, S.N);
-    }
+DRB_HD bool e5_prepare_from_null(Mat& M, E5Sample<T>& S) {
     e5_constraints<T, Mat>(S.N, M);
     bool ok = e5_eliminate<T, Mat>(M);
     DRB_UNROLL
@@ -351,6 +347,18 @@ DRB_HD bool e5_prepare(const T (*pts)[4], Mat& M, E5Sample<T>& S) {
     DRB_UNROLL
     for (int i = 0; i <= 10; ++i) ok = ok && (S.P[i] == S.P[i]) && (t_abs(S.P[i]) < T(1e30));
     return ok;
+}
+
+// Stage 1: points -> E5Sample.
+template <class T, class Mat>
+DRB_HD bool e5_prepare(const T (*pts)[4], Mat& M, E5Sample<T>& S) {
+    {
+        T rows[5][9];
+        DRB_UNROLL
+        for (int j = 0; j < 5; ++j) epipolar_row(pts[j][0], pts[j][1], pts[j][2], pts[j][3], rows[j]);
+        null_space_rows<T, 5>(rows, S.N);
+    }
+    return e5_prepare_from_null<T, Mat>(M, S);
 }
 
 // Stage 3: one root z of P -> (x, y) from the best-conditioned pair of the three equations -> Gauss-Newton

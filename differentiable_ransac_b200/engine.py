@@ -110,6 +110,56 @@ def ransac_f7_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     return out
 
 
+# ---- after the loop: local optimisation and the final refit -----------------
+def _fit_and_score(matches, mask, thr, fmat, weights=None):
+    """Non-minimal fit on the selected correspondences of every pair, scored on all correspondences:
+    -> (score [B], model [B,3,3], inlier mask [B,N] bool, ninl [B]) of the best candidate per pair
+    (score 0 / identity when the fit produced nothing)."""
+    fit = ops.refit_f8 if fmat else ops.refit_e5
+    models, nsol = fit(matches, mask, weights)
+    _, packed = ops.score_msac(matches, models, thr, count=nsol, want_scores=False)
+    _, score, model, inl, ninl = ops.best_finalize(matches, models, packed, thr)
+    return score, model, inl.view(torch.bool), ninl
+
+
+def local_optimization(matches, state, thr, fmat, iters):
+    """`RANSAC.localOptimization` for lo = 1 (iters = 1) and lo = 2 (iters = lo_iters), ransac.py:217-257, for
+    B pairs at once: refit on the current inliers, accept while the score does not drop (`>=`, :250), stop a
+    pair at its first rejection.  `state` = dict(best_score [B], best_model [B,3,3], mask [B,N], ninl [B]);
+    returns the updated dict.  One host sync per iteration (the reference syncs on the same comparison)."""
+    score, model, mask, ninl = state["best_score"], state["best_model"], state["mask"], state["ninl"]
+    active = torch.ones_like(score, dtype=torch.bool)
+    for _ in range(int(iters)):
+        s2, m2, k2, n2 = _fit_and_score(matches, mask, thr, fmat)
+        take = active & (s2 >= score)
+        score = torch.where(take, s2, score)
+        model = torch.where(take[:, None, None], m2, model)
+        mask = torch.where(take[:, None], k2, mask)
+        ninl = torch.where(take, n2, ninl)
+        active = take
+        if not bool(active.any()):
+            break
+    out = dict(state)
+    out.update(best_score=score, best_model=model, mask=mask, ninl=ninl)
+    return out
+
+
+def final_refit(matches, state, thr, fmat, weights=None):
+    """ransac.py:148-185: the eight-point on the winner's inliers (`fmat`), or the five-point system on ALL
+    correspondences (what `estimate_model` does without pymagsac, nister.py:51-65; the reference runs it in
+    fp64, so does the kernel).  The candidate replaces the winner only if it scores strictly higher (:181);
+    the inlier mask is NOT recomputed (the reference keeps the loop's mask)."""
+    fit = ops.refit_f8 if fmat else ops.refit_e5
+    models, nsol = fit(matches, state["mask"] if fmat else None, weights)
+    _, packed = ops.score_msac(matches, models, thr, count=nsol, want_scores=False)
+    _, s2, m2, _, _ = ops.best_finalize(matches, models, packed, thr, want_mask=False)
+    take = s2 > state["best_score"]
+    out = dict(state)
+    out.update(best_score=torch.where(take, s2, state["best_score"]),
+               best_model=torch.where(take[:, None, None], m2, state["best_model"]), refit_taken=take)
+    return out
+
+
 # ---- train mode --------------------------------------------------------------------------------
 class _HypothesizeBase(torch.autograd.Function):
     """sample -> minimal solve (-> slot selection); backward: solver IFT adjoint ->

@@ -7,32 +7,6 @@ from .. import ops
 from ._autograd import F8Solve
 
 
-def normalized_eight_point_torch(matches, weights=None):
-    """Non-minimal (n > 8) normalised 8-point with torch ops on the device -- the final refit of
-    `ransac.py:150-155`, once per pair and outside the hot loop.  matches [1,n,4] -> [1,3,3]."""
-    m = matches.float()
-    mass = m.mean(1, keepdim=True)
-    c = m - mass
-    r1 = (2 ** 0.5) / c[..., :2].norm(dim=-1).mean(1)
-    r2 = (2 ** 0.5) / c[..., 2:].norm(dim=-1).mean(1)
-    x1, y1 = c[..., 0] * r1[:, None], c[..., 1] * r1[:, None]
-    x2, y2 = c[..., 2] * r2[:, None], c[..., 3] * r2[:, None]
-    A = torch.stack((x1 * x2, x2 * y1, x2, y2 * x1, y2 * y1, y2, x1, y1, torch.ones_like(x1)), -1)
-    if weights is not None:
-        A = weights.reshape(1, -1, 1).float() * A
-    _, vecs = torch.linalg.eigh(A.transpose(-1, -2) @ A)
-    Fn = vecs[..., 0].reshape(-1, 3, 3)
-    B = m.shape[0]
-    T1 = torch.zeros(B, 3, 3, device=m.device)
-    T2 = torch.zeros(B, 3, 3, device=m.device)
-    T1[:, 0, 0] = T1[:, 1, 1] = r1
-    T2[:, 0, 0] = T2[:, 1, 1] = r2
-    T1[:, 2, 2] = T2[:, 2, 2] = 1
-    T1[:, 0, 2], T1[:, 1, 2] = -r1 * mass[:, 0, 0], -r1 * mass[:, 0, 1]
-    T2[:, 0, 2], T2[:, 1, 2] = -r2 * mass[:, 0, 2], -r2 * mass[:, 0, 3]
-    return T2.transpose(-1, -2) @ Fn @ T1
-
-
 class FundamentalMatrixEstimatorNew:
     def __init__(self, device="cuda", weighted=0):
         self.sample_size = 7
@@ -50,6 +24,7 @@ class FundamentalMatrixEstimatorNew:
             models, nsol = ops.solve_f7(matches.float())
             self.last_nsol = nsol[0]
             return models[0].reshape(-1, 3, 3).to(matches.dtype)
-        if s > 8:
-            return normalized_eight_point_torch(matches, weights).to(matches.dtype)
+        if s > 8:                                     # normalise + eight-point on all n rows (:169-175), no gradient
+            models, _ = ops.refit_f8(matches.detach().float(), None, weights)
+            return models.reshape(-1, 3, 3).to(matches.dtype)
         return None

@@ -192,6 +192,29 @@ def solve_f7(matches, idx=None):
     return models, nsol
 
 
+def _refit(name, slots, matches, mask, weights):
+    matches = _f32(matches)
+    B, N, _ = matches.shape
+    models = torch.empty(B, slots, 3, 3, dtype=torch.float32, device=matches.device)
+    nsol = torch.empty(B, dtype=torch.int32, device=matches.device)
+    mk = None if mask is None else mask.to(torch.uint8).contiguous()
+    w = None if weights is None else _f32(weights)
+    lib = _lib.load()
+    check(getattr(lib, name)(_p(matches), _p(mk), _p(w), B, N, _p(models), _p(nsol), _stream()), name)
+    return models, nsol
+
+
+def refit_e5(matches, mask=None, weights=None):
+    """Essential matrices of the selected correspondences of each pair (non-minimal five-point):
+    matches [B,N,4], mask [B,N] or None -> models [B,10,3,3] (identity beyond nsol), nsol [B]."""
+    return _refit("drb_refit_e5", E5_SLOTS, matches, mask, weights)
+
+
+def refit_f8(matches, mask=None, weights=None):
+    """Hartley-normalised eight-point on the selected correspondences: -> F [B,1,3,3], ok [B]."""
+    return _refit("drb_refit_f8", 1, matches, mask, weights)
+
+
 def solve_rigid3(points, idx=None, flag=True):
     points, idx, B, K, N = _rows(points, idx, 3, 6)
     models = torch.empty(B, K, 4, 4, dtype=torch.float32, device=points.device)

@@ -13,7 +13,6 @@ import math
 import torch
 
 from . import engine, ops
-from .estimators.fundamental_matrix_estimator import normalized_eight_point_torch
 
 
 def normalized_threshold(threshold, K1, K2, fmat):
@@ -96,7 +95,7 @@ class RANSAC(object):
         best = None
         iterations, max_iters = 0, self.max_iterations
         noise = self.sampler.injected_noise
-        chunk = 0
+        chunk, last_noise = 0, None
         while iterations < max_iters:
             nz = None
             if noise is not None:
@@ -107,29 +106,41 @@ class RANSAC(object):
             out = run(m, lg, rbs, thr, self.sampler.tau, nz, self.sampler.seed, self.sampler._next_offset())
             if best is None or bool(out["best_score"][0] > best["best_score"][0]):     # ransac.py:116
                 best = out
+                if self.lo in (1, 2):                                                  # ransac.py:122-132
+                    best = engine.local_optimization(m, best, thr, self.fmat, self.lo_iters if self.lo == 2 else 1)
+                elif self.lo:
+                    raise NotImplementedError("lo=3 needs the reference's UniformSampler, which cannot run "
+                                              "(SURVEY 2.1 #5)")
                 if self.adaptive:
                     max_iters = min(self.max_iterations,
-                                    self.adaptive_iteration_number(int(out["ninl"][0]), N, self.confidence))
+                                    self.adaptive_iteration_number(int(best["ninl"][0]), N, self.confidence))
             iterations += rbs
             chunk += 1
+            last_noise = nz
+        if self.final_refit:
+            # ransac.py:148-185.  `weighted` hands the eight-point the soft one-hot of the last chunk's first
+            # sample (:153); that row exists only when the noise is injected, otherwise softmax(logits / tau).
+            w = None
+            if self.fmat and self.weighted:
+                key = lg if last_noise is None else lg + last_noise[:, 0].to(lg.dtype)
+                w = torch.softmax(key / self.sampler.tau, dim=-1)
+            best = engine.final_refit(m, best, thr, self.fmat, w)
         best_model, best_mask, best_score = best["best_model"][0], best["mask"][0], best["best_score"][0]
-        if self.final_refit and self.fmat and int(best_mask.sum()) >= 8:
-            # ransac.py:148-176: non-minimal 8-point on the inliers, kept only if it scores higher
-            cand = normalized_eight_point_torch(matches[best_mask][None])
-            sc, _ = ops.score_msac(m, cand.reshape(1, 1, 9), thr)
-            if bool(sc[0, 0] > best_score):
-                best_model, best_score = cand[0], sc[0, 0]
-        # The essential-matrix refit of the reference is pymagsac's C++ optimiser or, without it, a
-        # 5-point solve on ALL points (nister.py:51-65): outside the hot path.
         return best_model.to(matches.dtype), best_mask, best_score, iterations
 
     # -- B pairs at once (replaces the python loop of model_cl.py:488-510) ---------------------------
     def batched_test(self, matches, logits, thresholds, K=None):
         """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict for K hypotheses per pair
-        (default: max_iterations, no early exit)."""
+        (default: max_iterations, no early exit), followed by the optional LO pass and the final refit for all
+        pairs at once."""
         K = K or self.max_iterations
         run = {5: engine.ransac_e5_test, 7: engine.ransac_f7_test, 8: engine.ransac_f8_test}[self.sample_size]
-        return run(matches, logits, K, thresholds, self.sampler.tau, None, self.sampler.seed, self.sampler._next_offset())
+        out = run(matches, logits, K, thresholds, self.sampler.tau, None, self.sampler.seed, self.sampler._next_offset())
+        if self.lo in (1, 2):
+            out = engine.local_optimization(matches, out, thresholds, self.fmat, self.lo_iters if self.lo == 2 else 1)
+        if self.final_refit:
+            out = engine.final_refit(matches, out, thresholds, self.fmat)
+        return out
 
 
 class RANSAC3D(RANSAC):

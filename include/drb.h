@@ -172,6 +172,20 @@ int drb_rigid_residual_backward(const float* points, const float* models, const 
 int drb_gather_backward(const float* matches, const int32_t* idx, const float* g_pts,
                         int B, int K, int N, int s, int D, float* g_sel, float* grad_matches, void* stream);
 
+/* ---- non-minimal refit / local optimisation on a set of correspondences --------
+ * Replaces, for n > sample_size selected points, EssentialMatrixEstimatorNister.estimate_model without
+ * pymagsac (essential_matrix_estimator_nister.py:51-65 -> :69-430: the four smallest right singular vectors
+ * of A^T A, then the five-point polynomial system) and FundamentalMatrixEstimatorNew.normalize +
+ * estimate_non_minimal_model (fundamental_matrix_estimator.py:177-260), as called by the final refit
+ * (ransac.py:148-165) and by localOptimization (ransac.py:217-257, lo = 1, 2).
+ * matches[B,N,4]; mask[B,N] (nullable = all points; nonzero = selected); weights[B,N] (nullable; rows are
+ * scaled by the weight as the reference does).  Accumulation and solve in double.
+ * drb_refit_e5: models[B,10,9] (slots >= nsol[b] = identity); drb_refit_f8: models[B,1,9], nsol[b] in {0,1}. */
+int drb_refit_e5(const float* matches, const uint8_t* mask, const float* weights, int B, int N,
+                 float* models, int32_t* nsol, void* stream);
+int drb_refit_f8(const float* matches, const uint8_t* mask, const float* weights, int B, int N,
+                 float* models, int32_t* nsol, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

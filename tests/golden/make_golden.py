@@ -243,5 +243,66 @@ def main():
          mean_residuals=torch.stack(list(mres3.values())), loss=loss3, grad_logits=lgr.grad)
 
 
+def refit_and_full_driver():
+    """the non-minimal fits of the final refit / LO and the whole test-mode driver
+    (`RANSAC.__call__`, adaptive exit + refit included) run by the reference itself."""
+    torch.set_num_threads(4)
+    K1 = torch.tensor([[800.0, 0, 320], [0, 800.0, 240], [0, 0, 1]])
+    est = EssentialMatrixEstimatorNister("cpu")
+    f8 = FundamentalMatrixEstimatorNew("cpu")
+
+    # non-minimal five-point: all points in fp64 (the refit call of ransac.py:157-165 without pymagsac)
+    # and on an inlier set (localOptimization, ransac.py:226-240)
+    N = 1000
+    m, Egt, inl = synth.relative_pose_pair(N, 0.6, seed=17, noise=2e-4)
+    thr = float(0.75 / 800.0)
+    sc, masks = MSACScore("cpu").score(m, Egt[None] / Egt.norm(), thr)
+    mask = masks[0]
+    E_all64 = est.estimate_model(m[None].double())
+    E_inl64 = est.estimate_model(m[mask][None].double())
+    E_inl32 = est.estimate_model(m[mask][None])
+    save("refit_e5", matches=m, mask=mask, E_all64=E_all64, E_inl64=E_inl64, E_inl32=E_inl32, E_gt=Egt,
+         threshold=thr)
+
+    # non-minimal eight-point on an inlier set, plain and weighted (ransac.py:151-155)
+    pm, Fgt, Kc, finl = synth.pixel_pair(2000, 0.5, seed=8)
+    g = torch.Generator().manual_seed(77)
+    fmask = finl.clone()
+    fmask[torch.randperm(2000, generator=g)[:40]] = True          # a few outliers slip in
+    w = torch.rand(2000, generator=g) * 0.9 + 0.1
+    F_inl32 = f8.estimate_model(pm[fmask][None])
+    F_inl64 = f8.estimate_model(pm[fmask][None].double())
+    F_w64 = f8.estimate_model(pm[fmask][None].double(), w[fmask][None].double())
+    save("refit_f8", matches=pm, mask=fmask, weights=w, F_inl32=F_inl32, F_inl64=F_inl64, F_w64=F_w64, F_gt=Fgt)
+
+    # the whole test-mode driver, essential and fundamental
+    Kc_, nchunks = 32, 4
+    lg = synth.logits_regime(1, N, "L0", seed=6)[0]
+    noises = [synth.gumbel_noise((Kc_, N), seed=300 + c) for c in range(nchunks)]
+    for lo in (0, 2):
+        smp = injected_sampler(Kc_, 5, noises)
+        drv = RANSAC(est, smp, MSACScore("cpu"), fmat=False, train=False, ransac_batch_size=Kc_, sampler_id=2,
+                     threshold=0.75, max_iterations=Kc_ * nchunks, lo=lo, lo_iters=8)
+        bm, bmask, bs, its = drv(m, lg, K1, K1, Egt)
+        save(f"driver_full_e5_lo{lo}", matches=m, logits=lg, noise_seeds=[300 + c for c in range(nchunks)], K1=K1, best_model=bm,
+             best_mask=bmask, best_score=bs, iterations=its, E_gt=Egt)
+
+    N8 = 1000
+    pm8, Fgt8, Kc8, finl8 = synth.pixel_pair(N8, 0.5, seed=31)
+    lg8 = synth.logits_regime(1, N8, "L1", seed=9)[0]
+    noises8 = [synth.gumbel_noise((Kc_, N8), seed=400 + c) for c in range(nchunks)]
+    for lo in (0, 2):
+        smp = injected_sampler(Kc_, 8, noises8)
+        drv = RANSAC(f8, smp, MSACScore("cpu"), fmat=True, train=False, ransac_batch_size=Kc_, sampler_id=3,
+                     threshold=0.75, max_iterations=Kc_ * nchunks, lo=lo, lo_iters=8)
+        bm, bmask, bs, its = drv(pm8, lg8, Kc8, Kc8, Fgt8)
+        save(f"driver_full_f8_lo{lo}", matches=pm8, logits=lg8, noise_seeds=[400 + c for c in range(nchunks)], K=Kc8, best_model=bm,
+             best_mask=bmask, best_score=bs, iterations=its, F_gt=Fgt8)
+
+
 if __name__ == "__main__":
-    main()
+    if "refit" in sys.argv[1:]:
+        refit_and_full_driver()
+    else:
+        main()
+        refit_and_full_driver()

@@ -3,6 +3,7 @@
 // suite (no GPU in the build container) can run the exact arithmetic of the
 // CUDA kernels against the oracle.  The package never loads this library; the
 // product path is the CUDA library and fails loudly without it.
+#include <cmath>
 #include <cstring>
 #include <vector>
 
@@ -10,6 +11,7 @@
 #include "e5_backward.cuh"
 #include "f8_math.cuh"
 #include "rigid_math.cuh"
+#include "refit_math.cuh"
 
 namespace {
 template <class T>
@@ -113,6 +115,56 @@ HC_RIGID(hc_rigid3_solve_f64, double)
     }
 HC_RIGIDB(hc_rigid3_backward_f32, float)
 HC_RIGIDB(hc_rigid3_backward_f64, double)
+
+// Serial restatement of refit.cu's moment accumulation + the shared serial tail (refit_math.cuh).
+int hc_refit(int fmat, const float* matches, const unsigned char* mask, const float* weights, int N, float* models) {
+    drb::HartleyNorm<double> h;
+    h.m[0] = h.m[1] = h.m[2] = h.m[3] = 0.0;
+    h.r1 = h.r2 = 1.0;
+    double count = 0.0, s[4] = {0, 0, 0, 0};
+    for (int n = 0; n < N; ++n) {
+        if (mask && !mask[n]) continue;
+        count += 1.0;
+        for (int c = 0; c < 4; ++c) s[c] += matches[n * 4 + c];
+    }
+    if (count < (fmat ? 8 : 5)) return 0;
+    if (fmat) {
+        for (int c = 0; c < 4; ++c) h.m[c] = s[c] / count;
+        double d1 = 0.0, d2 = 0.0;
+        for (int n = 0; n < N; ++n) {
+            if (mask && !mask[n]) continue;
+            const double a = matches[n * 4] - h.m[0], b = matches[n * 4 + 1] - h.m[1];
+            const double c = matches[n * 4 + 2] - h.m[2], e = matches[n * 4 + 3] - h.m[3];
+            d1 += std::sqrt(a * a + b * b);
+            d2 += std::sqrt(c * c + e * e);
+        }
+        h.r1 = 1.4142135623730951 / (d1 / count);
+        h.r2 = 1.4142135623730951 / (d2 / count);
+    }
+    double acc[45];
+    for (int i = 0; i < 45; ++i) acc[i] = 0.0;
+    for (int n = 0; n < N; ++n) {
+        if (mask && !mask[n]) continue;
+        double row[9];
+        drb::epipolar_row<double>((matches[n * 4] - h.m[0]) * h.r1, (matches[n * 4 + 1] - h.m[1]) * h.r1,
+                                  (matches[n * 4 + 2] - h.m[2]) * h.r2, (matches[n * 4 + 3] - h.m[3]) * h.r2, row);
+        const double ww = weights ? (double)weights[n] * (double)weights[n] : 1.0;
+        int e = 0;
+        for (int i = 0; i < 9; ++i)
+            for (int j = i; j < 9; ++j) acc[e++] += ww * row[i] * row[j];
+    }
+    if (fmat) {
+        double F[9];
+        if (!drb::f8_refit_from_moments<double>(acc, h, F)) return 0;
+        for (int i = 0; i < 9; ++i) models[i] = (float)F[i];
+        return 1;
+    }
+    double E[10][9];
+    const int n_out = drb::e5_refit_from_moments<double>(acc, E);
+    for (int k = 0; k < n_out; ++k)
+        for (int i = 0; i < 9; ++i) models[k * 9 + i] = (float)E[k][i];
+    return n_out;
+}
 
 int hc_roots_f32(const float* coef, float* roots) { return drb::real_roots_deg10<float>(coef, roots); }
 int hc_roots_f64(const double* coef, double* roots) { return drb::real_roots_deg10<double>(coef, roots); }

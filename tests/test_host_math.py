@@ -157,3 +157,35 @@ def test_rigid_forward_backward(lib, golden, flag):
                                16, flag, vp(gours), vp(ok))
     rel = (torch.from_numpy(gours) - gr).flatten(1).abs().max(1).values / gr.flatten(1).abs().max(1).values
     assert ok.all() and rel.max() < 1e-8
+
+
+def run_refit(lib, fmat, matches, mask=None, weights=None):
+    m = np.ascontiguousarray(matches.numpy(), dtype=np.float32)
+    out = np.zeros((10, 9), np.float32)
+    mk = None if mask is None else np.ascontiguousarray(mask.numpy(), dtype=np.uint8)
+    w = None if weights is None else np.ascontiguousarray(weights.numpy(), dtype=np.float32)
+    n = lib.hc_refit(int(fmat), vp(m), None if mk is None else vp(mk), None if w is None else vp(w), m.shape[0],
+                     vp(out))
+    return torch.from_numpy(out[:n]).view(-1, 3, 3)
+
+
+def test_refit_e5_finds_every_genuine_reference_model(lib, golden):
+    """The non-minimal five-point of the final refit / LO (nister.py:51-65 on n > 5 rows), fp64 reference."""
+    g = golden("refit_e5")
+    for ref, mask in ((g["E_all64"], None), (g["E_inl64"], g["mask"])):
+        ours = run_refit(lib, False, g["matches"], mask)
+        genuine = trace_constraint_residual(ref) < 1e-8           # the other slots are complex-root leftovers (D3)
+        assert int(genuine.sum()) == ours.shape[0] > 0
+        d = match_up_to_sign(ours[None], unit(ref[genuine])[None])[0]
+        assert d.max() < 1e-6
+
+
+def test_refit_f8_matches_reference(lib, golden):
+    g = golden("refit_f8")
+    for ref, w in ((g["F_inl64"], None), (g["F_w64"], g["weights"])):
+        F = run_refit(lib, True, g["matches"], g["mask"], w)[0].double()
+        assert min((F - ref[0]).abs().max(), (F + ref[0]).abs().max()) < 1e-6   # same scale, sign arbitrary
+    # fewer than eight selected correspondences: no model
+    few = torch.zeros(2000, dtype=torch.bool)
+    few[:7] = True
+    assert run_refit(lib, True, g["matches"], few).shape[0] == 0

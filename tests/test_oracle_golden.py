@@ -1,5 +1,6 @@
 """The CPU oracle against the reference's own outputs (tests/golden/*.npz,
 produced by tests/golden/make_golden.py from /root/reference).  CPU only."""
+import pytest
 import torch
 
 from oracle import driver, fundamental, nister, rigid, sampler, scoring, stewenius
@@ -112,3 +113,34 @@ def test_rigid_train_loop(golden):
     models, res, mres = driver.rigid_train_loop(g["points"], g["logits"], list(g["noise"]))
     assert torch.allclose(torch.cat(models), g["models"], atol=1e-6)
     assert torch.allclose(torch.cat(res), g["residuals"], rtol=1e-5)
+
+
+def test_nonminimal_fits(golden):
+    """the fits behind the final refit and LO (nister.py:51-65, fundamental...:169-175)."""
+    g = golden("refit_e5")
+    m, mask = g["matches"], g["mask"].bool()
+    assert torch.allclose(nister.five_point(m[None].double()), g["E_all64"], atol=1e-9)
+    assert torch.allclose(nister.five_point(m[mask][None].double()), g["E_inl64"], atol=1e-9)
+    f = golden("refit_f8")
+    m, mask, w = f["matches"], f["mask"].bool(), f["weights"]
+    assert torch.allclose(fundamental.eight_point(m[mask][None].double()), f["F_inl64"], atol=1e-12)
+    assert torch.allclose(fundamental.eight_point(m[mask][None].double(), w[mask][None].double()), f["F_w64"],
+                          atol=1e-12)
+
+
+@pytest.mark.parametrize("name,fmat,s", [("driver_full_e5_lo0", False, 5), ("driver_full_e5_lo2", False, 5),
+                                         ("driver_full_f8_lo0", True, 8), ("driver_full_f8_lo2", True, 8)])
+def test_full_test_driver(golden, name, fmat, s):
+    """`RANSAC.__call__` in test mode run by the reference itself: adaptive exit, LO (lo=2, 8 iterations), final
+    refit."""
+    from differentiable_ransac_b200 import synth
+    g = golden(name)
+    m = g["matches"]
+    Kc = g["K"] if fmat else g["K1"]
+    noises = [synth.gumbel_noise((32, m.shape[0]), seed=int(sd)) for sd in g["noise_seeds"]]
+    model, mask, score, its = driver.full_test_driver(m, g["logits"], noises, Kc, Kc, 0.75, fmat=fmat, sample_size=s,
+                                                      lo=int(name[-1]), lo_iters=8)
+    assert its == int(g["iterations"])
+    assert abs(float(score) - float(g["best_score"])) < 1e-3 * float(g["best_score"])
+    assert min((model - g["best_model"]).abs().max(), (model + g["best_model"]).abs().max()) < 1e-4
+    assert (mask != g["best_mask"].bool()).sum() <= 1
