@@ -18,52 +18,12 @@
 #include "drb_common.cuh"
 #include "e5_math.cuh"
 #include "f8_math.cuh"
+#include "small_eig.cuh"
 
 namespace drb {
 
 // Packed index of the symmetric 9 x 9 moment matrix, i <= j.
 DRB_HD int sym9(int i, int j) { return i * 9 - (i * (i - 1)) / 2 + (j - i); }
-
-// Eigen-decomposition of a symmetric 9 x 9 matrix by cyclic Jacobi rotations.  `A` (row-major, 81) is
-// overwritten by its diagonal form, `V` (row-major) receives the eigenvectors as COLUMNS.
-template <class T>
-DRB_HD void jacobi_eig9(T* A, T* V, int max_sweeps = 16) {
-    for (int i = 0; i < 9; ++i)
-        for (int j = 0; j < 9; ++j) V[i * 9 + j] = (i == j) ? T(1) : T(0);
-    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
-        T off = T(0), diag = T(0);
-        for (int i = 0; i < 9; ++i) {
-            diag += A[i * 9 + i] * A[i * 9 + i];
-            for (int j = i + 1; j < 9; ++j) off += A[i * 9 + j] * A[i * 9 + j];
-        }
-        if (!(off > diag * T(1e-34))) break;
-        for (int p = 0; p < 8; ++p) {
-            for (int q = p + 1; q < 9; ++q) {
-                const T apq = A[p * 9 + q];
-                if (apq == T(0)) continue;
-                const T theta = (A[q * 9 + q] - A[p * 9 + p]) / (T(2) * apq);
-                const T t = (theta >= T(0) ? T(1) : T(-1)) / (t_abs(theta) + t_sqrt(theta * theta + T(1)));
-                const T c = T(1) / t_sqrt(t * t + T(1));
-                const T s = t * c;
-                for (int k = 0; k < 9; ++k) {
-                    const T akp = A[k * 9 + p], akq = A[k * 9 + q];
-                    A[k * 9 + p] = c * akp - s * akq;
-                    A[k * 9 + q] = s * akp + c * akq;
-                }
-                for (int k = 0; k < 9; ++k) {
-                    const T apk = A[p * 9 + k], aqk = A[q * 9 + k];
-                    A[p * 9 + k] = c * apk - s * aqk;
-                    A[q * 9 + k] = s * apk + c * aqk;
-                }
-                for (int k = 0; k < 9; ++k) {
-                    const T vkp = V[k * 9 + p], vkq = V[k * 9 + q];
-                    V[k * 9 + p] = c * vkp - s * vkq;
-                    V[k * 9 + q] = s * vkp + c * vkq;
-                }
-            }
-        }
-    }
-}
 
 // The `count` eigenvectors of the packed moment matrix with the smallest eigenvalues, written in the
 // reference's order (`v[:, -count:, :]` of torch.linalg.svd: descending singular values, so out[count-1] is
@@ -73,7 +33,7 @@ DRB_HD void smallest_eigenvectors9(const T* packed, int count, T (*out)[9]) {
     T A[81], V[81];
     for (int i = 0; i < 9; ++i)
         for (int j = i; j < 9; ++j) A[i * 9 + j] = A[j * 9 + i] = packed[sym9(i, j)];
-    jacobi_eig9<T>(A, V);
+    jacobi_eig<T, 9>(A, V);
     bool used[9];
     for (int i = 0; i < 9; ++i) used[i] = false;
     for (int r = 0; r < count; ++r) {

@@ -279,13 +279,16 @@ def refit_and_full_driver():
     Kc_, nchunks = 32, 4
     lg = synth.logits_regime(1, N, "L0", seed=6)[0]
     noises = [synth.gumbel_noise((Kc_, N), seed=300 + c) for c in range(nchunks)]
+    # fp32 is what the scripts run; the fp64 run of the same reference code is the noise-free answer (the fp32
+    # five-point loses genuine models to LAPACK rounding)
     for lo in (0, 2):
-        smp = injected_sampler(Kc_, 5, noises)
-        drv = RANSAC(est, smp, MSACScore("cpu"), fmat=False, train=False, ransac_batch_size=Kc_, sampler_id=2,
-                     threshold=0.75, max_iterations=Kc_ * nchunks, lo=lo, lo_iters=8)
-        bm, bmask, bs, its = drv(m, lg, K1, K1, Egt)
-        save(f"driver_full_e5_lo{lo}", matches=m, logits=lg, noise_seeds=[300 + c for c in range(nchunks)], K1=K1, best_model=bm,
-             best_mask=bmask, best_score=bs, iterations=its, E_gt=Egt)
+        for prec, dt in (("", torch.float32), ("_64", torch.float64)):
+            smp = injected_sampler(Kc_, 5, [n.to(dt) for n in noises], dtype=dt)
+            drv = RANSAC(est, smp, MSACScore("cpu"), fmat=False, train=False, ransac_batch_size=Kc_, sampler_id=2,
+                         threshold=0.75, max_iterations=Kc_ * nchunks, lo=lo, lo_iters=8)
+            bm, bmask, bs, its = drv(m.to(dt), lg.to(dt), K1.to(dt), K1.to(dt), Egt.to(dt))
+            save(f"driver_full_e5_lo{lo}{prec}", matches=m, logits=lg, noise_seeds=[300 + c for c in range(nchunks)],
+                 K1=K1, best_model=bm, best_mask=bmask, best_score=bs, iterations=its, E_gt=Egt)
 
     N8 = 1000
     pm8, Fgt8, Kc8, finl8 = synth.pixel_pair(N8, 0.5, seed=31)

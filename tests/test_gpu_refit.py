@@ -107,9 +107,11 @@ def _driver(fmat, lo):
                                        ("driver_full_f8_lo0", True), ("driver_full_f8_lo2", True)])
 def test_full_test_mode_driver_vs_reference(golden, name, fmat):
     """`RANSAC.__call__` in test mode with the reference's injected noise: chunked loop, adaptive exit, LO on every
-    improvement (lo=2), final refit -- the reference's own end-to-end answer."""
+    improvement (lo=2), final refit -- the reference's own end-to-end answer.  For the five-point path the bar is
+    the reference run in fp64 (`*_64`): its fp32 run loses genuine models to LAPACK rounding (here the
+    winner of chunk 1), so it is only required that we are at least as close to fp64 as the fp32 reference is."""
     from differentiable_ransac_b200 import synth
-    g = golden(name)
+    g = golden(name if fmat else name + "_64")
     m = g["matches"]
     Kc = g["K"] if fmat else g["K1"]
     drv = _driver(fmat, int(name[-1]))
@@ -117,17 +119,15 @@ def test_full_test_mode_driver_vs_reference(golden, name, fmat):
     drv.sampler.injected_noise = noise.to(DEV)
     model, mask, score, its = drv(m.to(DEV), g["logits"].to(DEV), Kc, Kc, None)
     assert its == int(g["iterations"])
-    ref_model, ref_mask = g["best_model"], g["best_mask"].bool()
+    ref_model, ref_mask = g["best_model"].float(), g["best_mask"].bool()
     rel = abs(float(score) - float(g["best_score"])) / float(g["best_score"])
     mu, ru = unit(model.cpu()), unit(ref_model)
     dist = float(min((mu - ru).norm(), (mu + ru).norm()))
     iou = (mask.cpu() & ref_mask).sum().item() / max((mask.cpu() | ref_mask).sum().item(), 1)
-    if fmat:
-        # eight-point chain: everything is a linear solve, parity to rounding
-        assert rel < 1e-3 and dist < 1e-3 and iou > 0.98
-    else:
-        # the five-point models of the fp32 reference carry its LAPACK noise
-        assert rel < 0.02 and dist < 5e-3 and iou > 0.95
+    assert rel < 2e-3 and dist < 2e-3 and iou > 0.98, (rel, dist, iou)
+    if not fmat:
+        g32 = golden(name)
+        assert abs(float(score) - float(g["best_score"])) <= abs(float(g32["best_score"]) - float(g["best_score"])) + 0.5
 
 
 def test_batched_refit_improves_or_keeps_every_pair():

@@ -129,17 +129,19 @@ def test_nonminimal_fits(golden):
 
 
 @pytest.mark.parametrize("name,fmat,s", [("driver_full_e5_lo0", False, 5), ("driver_full_e5_lo2", False, 5),
+                                         ("driver_full_e5_lo0_64", False, 5), ("driver_full_e5_lo2_64", False, 5),
                                          ("driver_full_f8_lo0", True, 8), ("driver_full_f8_lo2", True, 8)])
 def test_full_test_driver(golden, name, fmat, s):
     """`RANSAC.__call__` in test mode run by the reference itself: adaptive exit, LO (lo=2, 8 iterations), final
     refit."""
     from differentiable_ransac_b200 import synth
     g = golden(name)
-    m = g["matches"]
-    Kc = g["K"] if fmat else g["K1"]
-    noises = [synth.gumbel_noise((32, m.shape[0]), seed=int(sd)) for sd in g["noise_seeds"]]
-    model, mask, score, its = driver.full_test_driver(m, g["logits"], noises, Kc, Kc, 0.75, fmat=fmat, sample_size=s,
-                                                      lo=int(name[-1]), lo_iters=8)
+    dt = torch.float64 if name.endswith("_64") else torch.float32
+    m = g["matches"].to(dt)
+    Kc = (g["K"] if fmat else g["K1"]).to(dt)
+    noises = [synth.gumbel_noise((32, m.shape[0]), seed=int(sd)).to(dt) for sd in g["noise_seeds"]]
+    model, mask, score, its = driver.full_test_driver(m, g["logits"].to(dt), noises, Kc, Kc, 0.75, fmat=fmat,
+                                                      sample_size=s, lo=int(name.split("lo")[1][0]), lo_iters=8)
     assert its == int(g["iterations"])
     assert abs(float(score) - float(g["best_score"])) < 1e-3 * float(g["best_score"])
     assert min((model - g["best_model"]).abs().max(), (model + g["best_model"]).abs().max()) < 1e-4
