@@ -193,7 +193,15 @@ def auc_parity(dev, pairs=12, N=1000, K=192):
         e_ref.append(max(pose_eval.pose_error_deg(ref["best_model"].numpy(), matches[b].numpy(), R, t,
                                                   ref["best_mask"].numpy())))
     a, r = pose_eval.auc(e_ours), pose_eval.auc(e_ref)
-    return dict(auc5_10_20_ours=a, auc5_10_20_cpu_reference=r, same_best_hypothesis=f"{same}/{pairs}",
+    # the same evaluation without leaving the device (drb_recover_pose: decomposition, DLT cheirality vote over all
+    # correspondences as test.py:73-76 does, angular errors), one launch for all pairs
+    from differentiable_ransac_b200 import cv_utils
+    R_gt = torch.stack([d[3] for d in data]).float().to(dev)
+    t_gt = torch.stack([d[4] for d in data]).float().to(dev)
+    err = cv_utils.pose_errors(ours["best_model"], matches.to(dev), R_gt, t_gt)[:, 0]
+    a_dev = pose_eval.auc(err.max(dim=-1).values.cpu().tolist())
+    return dict(auc5_10_20_ours=a, auc5_10_20_cpu_reference=r, auc5_10_20_ours_device_pose=a_dev,
+                same_best_hypothesis=f"{same}/{pairs}",
                 sample=f"{pairs} synthetic pairs x {K} hyps x {N} corrs, identical injected Gumbel noise, "
                        "pose from cv2.recoverPose, AUC as cv_utils.py:528-546")
 

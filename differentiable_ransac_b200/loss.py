@@ -4,7 +4,7 @@ from __future__ import annotations
 import numpy as np
 import torch
 
-from . import engine
+from . import cv_utils, engine
 
 
 def denormalize_pts(pts, im_size):
@@ -18,19 +18,11 @@ def normalize_keypoints_tensor(pts, K):
 
 
 def gt_inlier_mask(gt_E, pts1, pts2):
-    """The reference asks cv2.recoverPose for the inliers of the GT model (loss.py:126-135, on the
-    host, non-differentiable).  Falls back to a Sampson threshold if OpenCV is unavailable."""
-    try:
-        import cv2
-
-        _, _, _, inl = cv2.recoverPose(np.asarray(gt_E, dtype=np.float64), pts1.detach().cpu().numpy()[:, None],
-                                       pts2.detach().cpu().numpy()[:, None], np.eye(3))
-        return torch.from_numpy(inl.ravel() > 0).to(pts1.device)
-    except ImportError:
-        from .scorings.msac_score import sampson_sq
-
-        m = torch.cat((pts1, pts2), -1)
-        return sampson_sq(m, torch.as_tensor(gt_E, device=m.device, dtype=m.dtype)) < 1e-5
+    """loss.py:126-135 asks cv2.recoverPose, on the host, for the correspondences that lie in front of both
+    cameras under the ground-truth pose; `drb_recover_pose` returns the same mask without leaving the device."""
+    m = torch.cat((pts1, pts2), -1).detach().float()[None]
+    E = torch.as_tensor(np.asarray(gt_E, dtype=np.float32) if not torch.is_tensor(gt_E) else gt_E)
+    return cv_utils.gt_inlier_mask(E.to(m.device).float().reshape(1, 3, 3), m)[0]
 
 
 class MatchLoss(object):

@@ -215,6 +215,28 @@ def refit_f8(matches, mask=None, weights=None):
     return _refit("drb_refit_f8", 1, matches, mask, weights)
 
 
+def recover_pose(E, matches, npts=None, R_gt=None, t_gt=None, dist=50.0, want_mask=True):
+    """E [B,M,3,3] (or [B,3,3]), matches [B,N,4] normalised coordinates -> dict(R [B,M,3,3], t [B,M,3],
+    mask [B,M,N] bool | None, ngood [B,M], err [B,M,2] degrees | None)."""
+    matches = _f32(matches)
+    B, N, _ = matches.shape
+    E = _f32(E).reshape(B, -1, 9)
+    M = E.shape[1]
+    dev = matches.device
+    R = torch.empty(B, M, 3, 3, dtype=torch.float32, device=dev)
+    t = torch.empty(B, M, 3, dtype=torch.float32, device=dev)
+    mask = torch.empty(B, M, N, dtype=torch.uint8, device=dev) if want_mask else None
+    ngood = torch.empty(B, M, dtype=torch.int32, device=dev)
+    have_gt = R_gt is not None and t_gt is not None
+    err = torch.empty(B, M, 2, dtype=torch.float32, device=dev) if have_gt else None
+    lib = _lib.load()
+    check(lib.drb_recover_pose(_p(E), _p(matches), _p(None if npts is None else _i32(npts)),
+                               _p(_f32(R_gt).reshape(B, 9) if have_gt else None),
+                               _p(_f32(t_gt).reshape(B, 3) if have_gt else None), B, M, N, float(dist), _p(R), _p(t),
+                               _p(mask), _p(ngood), _p(err), _stream()), "drb_recover_pose")
+    return dict(R=R, t=t, mask=None if mask is None else mask.view(torch.bool), ngood=ngood, err=err)
+
+
 def solve_rigid3(points, idx=None, flag=True):
     points, idx, B, K, N = _rows(points, idx, 3, 6)
     models = torch.empty(B, K, 4, 4, dtype=torch.float32, device=points.device)

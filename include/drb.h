@@ -186,6 +186,19 @@ int drb_refit_e5(const float* matches, const uint8_t* mask, const float* weights
 int drb_refit_f8(const float* matches, const uint8_t* mask, const float* weights, int B, int N,
                  float* models, int32_t* nsol, void* stream);
 
+/* ---- pose from an essential matrix ------------------------------------------
+ * Replaces cv_utils.recoverPose / decompose_E / cheirality_check (cv_utils.py:48-116, :179-189; host loop
+ * around cv2.triangulatePoints), cv2.recoverPose as MatchLoss uses it for the ground-truth inlier mask
+ * (loss.py:126-135) and evaluate_R_t_tensor behind eval_essential_matrix (cv_utils.py:361-378, :503-525).
+ * E[B,M,9] (x2^T E x1 = 0, any scale), matches[B,N,4] in normalised camera coordinates, npts[B] nullable
+ * (only the first npts[b] correspondences vote), dist = OpenCV's distanceThresh (the reference: 50).
+ * Out: R[B,M,9], t[B,M,3] (unit) of the pose with the most correspondences in front of both cameras,
+ * mask[B,M,N] (nullable) = those correspondences, ngood[B,M]; with R_gt[B,9], t_gt[B,3] also
+ * err[B,M,2] = (rotation, translation) angular error in degrees.  Arithmetic in double.            */
+int drb_recover_pose(const float* E, const float* matches, const int32_t* npts, const float* R_gt,
+                     const float* t_gt, int B, int M, int N, float dist, float* R, float* t, uint8_t* mask,
+                     int32_t* ngood, float* err, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

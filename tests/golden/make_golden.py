@@ -303,9 +303,43 @@ def refit_and_full_driver():
              best_mask=bmask, best_score=bs, iterations=its, F_gt=Fgt8)
 
 
+def pose_recovery():
+    """pose from E (`cv_utils.recoverPose`, `eval_essential_matrix`) and the ground-truth
+    inlier mask `MatchLoss` asks `cv2.recoverPose` for (loss.py:126-135), by the reference / its OpenCV."""
+    import cv2
+    from cv_utils import eval_essential_matrix, recoverPose
+    out = {}
+    cases = []
+    for i, (ratio, seed, small) in enumerate([(0.6, 41, True), (0.4, 42, True), (0.7, 43, False), (0.5, 44, False)]):
+        m, Egt, inl, R, t = synth.relative_pose_pair(600, ratio, seed=seed, noise=3e-4, small_motion=small,
+                                                     return_pose=True)
+        g = torch.Generator().manual_seed(seed)
+        # candidates: the GT model, a slightly wrong one, a badly wrong one
+        Es = [Egt, Egt + 0.02 * torch.randn(3, 3, generator=g), torch.randn(3, 3, generator=g)]
+        cases.append((m, Egt, inl, R, t, Es))
+    for i, (m, Egt, inl, R, t, Es) in enumerate(cases):
+        p1, p2 = m[:, :2].numpy(), m[:, 2:].numpy()
+        Rs, ts, errs = [], [], []
+        for E in Es:
+            Rr, tr = recoverPose(E.double(), p1, p2, True)
+            Rs.append(Rr)
+            ts.append(tr.flatten())
+            eq, et = eval_essential_matrix(p1, p2, E.double(), R.double(), t.double())
+            errs.append(torch.stack((torch.as_tensor(eq), torch.as_tensor(et))))
+        n, Rc, tc, mk = cv2.recoverPose(Egt.numpy().astype(np.float64), p1[:, None].copy(), p2[:, None].copy(),
+                                        np.eye(3))
+        out.update({f"matches_{i}": m, f"E_{i}": torch.stack(Es), f"R_gt_{i}": R, f"t_gt_{i}": t, f"inl_{i}": inl,
+                    f"R_{i}": torch.stack(Rs), f"t_{i}": torch.stack(ts), f"err_{i}": torch.stack(errs),
+                    f"cv_mask_{i}": mk.ravel() > 0, f"cv_R_{i}": Rc, f"cv_t_{i}": tc.ravel(), f"cv_n_{i}": n})
+    save("pose", n_cases=len(cases), **out)
+
+
 if __name__ == "__main__":
-    if "refit" in sys.argv[1:]:
+    if "pose" in sys.argv[1:]:
+        pose_recovery()
+    elif "refit" in sys.argv[1:]:
         refit_and_full_driver()
     else:
         main()
         refit_and_full_driver()
+        pose_recovery()

@@ -12,6 +12,7 @@
 #include "f8_math.cuh"
 #include "rigid_math.cuh"
 #include "refit_math.cuh"
+#include "pose_math.cuh"
 
 namespace {
 template <class T>
@@ -164,6 +165,28 @@ int hc_refit(int fmat, const float* matches, const unsigned char* mask, const fl
     for (int k = 0; k < n_out; ++k)
         for (int i = 0; i < 9; ++i) models[k * 9 + i] = (float)E[k][i];
     return n_out;
+}
+
+// Serial restatement of pose.cu: decompose, vote over the correspondences, pick the pose, mask, errors.
+int hc_recover_pose(const double* E, const float* matches, int N, double dist, const double* R_gt,
+                    const double* t_gt, double* R, double* t, unsigned char* mask, int* counts, double* err) {
+    drb::PoseCandidates<double> pc;
+    if (!drb::decompose_essential<double>(E, pc)) return -1;
+    std::vector<int> bits(N);
+    for (int c = 0; c < 4; ++c) counts[c] = 0;
+    for (int n = 0; n < N; ++n) {
+        bits[n] = drb::cheirality_bits<double>(pc, matches[n * 4], matches[n * 4 + 1], matches[n * 4 + 2],
+                                               matches[n * 4 + 3], dist);
+        for (int c = 0; c < 4; ++c) counts[c] += (bits[n] >> c) & 1;
+    }
+    int best = 0;
+    for (int c = 1; c < 4; ++c)
+        if (counts[c] > counts[best]) best = c;
+    for (int i = 0; i < 9; ++i) R[i] = (best & 1) ? pc.R2[i] : pc.R1[i];
+    for (int i = 0; i < 3; ++i) t[i] = (best & 2) ? -pc.t[i] : pc.t[i];
+    for (int n = 0; n < N; ++n) mask[n] = (bits[n] >> best) & 1;
+    if (R_gt && t_gt) drb::pose_errors_deg<double>(R, t, R_gt, t_gt, err[0], err[1]);
+    return best;
 }
 
 int hc_roots_f32(const float* coef, float* roots) { return drb::real_roots_deg10<float>(coef, roots); }

@@ -189,3 +189,27 @@ def test_refit_f8_matches_reference(lib, golden):
     few = torch.zeros(2000, dtype=torch.bool)
     few[:7] = True
     assert run_refit(lib, True, g["matches"], few).shape[0] == 0
+
+
+def test_pose_recovery_math_against_reference(lib, golden):
+    """csrc/pose_math.cuh on the host: R, t, errors of `cv_utils.recoverPose` / `eval_essential_matrix` and the
+    cheirality mask of cv2.recoverPose, from the reference-generated fixture."""
+    g = golden("pose")
+    for i in range(int(g["n_cases"])):
+        m = np.ascontiguousarray(g[f"matches_{i}"].numpy(), dtype=np.float32)
+        N = m.shape[0]
+        Rg = np.ascontiguousarray(g[f"R_gt_{i}"].numpy(), dtype=np.float64)
+        tg = np.ascontiguousarray(g[f"t_gt_{i}"].numpy(), dtype=np.float64)
+        for j in range(3):
+            E = np.ascontiguousarray(g[f"E_{i}"][j].numpy(), dtype=np.float64)
+            R, t, err = np.zeros(9), np.zeros(3), np.zeros(2)
+            mask, cnt = np.zeros(N, np.uint8), np.zeros(4, np.int32)
+            best = lib.hc_recover_pose(vp(E), vp(m), N, ctypes.c_double(50.0), vp(Rg), vp(tg), vp(R), vp(t), vp(mask),
+                                       vp(cnt), vp(err))
+            assert best >= 0
+            assert abs(R.reshape(3, 3) - g[f"R_{i}"][j].numpy()).max() < 1e-9
+            assert abs(t - g[f"t_{i}"][j].numpy()).max() < 1e-9
+            assert abs(err - g[f"err_{i}"][j].numpy()).max() < 1e-5
+            if j == 0:
+                assert (mask.astype(bool) == g[f"cv_mask_{i}"].numpy().astype(bool)).all()
+                assert int(cnt.max()) == int(g[f"cv_n_{i}"])

@@ -146,3 +146,19 @@ def test_full_test_driver(golden, name, fmat, s):
     assert abs(float(score) - float(g["best_score"])) < 1e-3 * float(g["best_score"])
     assert min((model - g["best_model"]).abs().max(), (model + g["best_model"]).abs().max()) < 1e-4
     assert (mask != g["best_mask"].bool()).sum() <= 1
+
+
+def test_pose_recovery_restatement(golden):
+    """`cv_utils.recoverPose` / `eval_essential_matrix` and OpenCV's recoverPose mask as
+    MatchLoss uses it (rank 3)."""
+    from oracle import pose_eval
+    g = golden("pose")
+    for i in range(int(g["n_cases"])):
+        m = g[f"matches_{i}"].numpy()
+        for j in range(3):
+            R, t, mask, _ = pose_eval.recover_pose_ref(g[f"E_{i}"][j].numpy(), m[:, :2], m[:, 2:])
+            assert abs(R - g[f"R_{i}"][j].numpy()).max() < 1e-9 and abs(t - g[f"t_{i}"][j].numpy()).max() < 1e-9
+            er, et = pose_eval.pose_error_ref(R, t, g[f"R_gt_{i}"].numpy(), g[f"t_gt_{i}"].numpy())
+            assert abs(er - float(g[f"err_{i}"][j, 0])) < 1e-5 and abs(et - float(g[f"err_{i}"][j, 1])) < 1e-5
+            if j == 0:
+                assert (mask == g[f"cv_mask_{i}"].numpy().astype(bool)).all()
