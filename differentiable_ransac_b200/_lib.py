@@ -4,7 +4,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import c_char_p, c_float, c_int, c_uint64, c_void_p
+from ctypes import c_char_p, c_double, c_float, c_int, c_uint64, c_void_p
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libdrb.so")
@@ -29,6 +29,8 @@ _SIGNATURES = {
     "drb_solve_f7": ([P, P, c_int, c_int, c_int, P, P, P], c_int),
     "drb_refit_e5": ([P, P, P, c_int, c_int, P, P, P], c_int),
     "drb_refit_f8": ([P, P, P, c_int, c_int, P, P, P], c_int),
+    "drb_adaptive_select": ([P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
+                             c_double, P, P, P, P, P], c_int),
     "drb_recover_pose": ([P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P, P], c_int),
     "drb_solve_rigid3": ([P, P, c_int, c_int, c_int, c_int, P, P, P], c_int),
     "drb_solve_rigid3_backward": ([P, P, c_int, c_int, c_int, c_int, P, P, P, P], c_int),

@@ -13,6 +13,7 @@
 #include "../../include/drb.h"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
+#include "sampson.cuh"
 #include "tile_pipe.cuh"
 
 namespace drb {
@@ -24,29 +25,6 @@ constexpr int kTile = 1024;       // 2-D correspondences (16 B) per stage (episy
 constexpr int kMsacThreads = 32;
 constexpr int kMsacTile = 192;
 constexpr int kTileRigid = 768;   // 3-D correspondences (24 B) per stage
-
-__device__ __forceinline__ unsigned long long pack_best(float score, int id) {
-    // scores are >= 0, so the float bit pattern is monotone; ~id breaks ties towards the
-    // lowest id (torch.argmax returns the first maximum).  NaN never wins.
-    if (!(score >= 0.f)) return 0ull;
-    return ((unsigned long long)__float_as_uint(score) << 32) | (unsigned long long)(0xffffffffu - (unsigned)id);
-}
-
-// Sampson distance pieces for x2^T M x1
-struct Sampson {
-    float r, j;
-};
-__device__ __forceinline__ Sampson sampson(const float* m, float x1, float y1, float x2, float y2) {
-    const float e0 = fmaf(m[0], x1, fmaf(m[1], y1, m[2]));
-    const float e1 = fmaf(m[3], x1, fmaf(m[4], y1, m[5]));
-    const float e2 = fmaf(m[6], x1, fmaf(m[7], y1, m[8]));
-    const float f0 = fmaf(m[0], x2, fmaf(m[3], y2, m[6]));
-    const float f1 = fmaf(m[1], x2, fmaf(m[4], y2, m[7]));
-    Sampson s;
-    s.r = fmaf(x2, e0, fmaf(y2, e1, e2));
-    s.j = fmaf(e0, e0, fmaf(e1, e1, fmaf(f0, f0, f1 * f1)));
-    return s;
-}
 
 template <bool SCHED>
 __global__ void __launch_bounds__(kMsacThreads)

@@ -110,6 +110,50 @@ def ransac_f7_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     return out
 
 
+# ---- the chunked loop with adaptive exit, no host sync -----------------------
+def ransac_test_adaptive(matches, logits, rbs, max_iterations, thr, sample_size=5, confidence=0.999, eps=1e-5,
+                         tau=1.0, noise=None, seed=0, offset=0, sampler="sets"):
+    """What `RANSAC.__call__` returns in test mode with lo = 0 (ransac.py:55-144) for B pairs at once: all
+    C = ceil(max_iterations / rbs) chunks go through sample -> solve -> score in one pass, then
+    `drb_adaptive_select` replays the loop's bookkeeping (per-chunk arg-max, strict improvement, adaptive
+    iteration budget from the winner's inlier count) on the device.  `noise` (optional) is [B, C*rbs, N], chunk c
+    = rows [c*rbs, (c+1)*rbs).  -> dict(best_model, best_id, best_score, mask, ninl, iterations [B], ...)."""
+    B = matches.shape[0]
+    C = -(-int(max_iterations) // int(rbs))
+    K = C * int(rbs)
+    idx = _draw(logits, K, sample_size, tau, noise, seed, offset, sampler)
+    if sample_size == 5:
+        slots = ops.E5_SLOTS
+        best0, cc0 = ops.zeroed_counters(B, matches.device)
+        models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True, ccount=cc0)
+        scores, _ = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True, best=best0)
+        extra = dict(nsol=nsol)
+    elif sample_size == 7:
+        slots = ops.F7_SLOTS
+        models, nsol = ops.solve_f7(matches, idx)
+        live = torch.arange(slots, device=models.device)[None, None, :] < nsol[..., None]
+        scored = torch.where(live[..., None, None], models, torch.full_like(models, float("nan"))).reshape(B, -1, 9)
+        scores, _ = ops.score_msac(matches, scored, thr, want_scores=True)
+        cc = cid = None
+        extra = dict(nsol=nsol)
+    elif sample_size == 8:
+        slots = 1
+        models, valid = ops.solve_f8(matches, idx)
+        scores, _ = ops.score_msac(matches, models, thr, want_scores=True)
+        cc = cid = None
+        extra = dict(valid=valid.bool())
+    else:
+        raise NotImplementedError("test mode supports the 5-, 7- and 8-point samplers")
+    dense = models.reshape(B, -1, 9)
+    best, its, chunk_best, chunk_ninl = ops.adaptive_select(matches, dense, scores, thr, int(rbs) * slots, rbs,
+                                                            max_iterations, sample_size, confidence, eps, cc, cid)
+    best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, dense, best, thr)
+    out = dict(best_model=best_model, best_id=best_id, best_score=best_score, mask=mask.view(torch.bool), ninl=ninl,
+               iterations=its, idx=idx, models=models, chunk_ninl=chunk_ninl)
+    out.update(extra)
+    return out
+
+
 # ---- after the loop: local optimisation and the final refit (SURVEY 8f rank 1) -----------------
 def _fit_and_score(matches, mask, thr, fmat, weights=None):
     """Non-minimal fit on the selected correspondences of every pair, scored on all correspondences:

@@ -275,6 +275,29 @@ def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, bes
     return scores, best
 
 
+def adaptive_select(matches, models_dense, scores, thr, span, rbs, max_iterations, sample_size, confidence=0.999,
+                    eps=1e-5, count=None, ids=None):
+    """Replay of the reference's chunked loop with adaptive exit on per-model scores (see drb.h):
+    -> best_packed [B] (for best_finalize), iterations [B], chunk_best [B,C], chunk_ninl [B,C]."""
+    matches = _f32(matches)
+    B, N, _ = matches.shape
+    md = _f32(models_dense).reshape(B, -1, 9)
+    scores = _f32(scores).reshape(B, -1)
+    C = -(-int(max_iterations) // int(rbs))
+    dev = matches.device
+    chunk_best = torch.empty(B, C, dtype=torch.int64, device=dev)
+    chunk_ninl = torch.empty(B, C, dtype=torch.int32, device=dev)
+    best = torch.empty(B, dtype=torch.int64, device=dev)
+    its = torch.empty(B, dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    check(lib.drb_adaptive_select(_p(matches), _p(md), _p(scores), _p(None if count is None else _i32(count)),
+                                  _p(None if ids is None else _i32(ids)), _p(_f32(thr).reshape(B)), B, scores.shape[1],
+                                  md.shape[1], N, int(span), int(rbs), int(max_iterations), int(sample_size),
+                                  float(confidence), float(eps), _p(chunk_best), _p(chunk_ninl), _p(best), _p(its),
+                                  _stream()), "drb_adaptive_select")
+    return best, its, chunk_best, chunk_ninl
+
+
 def best_finalize(matches, models_dense, best_packed, thr, want_mask=True):
     matches = _f32(matches)
     B, N, _ = matches.shape

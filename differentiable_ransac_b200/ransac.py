@@ -86,43 +86,61 @@ class RANSAC(object):
             out[c * rbs] = models[0, sl][valid[0, sl]]
         return out, [], 0, K
 
-    def _test(self, matches, logits, threshold):
-        rbs = self.ransac_batch_size
-        dev = matches.device
-        thr = torch.tensor([threshold], device=dev, dtype=torch.float32)
-        N = matches.shape[0]
-        m, lg = matches[None].float(), logits[None].float()
-        best = None
-        iterations, max_iters = 0, self.max_iterations
-        noise = self.sampler.injected_noise
-        chunk, last_noise = 0, None
+    def _run(self):
+        run = {5: engine.ransac_e5_test, 7: engine.ransac_f7_test, 8: engine.ransac_f8_test}.get(self.sample_size)
+        if run is None:
+            raise NotImplementedError("test mode supports the 5-, 7- and 8-point samplers")
+        return run
+
+    def _loop(self, m, lg, thr, noise):
+        """ransac.py:55-144 for B pairs without LO, no host sync: every chunk in one pass, the loop's bookkeeping
+        (and its adaptive exit) replayed on the device.  noise: [B, chunks*rbs, N] or None."""
+        rbs, K = self.ransac_batch_size, self._chunks() * self.ransac_batch_size
+        off = self.sampler._next_offset()
+        if self.adaptive:
+            return engine.ransac_test_adaptive(m, lg, rbs, self.max_iterations, thr, self.sample_size,
+                                               self.confidence, self.eps, self.sampler.tau, noise, self.sampler.seed,
+                                               off)
+        out = self._run()(m, lg, K, thr, self.sampler.tau, noise, self.sampler.seed, off)
+        out["iterations"] = torch.full((m.shape[0],), K, dtype=torch.int32, device=m.device)
+        return out
+
+    def _loop_with_lo(self, m, lg, thr, noise):
+        """The same loop when LO runs after every improvement (ransac.py:122-132): the next comparison depends on
+        the optimised score, so the chunks are sequential -- one pair, one host sync per chunk, like the
+        reference."""
+        if self.lo not in (1, 2):
+            raise NotImplementedError("lo=3 needs the reference's UniformSampler, which cannot run (SURVEY 2.1 #5)")
+        rbs, N = self.ransac_batch_size, m.shape[1]
+        best, iterations, max_iters, chunk = None, 0, self.max_iterations, 0
         while iterations < max_iters:
-            nz = None
-            if noise is not None:
-                nz = noise.reshape(-1, rbs, noise.shape[-1])[chunk][None]
-            run = {5: engine.ransac_e5_test, 7: engine.ransac_f7_test, 8: engine.ransac_f8_test}.get(self.sample_size)
-            if run is None:
-                raise NotImplementedError("test mode supports the 5-, 7- and 8-point samplers")
-            out = run(m, lg, rbs, thr, self.sampler.tau, nz, self.sampler.seed, self.sampler._next_offset())
+            nz = None if noise is None else noise[:, chunk * rbs:(chunk + 1) * rbs]
+            out = self._run()(m, lg, rbs, thr, self.sampler.tau, nz, self.sampler.seed, self.sampler._next_offset())
             if best is None or bool(out["best_score"][0] > best["best_score"][0]):     # ransac.py:116
-                best = out
-                if self.lo in (1, 2):                                                  # ransac.py:122-132
-                    best = engine.local_optimization(m, best, thr, self.fmat, self.lo_iters if self.lo == 2 else 1)
-                elif self.lo:
-                    raise NotImplementedError("lo=3 needs the reference's UniformSampler, which cannot run "
-                                              "(SURVEY 2.1 #5)")
+                best = engine.local_optimization(m, out, thr, self.fmat, self.lo_iters if self.lo == 2 else 1)
                 if self.adaptive:
                     max_iters = min(self.max_iterations,
                                     self.adaptive_iteration_number(int(best["ninl"][0]), N, self.confidence))
             iterations += rbs
             chunk += 1
-            last_noise = nz
+        best["iterations"] = torch.full((1,), iterations, dtype=torch.int32, device=m.device)
+        return best
+
+    def _test(self, matches, logits, threshold):
+        dev = matches.device
+        thr = torch.tensor([threshold], device=dev, dtype=torch.float32)
+        m, lg = matches[None].float(), logits[None].float()
+        noise = self.sampler.injected_noise
+        if noise is not None:
+            noise = noise.reshape(1, -1, noise.shape[-1])
+        best = self._loop_with_lo(m, lg, thr, noise) if self.lo else self._loop(m, lg, thr, noise)
+        iterations = int(best["iterations"][0])
         if self.final_refit:
             # ransac.py:148-185.  `weighted` hands the eight-point the soft one-hot of the last chunk's first
             # sample (:153); that row exists only when the noise is injected, otherwise softmax(logits / tau).
             w = None
             if self.fmat and self.weighted:
-                key = lg if last_noise is None else lg + last_noise[:, 0].to(lg.dtype)
+                key = lg if noise is None else lg + noise[:, iterations - self.ransac_batch_size].to(lg.dtype)
                 w = torch.softmax(key / self.sampler.tau, dim=-1)
             best = engine.final_refit(m, best, thr, self.fmat, w)
         best_model, best_mask, best_score = best["best_model"][0], best["mask"][0], best["best_score"][0]
@@ -130,13 +148,19 @@ class RANSAC(object):
 
     # -- B pairs at once (replaces the python loop of model_cl.py:488-510) ---------------------------
     def batched_test(self, matches, logits, thresholds, K=None):
-        """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict for K hypotheses per pair
-        (default: max_iterations, no early exit), followed by the optional LO pass and the final refit for all
-        pairs at once."""
-        K = K or self.max_iterations
-        run = {5: engine.ransac_e5_test, 7: engine.ransac_f7_test, 8: engine.ransac_f8_test}[self.sample_size]
-        out = run(matches, logits, K, thresholds, self.sampler.tau, None, self.sampler.seed, self.sampler._next_offset())
+        """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict with, per pair, exactly what
+        `__call__` returns for it (winner, inlier mask, score, `iterations` [B]): the chunked loop with its
+        adaptive exit replayed on the device, then the optional LO pass and the final refit for all pairs at
+        once.  `K` overrides max_iterations for this call."""
+        keep = self.max_iterations
+        if K:
+            self.max_iterations = int(K)
+        try:
+            out = self._loop(matches, logits, thresholds, None)
+        finally:
+            self.max_iterations = keep
         if self.lo in (1, 2):
+            # batched LO runs once on the loop's winner (inside the loop it is sequential per pair: `__call__`)
             out = engine.local_optimization(matches, out, thresholds, self.fmat, self.lo_iters if self.lo == 2 else 1)
         if self.final_refit:
             out = engine.final_refit(matches, out, thresholds, self.fmat)

@@ -186,6 +186,20 @@ int drb_refit_e5(const float* matches, const uint8_t* mask, const float* weights
 int drb_refit_f8(const float* matches, const uint8_t* mask, const float* weights, int B, int N,
                  float* models, int32_t* nsol, void* stream);
 
+/* ---- the chunked test-mode loop with adaptive termination, replayed on the device -
+ * Replaces the bookkeeping of `while iterations < max_iters` (ransac.py:55-144): per-chunk arg-max (:114),
+ * keep-if-strictly-better (:116), adaptive_iteration_number from the winner's inlier count (:134-142, :202-215).
+ * Call after drb_score_msac with `scores` requested, for all C = ceil(max_iterations / rbs) chunks at once:
+ * scores[B,M] with optional count[B] / ids[B,M] exactly as handed to drb_score_msac; models_dense[B,Md,9];
+ * a chunk is `span` consecutive dense model ids (rbs * slots per sample).  chunk_best[B,C] and chunk_ninl[B,C]
+ * are caller-provided scratch (left filled: per-chunk winner key and its inlier count).
+ * Out: best_packed[B] (feed to drb_best_finalize) and iterations[B] = what the reference's loop would return. */
+int drb_adaptive_select(const float* matches, const float* models_dense, const float* scores,
+                        const int32_t* count, const int32_t* ids, const float* thr, int B, int M, int Md,
+                        int N, int span, int rbs, int max_iterations, int sample_size, double confidence,
+                        double eps, unsigned long long* chunk_best, int32_t* chunk_ninl,
+                        unsigned long long* best_packed, int32_t* iterations, void* stream);
+
 /* ---- pose from an essential matrix ------------------------------------------
  * Replaces cv_utils.recoverPose / decompose_E / cheirality_check (cv_utils.py:48-116, :179-189; host loop
  * around cv2.triangulatePoints), cv2.recoverPose as MatchLoss uses it for the ground-truth inlier mask
