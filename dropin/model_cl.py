@@ -1,8 +1,9 @@
 """Drop-in `model_cl` for the reference's scripts (train.py:6, test.py:3 do `from model_cl import *`).
 
 Everything the reference module defines (CLNet backbone, DS_Block, ...) is re-exported untouched;
-`RANSACLayer` / `RANSACLayer3D` are replaced by the B200 host mirror and `DeepRansac_CLNet.forward`
-hands the WHOLE batch to one launch per stage instead of the python loop of model_cl.py:488-510.
+`RANSACLayer` / `RANSACLayer3D` and the pose evaluation (`eval_essential_matrix`, `recoverPose`, `AUC`) are
+replaced by the B200 host mirror and `DeepRansac_CLNet.forward` hands the WHOLE batch to one launch per stage
+instead of the python loop of model_cl.py:488-510.
 Checkpoints are unaffected: RANSACLayer has no parameters."""
 import time
 
@@ -15,6 +16,10 @@ _ref = load_reference_module("model_cl")
 globals().update({k: v for k, v in vars(_ref).items() if not k.startswith("__")})
 
 from differentiable_ransac_b200.model_cl import RANSACLayer, RANSACLayer3D, batch_episym  # noqa: E402,F401
+# test.py:71-76 evaluates every pair with eval_essential_matrix, which reaches the scripts through this module's
+# `from cv_utils import *` (model_cl.py:10): pose recovery and the angular errors on the device instead of the
+# torch + cv2.triangulatePoints host loop of cv_utils.py:48-189
+from differentiable_ransac_b200.cv_utils import AUC, eval_essential_matrix, recoverPose  # noqa: E402,F401
 
 
 class DeepRansac_CLNet(_ref.DeepRansac_CLNet):

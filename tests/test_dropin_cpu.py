@@ -22,6 +22,9 @@ assert isinstance(model.ransac_layer, ours.RANSACLayer), type(model.ransac_layer
 assert RANSACLayer is ours.RANSACLayer and RANSACLayer3D is ours.RANSACLayer3D
 import differentiable_ransac_b200.loss as ol
 assert MatchLoss is ol.MatchLoss and 'PoseLoss' in globals() and 'CLNet' in globals()
+import differentiable_ransac_b200.cv_utils as oc
+assert eval_essential_matrix is oc.eval_essential_matrix and recoverPose is oc.recoverPose and AUC is oc.AUC
+assert 'evaluate_R_t' in globals() and 'denormalize_pts' in globals()       # the rest of cv_utils stays the reference's
 sd = torch.load('/root/reference/pretrained_models/saved_model_5PC_l_epi/model.net', map_location='cpu')
 missing, unexpected = model.load_state_dict(sd, strict=True), None
 print('OK', len(sd), sum(p.numel() for p in model.parameters()))

@@ -78,7 +78,7 @@ def test_cfg4_rigid_full_size():
             M = models[b, k].detach().double().cpu()
             p = pts[b].double().cpu()
             want = ((p[:, 3:] - (p[:, :3] @ M[:3, :3].T + M[:3, 3])) ** 2).sum()
-            assert abs(float(res[b, k]) - float(want)) < 1e-4 * float(want)
+            assert abs(float(res[b, k].detach()) - float(want)) < 1e-4 * float(want)
         if flag:
             res.mean().backward()
             assert torch.isfinite(logits.grad).all() and logits.grad.abs().sum() > 0
