@@ -8,12 +8,21 @@
 #pragma once
 
 #include "drb_common.cuh"
+#include "dual.cuh"
 #include "small_eig.cuh"
 
 namespace drb {
 
 DRB_HD float t_acos(float x) { return acosf(x); }
 DRB_HD double t_acos(double x) { return acos(x); }
+template <class T, int P>
+DRB_HD Dual<T, P> t_acos(const Dual<T, P>& a) {
+    Dual<T, P> r;
+    r.v = t_acos(a.v);
+    const T g = T(-1) / t_sqrt(T(1) - a.v * a.v);   // infinite at |x| = 1, as torch.arccos's backward
+    for (int i = 0; i < P; ++i) r.d[i] = a.d[i] * g;
+    return r;
+}
 
 template <class T>
 struct PoseCandidates {
@@ -71,6 +80,52 @@ DRB_HD bool decompose_essential(const T* E, PoseCandidates<T>& pc) {
     bool ok = true;
     for (int i = 0; i < 3; ++i) pc.t[i] = u3[i];
     for (int i = 0; i < 9; ++i) ok = ok && (pc.R1[i] == pc.R1[i]) && (pc.R2[i] == pc.R2[i]);
+    return ok;
+}
+
+// Horn's closed form (cv_utils.new_decompose_E, cv_utils.py:118-165; what PoseLoss uses, loss.py:17-30 `svd=False`):
+// b = sqrt(tr(E E^T)/2) * (e_i x e_j)/|e_i x e_j| for the largest pairwise cross product of the COLUMNS of E,
+// R1,2 = (Cof(E) -+ [b]x E) / (b.b), t = b/|b|.  The reference builds [b]x with torch.tensor(...) of tensor
+// elements, which cuts the graph: [b]x is a constant for the gradient (detach_value), everything else is
+// differentiated.  Cof(E) is formed from cross products of the rows (the reference: inv(E)^T det(E), which is
+// the same matrix computed through a nearly singular inverse).
+template <class T>
+DRB_HD bool decompose_essential_horn(const T* E, PoseCandidates<T>& pc) {
+    const T e1[3] = {E[0], E[3], E[6]}, e2[3] = {E[1], E[4], E[7]}, e3[3] = {E[2], E[5], E[8]};
+    T c[3][3];
+    cross3(e1, e2, c[0]);
+    cross3(e2, e3, c[1]);
+    cross3(e3, e1, c[2]);
+    T nrm[3];
+    for (int k = 0; k < 3; ++k) nrm[k] = t_sqrt(c[k][0] * c[k][0] + c[k][1] * c[k][1] + c[k][2] * c[k][2]);
+    int big = 0;  // torch.argmax: first maximum
+    if (nrm[1] > nrm[big]) big = 1;
+    if (nrm[2] > nrm[big]) big = 2;
+    if (!(nrm[big] > T(0))) return false;
+    T tr = T(0);
+    for (int i = 0; i < 9; ++i) tr += E[i] * E[i];
+    const T scale = t_sqrt(T(0.5) * tr);
+    T b[3], bb = T(0);
+    for (int i = 0; i < 3; ++i) {
+        b[i] = scale * c[big][i] / nrm[big];
+        bb += b[i] * b[i];
+    }
+    const T nb = t_sqrt(bb);
+    for (int i = 0; i < 3; ++i) pc.t[i] = b[i] / nb;
+    const T b0 = detach_value(b[0]), b1 = detach_value(b[1]), b2 = detach_value(b[2]);
+    const T Bx[9] = {T(0), -b2, b1, b2, T(0), -b0, -b1, b0, T(0)};
+    T cof[9];
+    cross3(E + 3, E + 6, cof);      // rows of the cofactor matrix = cross products of the other two rows
+    cross3(E + 6, E, cof + 3);
+    cross3(E, E + 3, cof + 6);
+    bool ok = true;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            const T be = Bx[i * 3] * E[j] + Bx[i * 3 + 1] * E[3 + j] + Bx[i * 3 + 2] * E[6 + j];
+            pc.R1[i * 3 + j] = (cof[i * 3 + j] - be) / bb;
+            pc.R2[i * 3 + j] = (cof[i * 3 + j] + be) / bb;
+            ok = ok && (pc.R1[i * 3 + j] == pc.R1[i * 3 + j]) && (pc.R2[i * 3 + j] == pc.R2[i * 3 + j]);
+        }
     return ok;
 }
 

@@ -1,10 +1,11 @@
-"""MatchLoss -- host mirror of `loss.py:107-153` (the `-w2` symmetric-epipolar training loss)."""
+"""MatchLoss (`-w2`, loss.py:107-153), PoseLoss (`-w0`, :11-68) and ClassificationLoss (`-w1`, :71-104) -- host
+mirrors over the CUDA path; none of them leaves the device."""
 from __future__ import annotations
 
 import numpy as np
 import torch
 
-from . import cv_utils, engine
+from . import cv_utils, engine, ops
 
 
 def denormalize_pts(pts, im_size):
@@ -47,3 +48,72 @@ class MatchLoss(object):
             else:
                 losses.append(row.mean())
         return sum(losses) / len(models)
+
+
+class _PoseErrorTerm(torch.autograd.Function):
+    """(err_R + err_t) / 2 in degrees per model, gradient to the models from `drb_pose_loss` (forward-mode duals
+    in the same launch, so the backward is one multiply)."""
+
+    @staticmethod
+    def forward(ctx, models, matches, R_gt, t_gt):
+        err, grad = ops.pose_loss(models.detach(), matches, R_gt, t_gt)
+        ctx.save_for_backward(grad)
+        return err.mean(-1)
+
+    @staticmethod
+    def backward(ctx, g):
+        (grad,) = ctx.saved_tensors
+        return g[..., None, None] * grad, None, None, None
+
+
+class PoseLoss(torch.nn.Module):
+    """`-w0`: average rotation / translation error of every model, host mirror of loss.py:11-68."""
+
+    def __init__(self, fmat=False):
+        super().__init__()
+        self.fmat = fmat
+
+    def forward_average(self, estimated_models, pts1, pts2, gt_R, gt_t, K1=None, K2=None, im_size1=None,
+                        im_size2=None, svd=False):
+        """estimated_models: list over pairs of [K_b,3,3].  The reference evaluates `models[i]` -- the models as
+        handed in, also when `fmat` (loss.py:59 ignores the `Es` it computes at :36) -- against points that are
+        K-normalised when `fmat`; mirrored as is.  `svd=True` differentiates through torch.linalg.svd in the
+        reference, which is singular for an essential matrix (two equal singular values); only the closed-form
+        branch the loss defaults to is provided."""
+        if svd:
+            raise NotImplementedError("PoseLoss differentiates Horn's closed form (svd=False, the reference default)")
+        total = 0.0
+        for b, models in enumerate(estimated_models):
+            if self.fmat:
+                p1 = normalize_keypoints_tensor(denormalize_pts(pts1[b].clone(), im_size1[b]), K1[b])
+                p2 = normalize_keypoints_tensor(denormalize_pts(pts2[b].clone(), im_size2[b]), K2[b])
+            else:
+                p1, p2 = pts1[b], pts2[b]
+            m = torch.cat((p1, p2), -1).detach().float()[None]
+            dev = m.device
+            term = _PoseErrorTerm.apply(models[None].float(), m, torch.as_tensor(gt_R[b]).to(dev).float()[None],
+                                        torch.as_tensor(gt_t[b]).to(dev).float().reshape(1, 3))
+            total = total + term.sum() / models.shape[0]
+        return total / len(estimated_models)
+
+
+class ClassificationLoss(torch.nn.Module):
+    """`-w1`: binary cross-entropy of the predicted weights against the ground-truth inlier mask, host mirror of
+    loss.py:71-104; the mask comes from `drb_recover_pose` instead of cv2.recoverPose on the host."""
+
+    def __init__(self, fmat):
+        super().__init__()
+        self.fmat = fmat
+
+    def forward(self, gt_E, pts1, pts2, logits, K1, K2, im_size1, im_size2):
+        masks = []
+        for b, l in enumerate(logits):
+            if self.fmat:   # cv2.undistortPoints without distortion = (x - c) / f  (loss.py:81-92); K arrives as numpy
+                Ka = torch.as_tensor(K1[b]).to(device=pts1[b].device, dtype=pts1[b].dtype)
+                Kb = torch.as_tensor(K2[b]).to(device=pts2[b].device, dtype=pts2[b].dtype)
+                p1 = normalize_keypoints_tensor(denormalize_pts(pts1[b].clone(), im_size1[b]), Ka)
+                p2 = normalize_keypoints_tensor(denormalize_pts(pts2[b].clone(), im_size2[b]), Kb)
+            else:
+                p1, p2 = pts1[b], pts2[b]
+            masks.append(gt_inlier_mask(gt_E[b], p1, p2).to(l.dtype))
+        return torch.nn.BCELoss()(logits, torch.stack(masks))

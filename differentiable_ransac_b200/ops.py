@@ -237,6 +237,22 @@ def recover_pose(E, matches, npts=None, R_gt=None, t_gt=None, dist=50.0, want_ma
     return dict(R=R, t=t, mask=None if mask is None else mask.view(torch.bool), ngood=ngood, err=err)
 
 
+def pose_loss(E, matches, R_gt, t_gt, npts=None, dist=50.0, want_grad=True):
+    """E [B,M,3,3], matches [B,N,4], R_gt [B,3,3], t_gt [B,3] -> err [B,M,2] degrees (Horn decomposition, as
+    PoseLoss), grad [B,M,3,3] = d((err_R + err_t)/2)/dE or None."""
+    matches = _f32(matches)
+    B, N, _ = matches.shape
+    E = _f32(E).reshape(B, -1, 9)
+    M = E.shape[1]
+    err = torch.empty(B, M, 2, dtype=torch.float32, device=matches.device)
+    grad = torch.empty(B, M, 3, 3, dtype=torch.float32, device=matches.device) if want_grad else None
+    lib = _lib.load()
+    check(lib.drb_pose_loss(_p(E), _p(matches), _p(None if npts is None else _i32(npts)), _p(_f32(R_gt).reshape(B, 9)),
+                            _p(_f32(t_gt).reshape(B, 3)), B, M, N, float(dist), _p(err), _p(grad), _stream()),
+          "drb_pose_loss")
+    return err, grad
+
+
 def solve_rigid3(points, idx=None, flag=True):
     points, idx, B, K, N = _rows(points, idx, 3, 6)
     models = torch.empty(B, K, 4, 4, dtype=torch.float32, device=points.device)

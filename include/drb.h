@@ -212,6 +212,12 @@ int drb_adaptive_select(const float* matches, const float* models_dense, const f
 int drb_recover_pose(const float* E, const float* matches, const int32_t* npts, const float* R_gt,
                      const float* t_gt, int B, int M, int N, float dist, float* R, float* t, uint8_t* mask,
                      int32_t* ngood, float* err, void* stream);
+/* One term of PoseLoss.forward_average per (pair, model) (loss.py:57-63 with its default svd=False): Horn's
+ * closed-form decomposition (cv_utils.py:118-165), the same cheirality vote, err[B,M,2] in degrees and
+ * (nullable) grad[B,M,9] = d((err_R + err_t)/2)/dE -- what autograd returns through the reference's chain,
+ * including its constant [b]x (cv_utils.py:146-150).  Non-finite derivatives (arccos at +-1) are zeroed. */
+int drb_pose_loss(const float* E, const float* matches, const int32_t* npts, const float* R_gt,
+                  const float* t_gt, int B, int M, int N, float dist, float* err, float* grad, void* stream);
 
 #ifdef __cplusplus
 }

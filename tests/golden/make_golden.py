@@ -333,6 +333,29 @@ def pose_recovery():
                     f"cv_mask_{i}": mk.ravel() > 0, f"cv_R_{i}": Rc, f"cv_t_{i}": tc.ravel(), f"cv_n_{i}": n})
     save("pose", n_cases=len(cases), **out)
 
+    # PoseLoss (`-w0`, loss.py:11-68): Horn decomposition + cheirality vote + angular errors under autograd.
+    # Run in fp64 (torch.set_default_dtype makes the `torch.tensor([...])` of cv_utils.py:146-150 double too):
+    # arccos near +-1 amplifies the fp32 noise of inv(E)*det(E) into the second digit of the gradient.
+    from loss import PoseLoss
+    torch.set_default_dtype(torch.float64)
+    try:
+        pl = {}
+        for i, (m, Egt, inl, R, t, _) in enumerate(cases[:3]):
+            g = torch.Generator().manual_seed(100 + i)
+            Es32 = torch.stack([Egt + s * torch.randn(3, 3, generator=g, dtype=torch.float32)
+                                for s in (0.002, 0.01, 0.03, 0.1, 0.3, 1.0)])
+            Es = Es32.double().requires_grad_(True)
+            p1, p2 = m[:, :2].double(), m[:, 2:].double()
+            loss = PoseLoss(False).forward_average([Es], [p1], [p2], R.double()[None], t.double()[None])
+            loss.backward()
+            per = [eval_essential_matrix(p1.numpy(), p2.numpy(), Es[k].detach(), R.double(), t.double(), svd=False)
+                   for k in range(Es.shape[0])]
+            pl.update({f"matches_{i}": m, f"E_{i}": Es32, f"R_gt_{i}": R, f"t_gt_{i}": t, f"loss_{i}": loss.detach(),
+                       f"grad_{i}": Es.grad, f"err_{i}": torch.tensor([[float(a), float(b)] for a, b in per])})
+        save("pose_loss", n_cases=3, **pl)
+    finally:
+        torch.set_default_dtype(torch.float32)
+
 
 if __name__ == "__main__":
     if "pose" in sys.argv[1:]:

@@ -189,6 +189,36 @@ int hc_recover_pose(const double* E, const float* matches, int N, double dist, c
     return best;
 }
 
+// PoseLoss term of one model (loss.py:57-63 with svd=False): Horn decomposition, cheirality vote, then
+// (err_R + err_t) / 2 in degrees and its gradient with respect to E by forward-mode duals.
+int hc_pose_loss(const double* E, const float* matches, int N, double dist, const double* R_gt, const double* t_gt,
+                 double* err, double* grad) {
+    typedef drb::Dual<double, 9> D;
+    drb::PoseCandidates<double> pc;
+    if (!drb::decompose_essential_horn<double>(E, pc)) return -1;
+    int counts[4] = {0, 0, 0, 0};
+    for (int n = 0; n < N; ++n) {
+        const int bits = drb::cheirality_bits<double>(pc, matches[n * 4], matches[n * 4 + 1], matches[n * 4 + 2],
+                                                      matches[n * 4 + 3], dist);
+        for (int c = 0; c < 4; ++c) counts[c] += (bits >> c) & 1;
+    }
+    int best = 0;
+    for (int c = 1; c < 4; ++c)
+        if (counts[c] > counts[best]) best = c;
+    D Ed[9], Rg[9], tg[3], R[9], t[3], er, et;
+    for (int i = 0; i < 9; ++i) { Ed[i] = D::variable(E[i], i); Rg[i] = D(R_gt[i]); }
+    for (int i = 0; i < 3; ++i) tg[i] = D(t_gt[i]);
+    drb::PoseCandidates<D> pd;
+    drb::decompose_essential_horn<D>(Ed, pd);
+    for (int i = 0; i < 9; ++i) R[i] = (best & 1) ? pd.R2[i] : pd.R1[i];
+    for (int i = 0; i < 3; ++i) t[i] = (best & 2) ? -pd.t[i] : pd.t[i];
+    drb::pose_errors_deg<D>(R, t, Rg, tg, er, et);
+    err[0] = er.v;
+    err[1] = et.v;
+    for (int i = 0; i < 9; ++i) grad[i] = 0.5 * (er.d[i] + et.d[i]);
+    return best;
+}
+
 int hc_roots_f32(const float* coef, float* roots) { return drb::real_roots_deg10<float>(coef, roots); }
 int hc_roots_f64(const double* coef, double* roots) { return drb::real_roots_deg10<double>(coef, roots); }
 }

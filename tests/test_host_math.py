@@ -213,3 +213,25 @@ def test_pose_recovery_math_against_reference(lib, golden):
             if j == 0:
                 assert (mask.astype(bool) == g[f"cv_mask_{i}"].numpy().astype(bool)).all()
                 assert int(cnt.max()) == int(g[f"cv_n_{i}"])
+
+
+def test_pose_loss_value_and_gradient_against_reference_autograd(lib, golden):
+    """One PoseLoss term per model (Horn decomposition, cheirality vote, angular errors) and its gradient by
+    forward-mode duals, against the reference's `PoseLoss.forward_average` + autograd run in fp64."""
+    g = golden("pose_loss")
+    for i in range(int(g["n_cases"])):
+        m = np.ascontiguousarray(g[f"matches_{i}"].numpy(), dtype=np.float32)
+        Rg = np.ascontiguousarray(g[f"R_gt_{i}"].numpy(), dtype=np.float64)
+        tg = np.ascontiguousarray(g[f"t_gt_{i}"].numpy(), dtype=np.float64)
+        M = g[f"E_{i}"].shape[0]
+        total = 0.0
+        for j in range(M):
+            E = np.ascontiguousarray(g[f"E_{i}"][j].numpy(), dtype=np.float64)
+            err, grad = np.zeros(2), np.zeros(9)
+            assert lib.hc_pose_loss(vp(E), vp(m), m.shape[0], ctypes.c_double(50.0), vp(Rg), vp(tg), vp(err),
+                                    vp(grad)) >= 0
+            assert abs(err - g[f"err_{i}"][j].numpy()).max() < 1e-8
+            want = g[f"grad_{i}"][j].numpy().ravel() * M          # forward_average divides by the number of models
+            assert abs(grad - want).max() < 1e-7 * abs(want).max()
+            total += err.mean()
+        assert abs(total / M - float(g[f"loss_{i}"])) < 1e-9
