@@ -31,8 +31,8 @@ _SIGNATURES = {
     "drb_refit_f8": ([P, P, P, c_int, c_int, P, P, P], c_int),
     "drb_adaptive_select": ([P, P, P, P, P, P, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_double,
                              c_double, P, P, P, P, P], c_int),
-    "drb_pose_loss": ([P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P], c_int),
-    "drb_recover_pose": ([P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P, P], c_int),
+    "drb_pose_loss": ([P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P], c_int),
+    "drb_recover_pose": ([P, P, P, P, P, c_int, c_int, c_int, c_float, P, P, P, P, P, P, P], c_int),
     "drb_solve_rigid3": ([P, P, c_int, c_int, c_int, c_int, P, P, P], c_int),
     "drb_solve_rigid3_backward": ([P, P, c_int, c_int, c_int, c_int, P, P, P, P], c_int),
     "drb_score_msac": ([P, P, P, P, P, c_int, c_int, c_int, P, P, P], c_int),

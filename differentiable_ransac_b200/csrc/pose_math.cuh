@@ -152,21 +152,26 @@ DRB_HD void triangulate_dlt(const T* R, const T* t, T x1, T y1, T x2, T y2, T* Q
     for (int k = 0; k < 4; ++k) Q[k] = V[k * 4 + best];
 }
 
-// Bit c of the result: the correspondence lies in front of both cameras, closer than `dist`, under pose c
+// The correspondence lies in front of both cameras, closer than `dist`, under pose c of the four
 // (cv_utils.py:184-187: Q_z Q_w > 0, Q_z / Q_w < dist, 0 < (P Q)_z < dist).
+template <class T>
+DRB_HD bool cheirality_one(const PoseCandidates<T>& pc, int c, T x1, T y1, T x2, T y2, T dist) {
+    const T* R = (c & 1) ? pc.R2 : pc.R1;
+    const T sg = (c & 2) ? T(-1) : T(1);
+    const T t[3] = {sg * pc.t[0], sg * pc.t[1], sg * pc.t[2]};
+    T Q[4];
+    triangulate_dlt<T>(R, t, x1, y1, x2, y2, Q);
+    const T X = Q[0] / Q[3], Y = Q[1] / Q[3], Z = Q[2] / Q[3];
+    const T z2 = R[6] * X + R[7] * Y + R[8] * Z + t[2];
+    return Q[2] * Q[3] > T(0) && Z < dist && z2 > T(0) && z2 < dist;
+}
+
+// Bit c of the result = cheirality_one under pose c.
 template <class T>
 DRB_HD int cheirality_bits(const PoseCandidates<T>& pc, T x1, T y1, T x2, T y2, T dist) {
     int bits = 0;
-    for (int c = 0; c < 4; ++c) {
-        const T* R = (c & 1) ? pc.R2 : pc.R1;
-        const T sg = (c & 2) ? T(-1) : T(1);
-        const T t[3] = {sg * pc.t[0], sg * pc.t[1], sg * pc.t[2]};
-        T Q[4];
-        triangulate_dlt<T>(R, t, x1, y1, x2, y2, Q);
-        const T X = Q[0] / Q[3], Y = Q[1] / Q[3], Z = Q[2] / Q[3];
-        const T z2 = R[6] * X + R[7] * Y + R[8] * Z + t[2];
-        if (Q[2] * Q[3] > T(0) && Z < dist && z2 > T(0) && z2 < dist) bits |= 1 << c;
-    }
+    for (int c = 0; c < 4; ++c)
+        if (cheirality_one<T>(pc, c, x1, y1, x2, y2, dist)) bits |= 1 << c;
     return bits;
 }
 

@@ -18,12 +18,26 @@ def normalize_keypoints_tensor(pts, K):
     return (pts - K[:2, 2]) / torch.stack((K[0, 0], K[1, 1]))
 
 
+def _as_E(gt_E, device):
+    E = torch.as_tensor(np.asarray(gt_E, dtype=np.float32) if not torch.is_tensor(gt_E) else gt_E)
+    return E.to(device).float().reshape(-1, 3, 3)
+
+
 def gt_inlier_mask(gt_E, pts1, pts2):
     """loss.py:126-135 asks cv2.recoverPose, on the host, for the correspondences that lie in front of both
     cameras under the ground-truth pose; `drb_recover_pose` returns the same mask without leaving the device."""
     m = torch.cat((pts1, pts2), -1).detach().float()[None]
-    E = torch.as_tensor(np.asarray(gt_E, dtype=np.float32) if not torch.is_tensor(gt_E) else gt_E)
-    return cv_utils.gt_inlier_mask(E.to(m.device).float().reshape(1, 3, 3), m)[0]
+    return cv_utils.gt_inlier_mask(_as_E(gt_E, m.device), m)[0]
+
+
+def gt_inlier_masks(gt_E, p1, p2):
+    """The masks of all pairs of a batch: one launch when the pairs hold the same number of correspondences
+    (the reference's loaders pad to a fixed count), else one per pair."""
+    if len({tuple(a.shape) for a in p1}) == 1:
+        m = torch.stack([torch.cat((a, b), -1) for a, b in zip(p1, p2)]).detach().float()
+        E = torch.cat([_as_E(gt_E[b], m.device) for b in range(len(p1))])
+        return list(cv_utils.gt_inlier_mask(E, m))
+    return [gt_inlier_mask(gt_E[b], p1[b], p2[b]) for b in range(len(p1))]
 
 
 class MatchLoss(object):
@@ -32,17 +46,23 @@ class MatchLoss(object):
 
     def forward(self, models, gt_E, pts1, pts2, K1, K2, im_size1, im_size2, topk_flag=False, k=1, gt_masks=None):
         """models: list over pairs of [K_b,3,3]; returns the scalar of loss.py:152-153."""
-        losses = []
+        Es, p1, p2 = [], [], []
         for b in range(len(models)):
             if self.fmat:
-                Es = K2[b].transpose(-1, -2) @ models[b] @ K1[b]
-                p1 = normalize_keypoints_tensor(denormalize_pts(pts1[b].clone(), im_size1[b]), K1[b])
-                p2 = normalize_keypoints_tensor(denormalize_pts(pts2[b].clone(), im_size2[b]), K2[b])
+                Es.append(K2[b].transpose(-1, -2) @ models[b] @ K1[b])
+                p1.append(normalize_keypoints_tensor(denormalize_pts(pts1[b].clone(), im_size1[b]), K1[b]))
+                p2.append(normalize_keypoints_tensor(denormalize_pts(pts2[b].clone(), im_size2[b]), K2[b]))
             else:
-                Es, p1, p2 = models[b], pts1[b], pts2[b]
-            mask = gt_masks[b] if gt_masks is not None else gt_inlier_mask(gt_E[b], p1, p2)
-            inl = torch.cat((p1[mask], p2[mask]), -1).float()[None]
-            row = engine.EpisymLoss.apply(inl, Es[None].float())[0] / max(inl.shape[1], 1)   # e_l.mean(1)
+                Es.append(models[b])
+                p1.append(pts1[b])
+                p2.append(pts2[b])
+        if gt_masks is None:
+            gt_masks = gt_inlier_masks(gt_E, p1, p2)
+        losses = []
+        for b in range(len(models)):
+            mask = gt_masks[b]
+            inl = torch.cat((p1[b][mask], p2[b][mask]), -1).float()[None]
+            row = engine.EpisymLoss.apply(inl, Es[b][None].float())[0] / max(inl.shape[1], 1)   # e_l.mean(1)
             if topk_flag:
                 losses.append(torch.topk(row, k=k, largest=False).values.mean())
             else:
@@ -106,14 +126,15 @@ class ClassificationLoss(torch.nn.Module):
         self.fmat = fmat
 
     def forward(self, gt_E, pts1, pts2, logits, K1, K2, im_size1, im_size2):
-        masks = []
-        for b, l in enumerate(logits):
+        p1, p2 = [], []
+        for b in range(len(logits)):
             if self.fmat:   # cv2.undistortPoints without distortion = (x - c) / f  (loss.py:81-92); K arrives as numpy
                 Ka = torch.as_tensor(K1[b]).to(device=pts1[b].device, dtype=pts1[b].dtype)
                 Kb = torch.as_tensor(K2[b]).to(device=pts2[b].device, dtype=pts2[b].dtype)
-                p1 = normalize_keypoints_tensor(denormalize_pts(pts1[b].clone(), im_size1[b]), Ka)
-                p2 = normalize_keypoints_tensor(denormalize_pts(pts2[b].clone(), im_size2[b]), Kb)
+                p1.append(normalize_keypoints_tensor(denormalize_pts(pts1[b].clone(), im_size1[b]), Ka))
+                p2.append(normalize_keypoints_tensor(denormalize_pts(pts2[b].clone(), im_size2[b]), Kb))
             else:
-                p1, p2 = pts1[b], pts2[b]
-            masks.append(gt_inlier_mask(gt_E[b], p1, p2).to(l.dtype))
-        return torch.nn.BCELoss()(logits, torch.stack(masks))
+                p1.append(pts1[b])
+                p2.append(pts2[b])
+        masks = gt_inlier_masks(gt_E, p1, p2)
+        return torch.nn.BCELoss()(logits, torch.stack(masks).to(logits.dtype))

@@ -229,12 +229,13 @@ def recover_pose(E, matches, npts=None, R_gt=None, t_gt=None, dist=50.0, want_ma
     ngood = torch.empty(B, M, dtype=torch.int32, device=dev)
     have_gt = R_gt is not None and t_gt is not None
     err = torch.empty(B, M, 2, dtype=torch.float32, device=dev) if have_gt else None
+    votes = torch.empty(B, M, 4, dtype=torch.int32, device=dev)
     lib = _lib.load()
     check(lib.drb_recover_pose(_p(E), _p(matches), _p(None if npts is None else _i32(npts)),
                                _p(_f32(R_gt).reshape(B, 9) if have_gt else None),
-                               _p(_f32(t_gt).reshape(B, 3) if have_gt else None), B, M, N, float(dist), _p(R), _p(t),
-                               _p(mask), _p(ngood), _p(err), _stream()), "drb_recover_pose")
-    return dict(R=R, t=t, mask=None if mask is None else mask.view(torch.bool), ngood=ngood, err=err)
+                               _p(_f32(t_gt).reshape(B, 3) if have_gt else None), B, M, N, float(dist), _p(votes), _p(R),
+                               _p(t), _p(mask), _p(ngood), _p(err), _stream()), "drb_recover_pose")
+    return dict(R=R, t=t, mask=None if mask is None else mask.view(torch.bool), ngood=ngood, err=err, votes=votes)
 
 
 def pose_loss(E, matches, R_gt, t_gt, npts=None, dist=50.0, want_grad=True):
@@ -246,10 +247,11 @@ def pose_loss(E, matches, R_gt, t_gt, npts=None, dist=50.0, want_grad=True):
     M = E.shape[1]
     err = torch.empty(B, M, 2, dtype=torch.float32, device=matches.device)
     grad = torch.empty(B, M, 3, 3, dtype=torch.float32, device=matches.device) if want_grad else None
+    votes = torch.empty(B, M, 4, dtype=torch.int32, device=matches.device)
     lib = _lib.load()
     check(lib.drb_pose_loss(_p(E), _p(matches), _p(None if npts is None else _i32(npts)), _p(_f32(R_gt).reshape(B, 9)),
-                            _p(_f32(t_gt).reshape(B, 3)), B, M, N, float(dist), _p(err), _p(grad), _stream()),
-          "drb_pose_loss")
+                            _p(_f32(t_gt).reshape(B, 3)), B, M, N, float(dist), _p(votes), _p(err), _p(grad),
+                            _stream()), "drb_pose_loss")
     return err, grad
 
 

@@ -208,16 +208,18 @@ int drb_adaptive_select(const float* matches, const float* models_dense, const f
  * (only the first npts[b] correspondences vote), dist = OpenCV's distanceThresh (the reference: 50).
  * Out: R[B,M,9], t[B,M,3] (unit) of the pose with the most correspondences in front of both cameras,
  * mask[B,M,N] (nullable) = those correspondences, ngood[B,M]; with R_gt[B,9], t_gt[B,3] also
- * err[B,M,2] = (rotation, translation) angular error in degrees.  Arithmetic in double.            */
+ * err[B,M,2] = (rotation, translation) angular error in degrees.  counts[B,M,4] is caller-provided scratch
+ * (left holding the votes of the four candidate poses).  Arithmetic in double.                      */
 int drb_recover_pose(const float* E, const float* matches, const int32_t* npts, const float* R_gt,
-                     const float* t_gt, int B, int M, int N, float dist, float* R, float* t, uint8_t* mask,
-                     int32_t* ngood, float* err, void* stream);
+                     const float* t_gt, int B, int M, int N, float dist, int32_t* counts, float* R, float* t,
+                     uint8_t* mask, int32_t* ngood, float* err, void* stream);
 /* One term of PoseLoss.forward_average per (pair, model) (loss.py:57-63 with its default svd=False): Horn's
  * closed-form decomposition (cv_utils.py:118-165), the same cheirality vote, err[B,M,2] in degrees and
  * (nullable) grad[B,M,9] = d((err_R + err_t)/2)/dE -- what autograd returns through the reference's chain,
  * including its constant [b]x (cv_utils.py:146-150).  Non-finite derivatives (arccos at +-1) are zeroed. */
 int drb_pose_loss(const float* E, const float* matches, const int32_t* npts, const float* R_gt,
-                  const float* t_gt, int B, int M, int N, float dist, float* err, float* grad, void* stream);
+                  const float* t_gt, int B, int M, int N, float dist, int32_t* counts, float* err, float* grad,
+                  void* stream);
 
 #ifdef __cplusplus
 }
