@@ -7,15 +7,32 @@ import ctypes
 
 import torch
 
+import threading
+
 from . import _lib
-from ._lib import check
 
 E5_SLOTS = 10
 F7_SLOTS = 3
 
+# Every tensor whose address goes into a launch is kept alive until that launch has been enqueued: a converted
+# copy made inline (`_p(_f32(x))`) would otherwise be freed as soon as its pointer is taken, and the caching
+# allocator could hand the same block to the NEXT inline copy of the same call.  After the launch the stream
+# orders any reuse behind the kernel, so `check` drops the references.
+_ARGS = threading.local()
+
+
+def check(status: int, what: str):
+    getattr(_ARGS, "alive", []).clear()
+    _lib.check(status, what)
+
 
 def _p(t):
-    return None if t is None else ctypes.c_void_p(t.data_ptr())
+    if t is None:
+        return None
+    if not hasattr(_ARGS, "alive"):
+        _ARGS.alive = []
+    _ARGS.alive.append(t)
+    return ctypes.c_void_p(t.data_ptr())
 
 
 def _stream():
