@@ -286,26 +286,96 @@ sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
 
 // ---------------------------------------------------------------------------------------------
 // Training forward, in-kernel noise, tau = 1: indices + log-sum-exp + selected keys, with the race
-// formulation for the ranking (rank by log2(u) * exp(-(l - lmax))) and
+// formulation for the ranking (rank by t = log2(u) * exp(-(l - lmax)), largest wins) and
 //   sum_n exp(l_n + g_n) = exp(lmax) * sum_n w_n / e_n,   w = exp(l - lmax),  e = -ln u,
 // for the normaliser: one log2 and one reciprocal per element instead of two logs, an IEEE add and
 // an online softmax.  Draws the SAME noise as sample_kernel (same Philox counters, same clamp), so
 // the backward (which regenerates it) and the exact kernel agree with it to rounding.
-constexpr int kTrainMaxN = 6016;   // two float tables of N entries in static shared memory (< 48 KB)
+//
+// Top-s without a running top-s: P(t_n > x) = 1 - 2^(x w_n) ~ -x w_n ln 2, so the number of elements above
+// x0 = -2s / (W ln 2), W = sum_n w_n, is Poisson with mean ~2s.  The sweep only APPENDS those few to a
+// per-hypothesis list in shared memory; the s largest of the list are ranked after the sweep.  Fewer than s
+// (or more than the list holds) sends the hypothesis through a second, unfiltered sweep with the warp-shared
+// running top-s (a few percent of the hypotheses for reference-like weights; every one in the worst case).
+// N is swept in chunks of kTrainChunk correspondences whose tables live in shared memory, so any N runs here.
+constexpr int kTrainChunk = 5376;  // two float tables per chunk + the candidate lists stay under 48 KB
+constexpr int kTrainCand = 64;
+
+template <int S, bool FILTER>
+__device__ __forceinline__ void train_sweep(const float* __restrict__ wtab, const float* __restrict__ winv, int base,
+                                            int len_pad, uint32_t k, uint32_t b, uint32_t c3, uint32_t k0, uint32_t k1,
+                                            float x0, float* cand_v, int* cand_i, int* cand_n, float& zacc, float& top_v,
+                                            int& top_i, float& thr, int lane) {
+    const unsigned FULL = 0xffffffffu;
+    for (int n0 = lane * 4; n0 < len_pad; n0 += 128) {
+        const Philox4 r = philox4x32_10((uint32_t)((base + n0) >> 2), k, b, c3, k0, k1);
+        const float4 wi = *reinterpret_cast<const float4*>(winv + n0);
+        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+        const float wiv[4] = {wi.x, wi.y, wi.z, wi.w};
+        float t[4];
+        if (FILTER) {
+            const float4 ww = *reinterpret_cast<const float4*>(wtab + n0);
+            const float wwv[4] = {ww.x, ww.y, ww.z, ww.w};
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) {
+                const float lg = fminf(lg2_approx(uniform_from_bits(rr[i])), -1.4426950408889634e-10f);
+                t[i] = lg * wiv[i];
+                zacc = fmaf(wwv[i], rcp_fast(lg), zacc);  // sum of w / log2(u)  (negative)
+            }
+            const float m4 = fmaxf(fmaxf(t[0], t[1]), fmaxf(t[2], t[3]));
+            if (m4 > x0) {
+                DRB_UNROLL
+                for (int i = 0; i < 4; ++i)
+                    if (t[i] > x0) {
+                        const int pos = atomicAdd(cand_n, 1);
+                        if (pos < kTrainCand) {
+                            cand_v[pos] = t[i];
+                            cand_i[pos] = base + n0 + i;
+                        }
+                    }
+            }
+        } else {
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i)
+                t[i] = fminf(lg2_approx(uniform_from_bits(rr[i])), -1.4426950408889634e-10f) * wiv[i];
+            float bv = t[0];
+            int bi = 0;
+            DRB_UNROLL
+            for (int i = 1; i < 4; ++i)
+                if (t[i] > bv) { bv = t[i]; bi = i; }
+            merge_candidates<S>(bv, base + n0 + bi, top_v, top_i, thr, lane);
+            float second = -INFINITY;
+            DRB_UNROLL
+            for (int i = 0; i < 4; ++i) second = (i == bi) ? second : fmaxf(second, t[i]);
+            if (__any_sync(FULL, second > thr)) {
+                DRB_UNROLL
+                for (int i = 0; i < 4; ++i)
+                    merge_candidates<S>((i == bi) ? -INFINITY : t[i], base + n0 + i, top_v, top_i, thr, lane);
+            }
+        }
+    }
+}
 
 template <int S>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
                     int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out) {
-    __shared__ __align__(16) float wtab[kTrainMaxN];     // exp(l - lmax)
-    __shared__ __align__(16) float winv[kTrainMaxN];     // exp(lmax - l)
+    __shared__ __align__(16) float wtab[kTrainChunk];     // exp(l - lmax)
+    __shared__ __align__(16) float winv[kTrainChunk];     // exp(lmax - l)
     __shared__ float red[kSamplerWarps];
+    __shared__ float cand_v[kSamplerWarps][kTrainCand];
+    __shared__ int cand_i[kSamplerWarps][kTrainCand];
+    __shared__ int cand_n[kSamplerWarps];
+    __shared__ int win_i[kSamplerWarps][8];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
     const int k = blockIdx.x * kSamplerWarps + warp;
+    const bool live = k < K;
     const float* logits_b = logits + (size_t)b * N;
-    const int n_pad = ((N + 127) / 128) * 128;
+    const int n_chunks = (N + kTrainChunk - 1) / kTrainChunk;
+
+    // lmax and W = sum exp(l - lmax) over the pair
     float mx = -INFINITY;
     for (int n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, __ldg(logits_b + n));
     DRB_UNROLL
@@ -315,44 +385,87 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
     mx = red[0];
     DRB_UNROLL
     for (int w = 1; w < kSamplerWarps; ++w) mx = fmaxf(mx, red[w]);
-    for (int n = threadIdx.x; n < n_pad; n += blockDim.x) {
-        const float d = n < N ? __ldg(logits_b + n) - mx : -INFINITY;
-        wtab[n] = __expf(d);                 // 0 for the padding
-        winv[n] = __expf(-d);                // +inf for the padding: log2(u) * inf = -inf never ranks
+    __syncthreads();
+    float wsum = 0.f;
+    auto build = [&](int c, bool accumulate) {
+        const int base = c * kTrainChunk;
+        const int len = min(kTrainChunk, N - base);
+        const int len_pad = ((len + 127) / 128) * 128;
+        for (int n = threadIdx.x; n < len_pad; n += blockDim.x) {
+            const float d = n < len ? __ldg(logits_b + base + n) - mx : -INFINITY;
+            const float w = __expf(d);
+            wtab[n] = w;                         // 0 for the padding
+            winv[n] = __expf(-d);                // +inf for the padding: log2(u) * inf = -inf never ranks
+            if (accumulate) wsum += w;
+        }
+    };
+    build(0, true);
+    for (int n = kTrainChunk + threadIdx.x; n < N; n += blockDim.x) wsum += __expf(__ldg(logits_b + n) - mx);
+    DRB_UNROLL
+    for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(FULL, wsum, o);
+    if (lane == 0) {
+        red[warp] = wsum;
+        cand_n[warp] = 0;
     }
     __syncthreads();
-    if (k >= K) return;
+    wsum = red[0];
+    DRB_UNROLL
+    for (int w = 1; w < kSamplerWarps; ++w) wsum += red[w];
+    const float x0 = -(2.f * S) / (0.6931471805599453f * wsum);
+
     const long long row = (long long)b * K + k;
+    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
     float top_v = -INFINITY, thr = -INFINITY, zacc = 0.f;
     int top_i = -1;
-    const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
-    for (int n0 = lane * 4; n0 < n_pad; n0 += 128) {
-        const Philox4 r = philox4x32_10((uint32_t)(n0 >> 2), (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
-        const float4 wi = *reinterpret_cast<const float4*>(winv + n0);
-        const float4 ww = *reinterpret_cast<const float4*>(wtab + n0);
-        const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-        const float wiv[4] = {wi.x, wi.y, wi.z, wi.w}, wwv[4] = {ww.x, ww.y, ww.z, ww.w};
-        float t[4];
-        DRB_UNROLL
-        for (int i = 0; i < 4; ++i) {
-            const float lg = fminf(lg2_approx(uniform_from_bits(rr[i])), -1.4426950408889634e-10f);
-            t[i] = lg * wiv[i];
-            zacc = fmaf(wwv[i], rcp_fast(lg), zacc);       // sum of w / log2(u)  (negative)
+    // sweep 1: filtered, all chunks
+    for (int c = 0; c < n_chunks; ++c) {
+        if (c > 0) {
+            __syncthreads();
+            build(c, false);
+            __syncthreads();
         }
-        float bv = t[0];
-        int bi = 0;
-        DRB_UNROLL
-        for (int i = 1; i < 4; ++i)
-            if (t[i] > bv) { bv = t[i]; bi = i; }
-        merge_candidates<S>(bv, n0 + bi, top_v, top_i, thr, lane);
-        float second = -INFINITY;
-        DRB_UNROLL
-        for (int i = 0; i < 4; ++i) second = (i == bi) ? second : fmaxf(second, t[i]);
-        if (__any_sync(FULL, second > thr)) {
-            DRB_UNROLL
-            for (int i = 0; i < 4; ++i) merge_candidates<S>((i == bi) ? -INFINITY : t[i], n0 + i, top_v, top_i, thr, lane);
+        const int len = min(kTrainChunk, N - c * kTrainChunk);
+        if (live)
+            train_sweep<S, true>(wtab, winv, c * kTrainChunk, ((len + 127) / 128) * 128, (uint32_t)k, (uint32_t)b,
+                                 (uint32_t)offset, k0, k1, x0, cand_v[warp], cand_i[warp], &cand_n[warp], zacc, top_v,
+                                 top_i, thr, lane);
+    }
+    __syncwarp();
+    const int nc = live ? cand_n[warp] : S;
+    const bool redo = live && (nc < S || nc > kTrainCand);
+    if (live && !redo) {
+        // rank the listed candidates (value descending, index ascending on ties); lane holds entries lane, lane+32
+        const float v0 = lane < nc ? cand_v[warp][lane] : -INFINITY, v1 = lane + 32 < nc ? cand_v[warp][lane + 32] : -INFINITY;
+        const int i0 = lane < nc ? cand_i[warp][lane] : 0x7fffffff, i1 = lane + 32 < nc ? cand_i[warp][lane + 32] : 0x7fffffff;
+        int r0 = 0, r1 = 0;
+        for (int j = 0; j < nc; ++j) {
+            const float vj = cand_v[warp][j];
+            const int ij = cand_i[warp][j];
+            r0 += (vj > v0 || (vj == v0 && ij < i0)) ? 1 : 0;
+            r1 += (vj > v1 || (vj == v1 && ij < i1)) ? 1 : 0;
+        }
+        if (lane < nc && r0 < S) win_i[warp][r0] = i0;
+        if (lane + 32 < nc && r1 < S) win_i[warp][r1] = i1;
+        __syncwarp();
+        if (lane < S) top_i = win_i[warp][lane];
+    }
+    // sweep 2 (rare): the hypotheses whose list came out short or overflowed, unfiltered
+    if (__syncthreads_or(redo ? 1 : 0)) {
+        for (int c = 0; c < n_chunks; ++c) {
+            if (n_chunks > 1) {
+                __syncthreads();
+                build(c, false);
+                __syncthreads();
+            }
+            const int len = min(kTrainChunk, N - c * kTrainChunk);
+            float zdummy = 0.f;
+            if (redo)
+                train_sweep<S, false>(wtab, winv, c * kTrainChunk, ((len + 127) / 128) * 128, (uint32_t)k, (uint32_t)b,
+                                      (uint32_t)offset, k0, k1, x0, nullptr, nullptr, nullptr, zdummy, top_v, top_i, thr,
+                                      lane);
         }
     }
+    if (!live) return;
     DRB_UNROLL
     for (int o = 16; o > 0; o >>= 1) zacc += __shfl_xor_sync(FULL, zacc, o);
     // Z = sum w / e = -(1 / ln 2) * zacc ;  lse = lmax + ln Z
@@ -555,7 +668,7 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     const long long rows = (long long)B * K;
     const unsigned grid = (unsigned)((rows + kSamplerWarps - 1) / kSamplerWarps);
     const dim3 block(kSamplerWarps * 32);
-    if (!noise && lse && sel_key && !noise_out && tau == 1.0f && N <= kTrainMaxN && B <= 65535) {
+    if (!noise && lse && sel_key && !noise_out && tau == 1.0f && B <= 65535) {
         // training forward with in-kernel noise at tau = 1
         const dim3 tgrid((K + kSamplerWarps - 1) / kSamplerWarps, B);
 #define DRB_LAUNCH_TRAIN(S_)                                                                                 \

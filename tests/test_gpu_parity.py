@@ -75,9 +75,17 @@ def test_sampler_philox_replay_and_statistics(drb):
 def test_sampler_race_equals_exact(drb):
     """Test mode uses the exponential-race fast path (one SFU op per element); it must pick the same
     points as the exact key = (logit + G) / tau path that the oracle replays, on the same Philox stream."""
-    for s, N, K, regime in ((5, 2000, 1000, "L0"), (8, 2000, 512, "L1"), (3, 4100, 64, "L1"), (7, 333, 100, "L0")):
+    # the last three rows: N beyond one shared-memory chunk of the training kernel (tables swept in pieces), and
+    # peaked weights, where its candidate pre-filter comes up short and the unfiltered second sweep takes over
+    for s, N, K, regime in ((5, 2000, 1000, "L0"), (8, 2000, 512, "L1"), (3, 4100, 64, "L1"), (7, 333, 100, "L0"),
+                            (3, 12000, 64, "L1"), (5, 50000, 24, "L0"), (8, 2000, 256, "peaked")):
         B = 4
-        logits = drb.synth.logits_regime(B, N, regime, seed=s).to(DEV)
+        if regime == "peaked":
+            logits = drb.synth.logits_regime(B, N, "L1", seed=s)
+            logits[:, ::400] += 9.0
+            logits = logits.to(DEV)
+        else:
+            logits = drb.synth.logits_regime(B, N, regime, seed=s).to(DEV)
         fast, _, _, _ = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3)
         # want_noise forces the exact-key kernel (the one the oracle replays)
         exact, lse_x, key_x, noise = drb.ops.sample(logits, K, s, 1.0, seed=11, offset=3, want_lse=True,
