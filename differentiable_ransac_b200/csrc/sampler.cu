@@ -298,7 +298,8 @@ sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
 // (or more than the list holds) sends the hypothesis through a second, unfiltered sweep with the warp-shared
 // running top-s (a few percent of the hypotheses for reference-like weights; every one in the worst case).
 // N is swept in chunks of kTrainChunk correspondences whose tables live in shared memory, so any N runs here.
-constexpr int kTrainChunk = 5376;  // two float tables per chunk + the candidate lists stay under 48 KB
+constexpr int kTrainWarps = 16;    // hypotheses per CTA: the tables are built once for all of them
+constexpr int kTrainChunk = 4992;  // two float tables per chunk + the candidate lists stay under 48 KB
 constexpr int kTrainCand = 64;
 
 template <int S, bool FILTER>
@@ -357,20 +358,20 @@ __device__ __forceinline__ void train_sweep(const float* __restrict__ wtab, cons
 }
 
 template <int S>
-__global__ void __launch_bounds__(kSamplerWarps * 32)
+__global__ void __launch_bounds__(kTrainWarps * 32)
 sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
                     int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out) {
     __shared__ __align__(16) float wtab[kTrainChunk];     // exp(l - lmax)
     __shared__ __align__(16) float winv[kTrainChunk];     // exp(lmax - l)
-    __shared__ float red[kSamplerWarps];
-    __shared__ float cand_v[kSamplerWarps][kTrainCand];
-    __shared__ int cand_i[kSamplerWarps][kTrainCand];
-    __shared__ int cand_n[kSamplerWarps];
-    __shared__ int win_i[kSamplerWarps][8];
+    __shared__ float red[kTrainWarps];
+    __shared__ float cand_v[kTrainWarps][kTrainCand];
+    __shared__ int cand_i[kTrainWarps][kTrainCand];
+    __shared__ int cand_n[kTrainWarps];
+    __shared__ int win_i[kTrainWarps][8];
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const int k = blockIdx.x * kSamplerWarps + warp;
+    const int k = blockIdx.x * kTrainWarps + warp;
     const bool live = k < K;
     const float* logits_b = logits + (size_t)b * N;
     const int n_chunks = (N + kTrainChunk - 1) / kTrainChunk;
@@ -384,7 +385,7 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
     __syncthreads();
     mx = red[0];
     DRB_UNROLL
-    for (int w = 1; w < kSamplerWarps; ++w) mx = fmaxf(mx, red[w]);
+    for (int w = 1; w < kTrainWarps; ++w) mx = fmaxf(mx, red[w]);
     __syncthreads();
     float wsum = 0.f;
     auto build = [&](int c, bool accumulate) {
@@ -410,7 +411,7 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
     __syncthreads();
     wsum = red[0];
     DRB_UNROLL
-    for (int w = 1; w < kSamplerWarps; ++w) wsum += red[w];
+    for (int w = 1; w < kTrainWarps; ++w) wsum += red[w];
     const float x0 = -(2.f * S) / (0.6931471805599453f * wsum);
 
     const long long row = (long long)b * K + k;
@@ -670,10 +671,10 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     const dim3 block(kSamplerWarps * 32);
     if (!noise && lse && sel_key && !noise_out && tau == 1.0f && B <= 65535) {
         // training forward with in-kernel noise at tau = 1
-        const dim3 tgrid((K + kSamplerWarps - 1) / kSamplerWarps, B);
-#define DRB_LAUNCH_TRAIN(S_)                                                                                 \
-    case S_:                                                                                                 \
-        sample_train_kernel<S_><<<tgrid, block, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key);      \
+        const dim3 tgrid((K + kTrainWarps - 1) / kTrainWarps, B);
+#define DRB_LAUNCH_TRAIN(S_)                                                                                       \
+    case S_:                                                                                                       \
+        sample_train_kernel<S_><<<tgrid, kTrainWarps * 32, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key); \
         break;
         switch (s) {
             DRB_LAUNCH_TRAIN(3)
