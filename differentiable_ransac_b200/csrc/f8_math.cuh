@@ -114,11 +114,58 @@ DRB_HD bool gauss_solve(AT* J, AT* b) {
     return true;
 }
 
+// Solve the symmetric positive definite 8 x 8 system M u = b in place (Cholesky, no pivoting; every loop has
+// constant bounds so the whole factorisation stays in registers).  Returns false on a non-positive pivot.
+template <class AT>
+DRB_HD bool chol_solve8(AT (*M)[8], AT* b) {
+    DRB_UNROLL
+    for (int j = 0; j < 8; ++j) {
+        AT d = M[j][j];
+        DRB_UNROLL
+        for (int k = 0; k < 8; ++k)
+            if (k < j) d -= M[j][k] * M[j][k];
+        if (!(d > AT(0))) return false;
+        const AT inv = AT(1) / t_sqrt(d);
+        M[j][j] = d * inv;  // = sqrt(d)
+        DRB_UNROLL
+        for (int i = 0; i < 8; ++i)
+            if (i > j) {
+                AT s = M[i][j];
+                DRB_UNROLL
+                for (int k = 0; k < 8; ++k)
+                    if (k < j) s -= M[i][k] * M[j][k];
+                M[i][j] = s * inv;
+            }
+    }
+    DRB_UNROLL
+    for (int i = 0; i < 8; ++i) {  // L y = b
+        AT s = b[i];
+        DRB_UNROLL
+        for (int k = 0; k < 8; ++k)
+            if (k < i) s -= M[i][k] * b[k];
+        b[i] = s / M[i][i];
+    }
+    DRB_UNROLL
+    for (int ii = 0; ii < 8; ++ii) {  // L^T u = y
+        const int i = 7 - ii;
+        AT s = b[i];
+        DRB_UNROLL
+        for (int k = 0; k < 8; ++k)
+            if (k > i) s -= M[k][i] * b[k];
+        b[i] = s / M[i][i];
+    }
+    return true;
+}
+
 // Backward of f8_solve: g = dL/dF -> gp[8][4] = dL/dpts.
 // Fn = unit null vector of A(n):  [A; f^T] df = [-dA f; 0]  =>  dL/dA = -u f^T with
-// [A; f^T]^T [u; lambda] = dL/dFn; then the chain through the Hartley normalisation.
+// [A; f^T]^T [u; lambda] = dL/dFn.  Because A f = 0 the bordered system splits: lambda = f . dL/dFn and
+// A^T u = dL/dFn - lambda f, solved through the 8 x 8 normal equations (A A^T) u = A (dL/dFn - lambda f) in AT
+// (double: cond(A)^2 ~ 1e8 leaves eight digits).  Then the chain through the Hartley normalisation.
+// `F_fwd` (nullable) is the forward's output: it fixes the sign of the recomputed null vector; without it the
+// forward is re-run in T for that purpose.
 template <class T, class AT = double>
-DRB_HD bool f8_backward(const T (*pts)[4], const T* g, T (*gp)[4]) {
+DRB_HD bool f8_backward(const T (*pts)[4], const T* g, T (*gp)[4], const T* F_fwd = nullptr) {
     AT p[8][4], n[8][4];
     for (int j = 0; j < 8; ++j)
         for (int c = 0; c < 4; ++c) p[j][c] = AT(pts[j][c]);
@@ -128,8 +175,14 @@ DRB_HD bool f8_backward(const T (*pts)[4], const T* g, T (*gp)[4]) {
     AT fv[1][9];
     null_space_rows<AT, 8>(rows, fv);
     const AT* f = fv[0];
-    // the forward ran in T: align the sign of the recomputed null vector with it
-    {
+    if (F_fwd != nullptr) {
+        AT Fd[9], dot = AT(0);
+        denormalize_f(f, h, Fd);
+        for (int i = 0; i < 9; ++i) dot += AT(F_fwd[i]) * Fd[i];
+        if (dot < AT(0))
+            for (int i = 0; i < 9; ++i) fv[0][i] = -fv[0][i];
+    } else {
+        // the forward ran in T: align the sign of the recomputed null vector with it
         T nf[8][4];
         const HartleyNorm<T> hf = hartley_normalize<T, 8>(pts, nf);
         (void)hf;
@@ -158,11 +211,30 @@ DRB_HD bool f8_backward(const T (*pts)[4], const T* g, T (*gp)[4]) {
     AT g_r2 = gT2[0] + gT2[4] - h.m[2] * gT2[2] - h.m[3] * gT2[5];
     AT g_m[4] = {-h.r1 * gT1[2], -h.r1 * gT1[5], -h.r2 * gT2[2], -h.r2 * gT2[5]};
     // adjoint of the null vector
-    AT J[81], v[9];
-    for (int r = 0; r < 9; ++r)
-        for (int c = 0; c < 9; ++c) J[r * 9 + c] = (c < 8) ? rows[c][r] : f[r];  // [A; f^T]^T
-    for (int i = 0; i < 9; ++i) v[i] = gFn[i];
-    if (!gauss_solve<AT, 9>(J, v)) return false;
+    AT v[8];
+    {
+        AT lam = AT(0), rhs[9], MM[8][8];
+        DRB_UNROLL
+        for (int i = 0; i < 9; ++i) lam += f[i] * gFn[i];
+        DRB_UNROLL
+        for (int i = 0; i < 9; ++i) rhs[i] = gFn[i] - lam * f[i];
+        DRB_UNROLL
+        for (int r = 0; r < 8; ++r) {
+            AT s = AT(0);
+            DRB_UNROLL
+            for (int i = 0; i < 9; ++i) s += rows[r][i] * rhs[i];
+            v[r] = s;
+            DRB_UNROLL
+            for (int c = 0; c < 8; ++c)
+                if (c <= r) {
+                    AT m = AT(0);
+                    DRB_UNROLL
+                    for (int i = 0; i < 9; ++i) m += rows[r][i] * rows[c][i];
+                    MM[r][c] = m;
+                }
+        }
+        if (!chol_solve8<AT>(MM, v)) return false;
+    }
     AT gn[8][4];
     for (int j = 0; j < 8; ++j) {
         AT ga[9];

@@ -298,9 +298,11 @@ sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
 // (or more than the list holds) sends the hypothesis through a second, unfiltered sweep with the warp-shared
 // running top-s (a few percent of the hypotheses for reference-like weights; every one in the worst case).
 // N is swept in chunks of kTrainChunk correspondences whose tables live in shared memory, so any N runs here.
-constexpr int kTrainWarps = 16;    // hypotheses per CTA: the tables are built once for all of them
-constexpr int kTrainChunk = 4992;  // two float tables per chunk + the candidate lists stay under 48 KB
+// Hypotheses (warps) per CTA share one pair of tables.  8 when N fits one chunk (more, smaller CTAs; measured
+// faster at N = 2000), 16 when the tables are rebuilt chunk after chunk (halves the rebuilding per hypothesis).
+// Chunk = what keeps two float tables + the candidate lists under 48 KB of static shared memory.
 constexpr int kTrainCand = 64;
+constexpr int train_chunk(int warps) { return warps == 8 ? 5376 : 4992; }
 
 template <int S, bool FILTER>
 __device__ __forceinline__ void train_sweep(const float* __restrict__ wtab, const float* __restrict__ winv, int base,
@@ -357,10 +359,11 @@ __device__ __forceinline__ void train_sweep(const float* __restrict__ wtab, cons
     }
 }
 
-template <int S>
+template <int S, int kTrainWarps>
 __global__ void __launch_bounds__(kTrainWarps * 32)
 sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
                     int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out) {
+    constexpr int kTrainChunk = train_chunk(kTrainWarps);
     __shared__ __align__(16) float wtab[kTrainChunk];     // exp(l - lmax)
     __shared__ __align__(16) float winv[kTrainChunk];     // exp(lmax - l)
     __shared__ float red[kTrainWarps];
@@ -671,10 +674,15 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     const dim3 block(kSamplerWarps * 32);
     if (!noise && lse && sel_key && !noise_out && tau == 1.0f && B <= 65535) {
         // training forward with in-kernel noise at tau = 1
-        const dim3 tgrid((K + kTrainWarps - 1) / kTrainWarps, B);
-#define DRB_LAUNCH_TRAIN(S_)                                                                                       \
-    case S_:                                                                                                       \
-        sample_train_kernel<S_><<<tgrid, kTrainWarps * 32, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key); \
+        const bool one_chunk = N <= train_chunk(8);
+        const int tw = one_chunk ? 8 : 16;
+        const dim3 tgrid((K + tw - 1) / tw, B);
+#define DRB_LAUNCH_TRAIN(S_)                                                                                      \
+    case S_:                                                                                                      \
+        if (one_chunk)                                                                                            \
+            sample_train_kernel<S_, 8><<<tgrid, 256, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key);     \
+        else                                                                                                      \
+            sample_train_kernel<S_, 16><<<tgrid, 512, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key);    \
         break;
         switch (s) {
             DRB_LAUNCH_TRAIN(3)

@@ -47,14 +47,20 @@ solve_f8_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
 
 __global__ void __launch_bounds__(128)
 solve_f8_backward_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
-                         const float* __restrict__ g_model, float* __restrict__ g_pts) {
+                         const float* __restrict__ models, const float* __restrict__ g_model,
+                         float* __restrict__ g_pts) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)B * K) return;
     float p[8][4], g[9], gp[8][4];
     load_minimal2d<8>(matches, idx, row, (int)(row / K), N, p);
     DRB_UNROLL
     for (int i = 0; i < 9; ++i) g[i] = g_model[row * 9 + i];
-    const bool ok = f8_backward<float, double>(p, g, gp);
+    float Ff[9];
+    if (models != nullptr) {
+        DRB_UNROLL
+        for (int i = 0; i < 9; ++i) Ff[i] = models[row * 9 + i];
+    }
+    const bool ok = f8_backward<float, double>(p, g, gp, models != nullptr ? Ff : nullptr);
     DRB_UNROLL
     for (int j = 0; j < 8; ++j)
         reinterpret_cast<float4*>(g_pts)[row * 8 + j] =
@@ -128,10 +134,10 @@ extern "C" int drb_solve_f8(const float* matches, const int32_t* idx, int B, int
 
 extern "C" int drb_solve_f8_backward(const float* matches, const int32_t* idx, int B, int K, int N,
                                      const float* models, const float* g_model, float* g_pts, void* stream) {
-    (void)models;  // the backward re-derives the null vector from the sample itself
+    // `models` (nullable): the forward's output, used only to fix the sign of the recomputed null vector
     if (!matches || !g_model || !g_pts) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
-    DRB_ROWS_LAUNCH(solve_f8_backward_kernel, matches, idx, B, K, N, g_model, g_pts);
+    DRB_ROWS_LAUNCH(solve_f8_backward_kernel, matches, idx, B, K, N, models, g_model, g_pts);
 }
 
 extern "C" int drb_solve_f7(const float* matches, const int32_t* idx, int B, int K, int N, float* models,

@@ -245,7 +245,7 @@ class HypothesizeF8(_HypothesizeBase):
     def forward(ctx, matches, logits, K, tau=1.0, noise=None, seed=0, offset=0):
         idx, lse, sel_key, _ = ops.sample(logits, K, 8, tau, noise, seed, offset, want_lse=True)
         models, valid = ops.solve_f8(matches, idx)
-        ctx.save_for_backward(ops._f32(matches), ops._f32(logits), idx, lse, sel_key)
+        ctx.save_for_backward(ops._f32(matches), ops._f32(logits), idx, lse, sel_key, models)
         ctx.tau, ctx.noise, ctx.seed, ctx.offset = float(tau), noise, int(seed), int(offset)
         valid = valid.bool()
         ctx.mark_non_differentiable(valid)
@@ -253,8 +253,8 @@ class HypothesizeF8(_HypothesizeBase):
 
     @staticmethod
     def backward(ctx, g_models, _g_valid):
-        matches, logits, idx, lse, sel_key = ctx.saved_tensors
-        g_pts = ops.solve_f8_backward(matches, idx, g_models.reshape(*idx.shape[:2], 9))
+        matches, logits, idx, lse, sel_key, models = ctx.saved_tensors
+        g_pts = ops.solve_f8_backward(matches, idx, g_models.reshape(*idx.shape[:2], 9), models)
         gm, gl = _HypothesizeBase._backward_common(ctx, g_pts)
         return gm, gl, None, None, None, None, None
 

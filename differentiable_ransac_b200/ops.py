@@ -191,12 +191,14 @@ def solve_f8(matches, idx=None):
     return models, valid
 
 
-def solve_f8_backward(matches, idx, g_model):
+def solve_f8_backward(matches, idx, g_model, models=None):
+    """`models` (the forward's output, optional) fixes the sign of the null vector the backward recomputes;
+    without it the kernel re-runs the forward for that."""
     matches, idx, B, K, N = _rows(matches, idx, 8, 4)
     g_pts = torch.empty(B, K, 8, 4, dtype=torch.float32, device=matches.device)
     lib = _lib.load()
-    check(lib.drb_solve_f8_backward(_p(matches), _p(idx), B, K, N, None, _p(_f32(g_model)), _p(g_pts), _stream()),
-          "drb_solve_f8_backward")
+    check(lib.drb_solve_f8_backward(_p(matches), _p(idx), B, K, N, _p(None if models is None else _f32(models)),
+                                    _p(_f32(g_model)), _p(g_pts), _stream()), "drb_solve_f8_backward")
     return g_pts
 
 
