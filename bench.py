@@ -244,10 +244,16 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-slots", type=int, default=int(os.environ.get("DRB_E2E_SLOTS", "3")),
+                    help="batches in flight in the end-to-end service (engine.E5TestService)")
+    ap.add_argument("--e2e-graph", type=int, default=int(os.environ.get("DRB_E2E_GRAPH", "1")),
+                    help="1: each service slot replays one CUDA graph (copy-in, kernels, copy-out) per batch")
+    ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "2")),
+                    help="CUDA streams the K device-resident steps are issued over (1 = strictly serial)")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "1")),
                     help="sub-batches on separate CUDA streams (measured: 1 is fastest, profiles/r1_notes.md)")
     args = ap.parse_args()
@@ -274,10 +280,35 @@ def main():
     matches_h, logits_h, thr_h, E_gt = make_inputs(B, N, seed=1234 + 1000 * rank)   # pairs shard over ranks
     matches_h, logits_h, thr_h = matches_h.pin_memory(), logits_h.pin_memory(), thr_h.pin_memory()
     matches, logits, thr = matches_h.to(dev), logits_h.to(dev), thr_h.to(dev)
+    # L2 policy for `value`: the steps cycle through NB copies of the inputs at distinct addresses, 168 MB in
+    # all (> the 126 MB L2), so a step never finds its inputs cached by an earlier one; the roofline pass
+    # below (one kernel timed alone) flushes L2 with a 256 MB write instead.
+    NB = 128
+    matches_all = matches.unsqueeze(0).repeat(NB, 1, 1, 1)
+    logits_all = logits.unsqueeze(0).repeat(NB, 1, 1)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
+    S = max(1, args.value_streams)
+    main_stream = torch.cuda.current_stream()
+    side = [torch.cuda.Stream(device=dev) for _ in range(S)]
 
-    def step(i):
-        return engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=i, streams=args.streams)
+    def run_steps(n, first):
+        """n independent steps (fresh Philox offset each), issued round-robin over S streams: the latency-bound
+        5-point kernel of one step overlaps the FMA-bound scoring kernel of the previous one."""
+        fork = torch.cuda.Event()
+        fork.record(main_stream)
+        outs = []
+        for st in side:
+            st.wait_event(fork)
+        for i in range(n):
+            j = (first + i) % NB
+            with torch.cuda.stream(side[i % S]):
+                outs.append(engine.ransac_e5_test(matches_all[j], logits_all[j], K, thr, seed=42 + rank,
+                                                  offset=first + i, streams=args.streams))
+                if len(outs) > 2 * S:
+                    outs.pop(0)
+        for st in side:
+            main_stream.wait_stream(st)
+        return outs[-1]
 
     def barrier():
         torch.cuda.synchronize()
@@ -286,21 +317,18 @@ def main():
         torch.cuda.synchronize()
 
     # ---- device-resident throughput ("value") -------------------------------------------------------
-    for i in range(warmup):
-        out = step(i)
+    out = run_steps(warmup, 0)
     barrier()
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    for i in range(args.steps):
-        flush.fill_(float(i))                   # L2 flush between timed iterations (untimed)
-        ev[i][0].record()
-        out = step(warmup + i)
-        ev[i][1].record()
+    t_begin.record(main_stream)
+    out = run_steps(args.steps, warmup)
+    t_end.record(main_stream)
     barrier()
-    ms_local = sum(a.elapsed_time(b) for a, b in ev)
+    ms_local = t_begin.elapsed_time(t_end)
     clock_info = clocks.stop() if rank == 0 else None
     t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -309,48 +337,43 @@ def main():
     ms_per_step = ms_total / args.steps
     value = world * B * K * args.steps / (ms_total / 1e3)
 
+    # the same K steps strictly one after the other on one stream, L2 flushed before each (reported beside it)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for i in range(args.steps):
+        flush.fill_(float(i))
+        ev[i][0].record()
+        out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i, streams=args.streams)
+        ev[i][1].record()
+    barrier()
+    ms_serial = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
-    # Every step copies ITS inputs from pinned host memory (one packed buffer: matches | logits | thr) and
-    # reads ITS results back (one packed buffer: model | id | score | #inliers).  Two slots: the copy-in of
-    # step i+1 runs on a copy stream while step i computes -- steady-state service throughput.  Inputs come
-    # from the host every step, so no L2 flush is inserted here (and it could not be excluded from the
-    # timed region once copies and compute overlap).
-    n_in = B * N * 4 + B * N + B
-    host_in = torch.cat((matches_h.flatten(), logits_h.flatten(), thr_h.flatten())).pin_memory()
-    h2d = host_in.numel() * 4
-    n_out = B * 9 + 3 * B
-    host_out = [torch.empty(n_out, dtype=torch.float32).pin_memory() for _ in range(2)]
-    d2h = n_out * 4
-    dev_in = [torch.empty(n_in, dtype=torch.float32, device=dev) for _ in range(2)]
-    copy_stream = torch.cuda.Stream(device=dev)
-    copied = [torch.cuda.Event() for _ in range(2)]
-    consumed = [torch.cuda.Event() for _ in range(2)]
-    main_stream = torch.cuda.current_stream()
+    # engine.E5TestService: every step copies ITS inputs from pinned host memory (one packed buffer: matches |
+    # logits | thr) and reads ITS results back (one packed buffer: model | id | score | #inliers) before the
+    # slot is reused.  `--e2e-slots` batches are in flight at once, each on its own compute stream, copies on
+    # a copy stream: steady-state service throughput.  Inputs come from the host every step, so no L2 flush
+    # is inserted here (and it could not be excluded from the timed region once copies and compute overlap).
+    svc = engine.E5TestService(B, N, K, dev, slots=args.e2e_slots, seed=42 + rank, graph=bool(args.e2e_graph))
+    for s_ in range(svc.slots):
+        svc.stage(s_, matches_h, logits_h, thr_h)      # synthetic: the same pairs staged in every slot
+    h2d, d2h = svc.h2d_bytes, svc.d2h_bytes
 
-    def run_e2e(n_steps, first):
-        for s_ in range(2):
-            consumed[s_].record(main_stream)
-        for i in range(n_steps):
-            slot = i & 1
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[slot])
-                dev_in[slot].copy_(host_in, non_blocking=True)
-                copied[slot].record(copy_stream)
-            main_stream.wait_event(copied[slot])
-            buf = dev_in[slot]
-            m = buf[: B * N * 4].view(B, N, 4)
-            l = buf[B * N * 4: B * N * 5].view(B, N)
-            th = buf[B * N * 5:]
-            o = engine.ransac_e5_test(m, l, K, th, seed=42 + rank, offset=first + i, streams=args.streams)
-            consumed[slot].record(main_stream)
-            packed = torch.cat((o["best_model"].flatten(), o["best_id"].float(), o["best_score"], o["ninl"].float()))
-            host_out[slot].copy_(packed, non_blocking=True)
+    def run_e2e(n_steps):
+        pending = []
+        for _ in range(n_steps):
+            if len(pending) == svc.slots:
+                svc.result(pending.pop(0))              # the caller reads the oldest batch's results (host sync)
+            pending.append(svc.submit())
+        for s_ in pending:
+            svc.result(s_)
 
-    run_e2e(warmup, 1000)
+    run_e2e(warmup)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(main_stream)
-    run_e2e(args.steps, 2000)
+    svc.after(e0)
+    run_e2e(args.steps)
+    svc.join(main_stream)
     e1.record(main_stream)
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
@@ -408,10 +431,13 @@ def main():
                     pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N,
                     noise="in-kernel Philox4x32-10; sets drawn without replacement from softmax(logits) "
                           "(= Gumbel top-5 in law, drb_sample_sets)",
-                    l2="flushed between timed iterations (256 MB write) for `value`; e2e re-copies its inputs "
-                       "from the host every step instead",
-                    e2e_mode="two slots: the packed H2D of step i+1 overlaps the compute of step i; one packed "
-                             "D2H of (model, id, score, #inliers) per step",
+                    l2="`value`: steps cycle through 128 copies of the inputs at distinct addresses (168 MB > L2); "
+                       "serial_ms_per_step and the roofline pass: L2 flushed by a 256 MB write before each launch; "
+                       "e2e re-copies its inputs from the host every step",
+                    value_streams=S, serial_ms_per_step=ms_serial,
+                    e2e_mode=f"engine.E5TestService(graph={bool(args.e2e_graph)}), {args.e2e_slots} batches in flight "
+                             "(one stream each; a CUDA graph per slot when graph=True): packed H2D per step, one packed D2H of (model, id, score, #inliers) "
+                             "per step, results read on the host before a slot is reused",
                     streams=args.streams,
                     parallelism=f"pairs sharded over {world} GPU(s)"),
         clocks=clock_info,

@@ -190,9 +190,10 @@ constexpr int kSetThreads = 256;
 
 template <int S>
 __global__ void __launch_bounds__(kSetThreads)
-sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
-                   int32_t* __restrict__ idx_out) {
+sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset,
+                   const unsigned long long* __restrict__ offset_dev, int K, int N, int32_t* __restrict__ idx_out) {
     extern __shared__ float cdf[];  // N inclusive prefix sums of exp(logit - max)
+    if (offset_dev) offset += *offset_dev;  // stream position kept on the device: a captured graph replays with fresh draws
     __shared__ float red[kSetThreads / 32];
     __shared__ float warp_tot[kSetThreads / 32];
     const int b = blockIdx.y;
@@ -730,8 +731,8 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     return check_launch();
 }
 
-extern "C" int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offset, int B, int K, int N, int s,
-                               int32_t* idx, void* stream) {
+extern "C" int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int B,
+                               int K, int N, int s, int32_t* idx, void* stream) {
     if (!logits || !idx) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || N <= 0 || s <= 0 || s > N || B > 65535) return DRB_ERR_BAD_SHAPE;
     const size_t smem = (size_t)N * sizeof(float);
@@ -746,7 +747,8 @@ extern "C" int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offs
                 return DRB_ERR_CUDA;                                                                              \
             configured = true;                                                                                    \
         }                                                                                                         \
-        sample_sets_kernel<S_><<<grid, kSetThreads, smem, (cudaStream_t)stream>>>(logits, seed, offset, K, N, idx); \
+        sample_sets_kernel<S_><<<grid, kSetThreads, smem, (cudaStream_t)stream>>>(                                \
+            logits, seed, offset, reinterpret_cast<const unsigned long long*>(offset_dev), K, N, idx);            \
         break;                                                                                                    \
     }
     switch (s) {

@@ -21,11 +21,13 @@ def _noise_args(noise, seed, offset):
 
 
 # ---- test mode ---------------------------------------------------------------------------------
-def _draw(logits, K, s, tau, noise, seed, offset, sampler):
+def _draw(logits, K, s, tau, noise, seed, offset, sampler, offset_dev=None):
     """Test-mode sampling: injected noise -> exact Gumbel keys (bit-exact with the reference);
     otherwise the set sampler (same distribution, no K x N noise) unless `sampler="gumbel"`."""
     if noise is None and sampler == "sets":
-        return ops.sample_sets(logits, K, s, int(seed), int(offset))
+        return ops.sample_sets(logits, K, s, int(seed), int(offset), offset_dev)
+    if offset_dev is not None:
+        raise ops._lib.DrbError("a device-side stream offset needs the set sampler")
     return ops.sample(logits, K, s, tau, **_noise_args(noise, seed, offset))[0]
 
 
@@ -40,7 +42,7 @@ def _side_streams(device, n):
 
 
 def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False,
-                   sampler="sets", streams=1):
+                   sampler="sets", streams=1, offset_dev=None):
     """matches [B,N,4], logits [B,N], thr [B] (normalised threshold, ransac.py:49-53).
     Returns dict(best_model [B,3,3], best_hyp [B], best_slot [B], best_score [B], mask [B,N] bool,
     ninl [B], idx [B,K,5], models [B,K,10,3,3], nsol [B,K] (, scores [B,K*10] in compact order,
@@ -64,7 +66,7 @@ def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
                                             int(offset) + (c << 32), False, sampler, 1))
             main.wait_stream(st)
         return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
-    idx = _draw(logits, K, 5, tau, noise, seed, offset, sampler)
+    idx = _draw(logits, K, 5, tau, noise, seed, offset, sampler, offset_dev)
     best0, cc0 = ops.zeroed_counters(B, matches.device)
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True, ccount=cc0)
     scores, best = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=want_scores, best=best0)
@@ -321,3 +323,130 @@ def match_loss(models, valid, pts, npts=None):
     n = (npts if npts is not None else torch.full((B,), P, device=pts.device)).to(row.dtype)
     v = valid.to(row.dtype)
     return (row * v).sum(1) / (v.sum(1).clamp_min(1.0) * n.clamp_min(1.0))
+
+
+# ---- host-buffer service: test-mode batches from pinned host memory, pipelined over streams -----------
+class E5TestService:
+    """Steady-state test-mode service for batches that live in HOST memory (the reference's
+    `model_cl.py:488-510` loop receives its pairs from a DataLoader).  `submit()` enqueues, for one batch of
+    B pairs: one packed host->device copy (matches | logits | thr), `ransac_e5_test`, and one packed
+    device->host copy of (best model, best id, best score, #inliers); `result()` waits for that batch and
+    returns host tensors.  Nothing blocks in `submit()` unless every slot is in flight.
+
+    `slots` batches are in flight at once, each on its own compute stream, with the copies on a separate copy
+    stream.  Batches are independent, so the latency-bound 5-point kernel of batch i+1 fills the issue slots
+    the FMA-bound scoring kernel of batch i leaves idle (measured on B200, cfg2: 0.309 -> 0.256 ms per batch
+    with two slots, profiles/r1_notes.md)."""
+
+    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False):
+        self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
+        self.graph = bool(graph)
+        self.device = torch.device(device)
+        self.slots = int(slots)
+        self.n_in = B * N * 4 + B * N + B
+        self.n_out = B * 9 + 3 * B
+        self.host_in = [torch.empty(self.n_in, dtype=torch.float32).pin_memory() for _ in range(self.slots)]
+        self.host_out = [torch.empty(self.n_out, dtype=torch.float32).pin_memory() for _ in range(self.slots)]
+        self.dev_in = [torch.empty(self.n_in, dtype=torch.float32, device=self.device) for _ in range(self.slots)]
+        self.copy_stream = torch.cuda.Stream(device=self.device)
+        self.compute = [torch.cuda.Stream(device=self.device) for _ in range(self.slots)]
+        self.copied = [torch.cuda.Event() for _ in range(self.slots)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.slots)]
+        self.done = [torch.cuda.Event() for _ in range(self.slots)]
+        self.busy = [False] * self.slots
+        self.step = 0
+        self.h2d_bytes = self.n_in * 4
+        self.d2h_bytes = self.n_out * 4
+        # graph mode: one CUDA graph per slot (copy-in, four kernels, copy-out), replayed by submit(); the Philox
+        # stream position of the slot's next batch lives on the device and is advanced inside the graph, so
+        # batch i draws with offset i exactly as in eager mode when the slots are used round-robin
+        self.counters = [torch.full((1,), s, dtype=torch.int64, device=self.device) for s in range(self.slots)]
+        self.graphs = [None] * self.slots
+
+    def _body(self, slot, offset, offset_dev):
+        B, N = self.B, self.N
+        buf = self.dev_in[slot]
+        o = ransac_e5_test(buf[: B * N * 4].view(B, N, 4), buf[B * N * 4: B * N * 5].view(B, N), self.K,
+                           buf[B * N * 5:], seed=self.seed, offset=offset, offset_dev=offset_dev)
+        return o, torch.cat((o["best_model"].flatten(), o["best_id"].float(), o["best_score"], o["ninl"].float()))
+
+    def _capture(self, slot):
+        ks = self.compute[slot]
+        ks.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(ks):
+            self._body(slot, 0, self.counters[slot])     # eager warm-up: lazy kernel attributes, allocator pools
+        ks.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=ks):
+            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            _, packed = self._body(slot, 0, self.counters[slot])
+            self.counters[slot].add_(self.slots)
+            self.host_out[slot].copy_(packed, non_blocking=True)
+        self.graphs[slot] = g
+
+    def stage(self, slot, matches, logits, thr):
+        """Pack one batch of host tensors into the slot's pinned staging buffer (a host-side memcpy; callers
+        that produce their batches directly in `host_in[slot]` skip this)."""
+        B, N = self.B, self.N
+        buf = self.host_in[slot]
+        buf[: B * N * 4].copy_(matches.reshape(-1))
+        buf[B * N * 4: B * N * 5].copy_(logits.reshape(-1))
+        buf[B * N * 5:].copy_(thr.reshape(-1))
+
+    def submit(self, slot=None):
+        """Enqueue the batch staged in `host_in[slot]`; returns the slot."""
+        if slot is None:
+            slot = self.step % self.slots
+        if self.busy[slot]:
+            self.done[slot].synchronize()          # the slot's previous results must have been collected
+        B, N = self.B, self.N
+        cs, ks = self.copy_stream, self.compute[slot]
+        if self.graph:
+            if self.graphs[slot] is None:
+                self._capture(slot)
+            with torch.cuda.stream(ks):
+                self.graphs[slot].replay()
+                self.done[slot].record(ks)
+            self.busy[slot] = True
+            self.step += 1
+            return slot
+        cs.wait_event(self.consumed[slot])         # the previous batch of this slot has read its inputs
+        with torch.cuda.stream(cs):
+            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            self.copied[slot].record(cs)
+        ks.wait_event(self.copied[slot])
+        with torch.cuda.stream(ks):
+            _, packed = self._body(slot, self.step, None)
+            self.consumed[slot].record(ks)
+            self.host_out[slot].copy_(packed, non_blocking=True)
+            self.done[slot].record(ks)
+        self.busy[slot] = True
+        self.step += 1
+        return slot
+
+    def result(self, slot):
+        """Wait for the slot's batch; -> dict of host tensors (views of the slot's pinned output buffer)."""
+        self.done[slot].synchronize()
+        self.busy[slot] = False
+        B = self.B
+        out = self.host_out[slot]
+        return dict(best_model=out[: 9 * B].view(B, 3, 3), best_id=out[9 * B: 10 * B].to(torch.int32),
+                    best_score=out[10 * B: 11 * B], ninl=out[11 * B: 12 * B].to(torch.int32))
+
+    def drain(self):
+        for s in range(self.slots):
+            if self.busy[s]:
+                self.done[s].synchronize()
+                self.busy[s] = False
+
+    def after(self, event):
+        """Order every stream of the service behind `event` (for timing from another stream)."""
+        self.copy_stream.wait_event(event)
+        for ks in self.compute:
+            ks.wait_event(event)
+
+    def join(self, stream):
+        """Make `stream` wait for everything enqueued so far."""
+        stream.wait_stream(self.copy_stream)
+        for ks in self.compute:
+            stream.wait_stream(ks)

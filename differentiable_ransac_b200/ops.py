@@ -78,15 +78,18 @@ def sample(logits, K, s, tau=1.0, noise=None, seed=0, offset=0, want_lse=False, 
     return idx, lse, sel_key, noise_out
 
 
-def sample_sets(logits, K, s, seed=0, offset=0):
+def sample_sets(logits, K, s, seed=0, offset=0, offset_dev=None):
     """Test-mode set sampler (Plackett-Luce by inverse CDF, no Gumbel noise): logits [B,N] -> idx [B,K,s].
-    Falls back to the Gumbel-race kernel when one pair's prefix sums do not fit in shared memory."""
+    Falls back to the Gumbel-race kernel when one pair's prefix sums do not fit in shared memory.
+    offset_dev: optional int64 [1] CUDA tensor added to `offset` on the device (for CUDA-graph replay)."""
     logits = _f32(logits)
     B, N = logits.shape
     idx = torch.empty(B, K, s, dtype=torch.int32, device=logits.device)
     lib = _lib.load()
-    rc = lib.drb_sample_sets(_p(logits), seed, offset, B, K, N, s, _p(idx), _stream())
-    if rc == -3 and s in (3, 5, 7, 8):
+    if offset_dev is not None and (offset_dev.dtype != torch.int64 or offset_dev.device != logits.device):
+        raise _lib.DrbError("offset_dev must be an int64 tensor on the device of `logits`")
+    rc = lib.drb_sample_sets(_p(logits), seed, offset, _p(offset_dev), B, K, N, s, _p(idx), _stream())
+    if rc == -3 and s in (3, 5, 7, 8) and offset_dev is None:
         return sample(logits, K, s, 1.0, None, seed, offset)[0]
     check(rc, "drb_sample_sets")
     return idx

@@ -66,9 +66,11 @@ int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t 
  * s items WITHOUT replacement from softmax(logits) (Plackett-Luce), drawn here directly by inverse
  * CDF on a per-pair prefix sum: one thread per hypothesis, O(s log N) instead of O(N).  Same
  * distribution as drb_sample, different realisation.  idx[B,K,s] ascending.  Requires N*4 bytes of
- * shared memory (N <= 51200), else DRB_ERR_UNSUPPORTED (use drb_sample).                         */
-int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offset, int B, int K, int N, int s,
-                    int32_t* idx, void* stream);
+ * shared memory (N <= 51200), else DRB_ERR_UNSUPPORTED (use drb_sample).
+ * offset_dev (nullable): one uint64 in device memory that is ADDED to `offset` when the kernel runs, so a
+ * captured CUDA graph draws fresh sets on every replay (the caller advances it on the same stream).  */
+int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offset, const uint64_t* offset_dev, int B,
+                    int K, int N, int s, int32_t* idx, void* stream);
 
 /* Straight-through backward of the sampler (autograd of gumbel_sampler.py:34-38 + ransac.py:64-65).
  * g_sel[B,K,s] = dL/d ret[b,k,idx[b,k,j]] = sum_c matches[n,c] * dL/d minimal[b,k,j,c].
