@@ -303,7 +303,8 @@ def main():
             j = (first + i) % NB
             with torch.cuda.stream(side[i % S]):
                 outs.append(engine.ransac_e5_test(matches_all[j], logits_all[j], K, thr, seed=42 + rank,
-                                                  offset=first + i, streams=args.streams))
+                                                  offset=first + i, streams=args.streams,
+                                                  scorer="block" if S > 1 else None))
                 if len(outs) > 2 * S:
                     outs.pop(0)
         for st in side:
@@ -392,13 +393,15 @@ def main():
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
     n_valid = int(cc.sum().item())
     reps = 10
+    msac_kernel = "block" if S > 1 else "stream"      # the kernel the timed steps above ran
+    msac_name = {"block": "score_msac_kernel", "stream": "score_msac_stream_kernel"}[msac_kernel]
     for _ in range(3):
-        ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True)
+        ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True, kernel=msac_kernel)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     for a, b_ in evs:
         flush.fill_(1.0)
         a.record()
-        ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True)
+        ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True, kernel=msac_kernel)
         b_.record()
     torch.cuda.synchronize()
     score_ms = sum(a.elapsed_time(b_) for a, b_ in evs) / reps          # includes the 8-byte/pair memset of `best`
@@ -407,7 +410,10 @@ def main():
     for name, fn in (("sample_sets", lambda: ops.sample_sets(logits, K, 5, seed=7, offset=1)),
                      ("sample_gumbel_race", lambda: ops.sample(logits, K, 5, 1.0, seed=7, offset=1)),
                      ("solve_e5", lambda: ops.solve_e5(matches, idx, compact=True)),
-                     ("score_msac", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=False)),
+                     ("score_msac", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=False,
+                                                           kernel=msac_kernel)),
+                     ("score_msac_stream", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
+                                                                  want_scores=False, kernel="stream")),
                      ):
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fn()
@@ -444,8 +450,8 @@ def main():
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=4 * max(1, args.streams) * args.steps,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                      traffic=load_traffic("score_msac_kernel"),
-                      kernel="score_msac_kernel", kernel_ms=score_ms, algorithmic_bytes=score_bytes,
+                      traffic=load_traffic(msac_name),
+                      kernel=msac_name, kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,
                       note="FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops",
                       fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,

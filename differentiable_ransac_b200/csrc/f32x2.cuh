@@ -53,4 +53,11 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+// max(0, min(1, a * b + c)) in one FMA-pipe instruction (FFMA.SAT); NaN -> +0
+__device__ __forceinline__ float fma_sat(float a, float b, float c) {
+    float d;
+    asm("fma.rn.sat.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 }  // namespace drb

@@ -124,11 +124,12 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
                 pk2_split(BJ, bjl, bjh);
                 const pk2 AU = pk2_mul(AR2, pk2_make(rcp_approx(ajl), rcp_approx(ajh)));
                 const pk2 BU = pk2_mul(BR2, pk2_make(rcp_approx(bjl), rcp_approx(bjh)));
-                float atl, ath, btl, bth;
-                pk2_split(pk2_fma(AU, neg_inv, one), atl, ath);
-                pk2_split(pk2_fma(BU, neg_inv, one), btl, bth);
-                acc = pk2_add(acc, pk2_make(fmaxf(atl, 0.f), fmaxf(ath, 0.f)));
-                accB = pk2_add(accB, pk2_make(fmaxf(btl, 0.f), fmaxf(bth, 0.f)));
+                // 1 - u / thr^2 <= 1 always, so the saturating FMA is the clamp max(., 0) (and NaN -> 0)
+                float aul, auh, bul, buh;
+                pk2_split(AU, aul, auh);
+                pk2_split(BU, bul, buh);
+                acc = pk2_add(acc, pk2_make(fma_sat(aul, -inv_thr2, 1.f), fma_sat(auh, -inv_thr2, 1.f)));
+                accB = pk2_add(accB, pk2_make(fma_sat(bul, -inv_thr2, 1.f), fma_sat(buh, -inv_thr2, 1.f)));
             }
             for (; i < npairs; ++i) {
                 const ulonglong2 a1 = t2[2 * i], a2 = t2[2 * i + 1];

@@ -42,11 +42,16 @@ def _side_streams(device, n):
 
 
 def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False,
-                   sampler="sets", streams=1, offset_dev=None):
+                   sampler="sets", streams=1, offset_dev=None, scorer=None):
     """matches [B,N,4], logits [B,N], thr [B] (normalised threshold, ransac.py:49-53).
     Returns dict(best_model [B,3,3], best_hyp [B], best_slot [B], best_score [B], mask [B,N] bool,
     ninl [B], idx [B,K,5], models [B,K,10,3,3], nsol [B,K] (, scores [B,K*10] in compact order,
     cids)).
+
+    scorer: "stream" (default; persistent work-queue kernel: lowest latency for one call, and it keeps every SM
+    busy when there are few models) or "block" (one CTA per 32 models: its CTAs retire one by one, which lets
+    the kernels of an independent call on another stream move in -- what pipelined callers want, see
+    E5TestService).
 
     streams > 1 splits the pairs into that many sub-batches issued on separate CUDA streams: the
     5-point kernel is latency-bound (one thread per hypothesis, ~7 warps per SM), so its idle issue
@@ -69,7 +74,8 @@ def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     idx = _draw(logits, K, 5, tau, noise, seed, offset, sampler, offset_dev)
     best0, cc0 = ops.zeroed_counters(B, matches.device)
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True, ccount=cc0)
-    scores, best = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=want_scores, best=best0)
+    scores, best = ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=want_scores, best=best0,
+                                  kernel=scorer)
     best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, models.reshape(B, -1, 9), best, thr)
     # best_id = hypothesis * 10 + slot; mask is 0/1 bytes, reinterpreted (not copied) as bool
     out = dict(best_model=best_model, best_id=best_id, best_score=best_score, mask=mask.view(torch.bool), ninl=ninl,
@@ -367,7 +373,8 @@ class E5TestService:
         B, N = self.B, self.N
         buf = self.dev_in[slot]
         o = ransac_e5_test(buf[: B * N * 4].view(B, N, 4), buf[B * N * 4: B * N * 5].view(B, N), self.K,
-                           buf[B * N * 5:], seed=self.seed, offset=offset, offset_dev=offset_dev)
+                           buf[B * N * 5:], seed=self.seed, offset=offset, offset_dev=offset_dev,
+                           scorer="block" if self.slots > 1 else None)
         return o, torch.cat((o["best_model"].flatten(), o["best_id"].float(), o["best_score"], o["ninl"].float()))
 
     def _capture(self, slot):

@@ -4,6 +4,7 @@ PyTorch here is plumbing (device memory + streams) -- all arithmetic is in libdr
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -143,6 +144,29 @@ def zeroed_counters(B, device):
     best_packed [B] (u64 as int64) and ccount [B] int32."""
     z = torch.zeros(2 * B, dtype=torch.int64, device=device)
     return z[:B], z[B:].view(torch.int32)[:B]
+
+
+_WS_CACHE = {}
+
+
+def score_workspace(B, M, N, device):
+    """Workspace of drb_score_msac_stream for (B, M, N): an int64 tensor whose leading queue / arrival counters
+    are zero.  The kernel leaves them zero, and launches on one stream are ordered, so the buffer is cached
+    per (device, stream, size) -- two streams never share one."""
+    lib = _lib.load()
+    nbytes = int(lib.drb_score_msac_workspace_bytes(int(B), int(M), int(N)))
+    zbytes = int(lib.drb_score_msac_workspace_zeroed_bytes(int(B), int(M)))
+    dev = torch.device(device)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream, nbytes, zbytes,
+           torch.cuda.is_current_stream_capturing())
+    ws = _WS_CACHE.get(key)
+    if ws is None:
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+        ws[: zbytes // 8].zero_()
+        if len(_WS_CACHE) > 64:
+            _WS_CACHE.clear()
+        _WS_CACHE[key] = ws
+    return ws
 
 
 def solve_e5(matches, idx=None, compact=False, ccount=None):
@@ -297,9 +321,14 @@ def solve_rigid3_backward(points, idx, g_model, flag=True):
 
 
 # ---- scoring -----------------------------------------------------------------------------------
-def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None):
+_MSAC_KERNEL = os.environ.get("DRB_MSAC_KERNEL", "stream")
+
+
+def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None, kernel=None):
     """matches [B,N,4], models [B,M,9|3,3], thr [B] -> scores [B,M] | None, best_packed [B] (int64 view of u64).
-    `best` may be a caller-zeroed [B] int64 buffer."""
+    `best` may be a caller-zeroed [B] int64 buffer.  kernel="stream": the evenly split persistent grid
+    (drb_score_msac_stream); "block": one CTA per (pair, 32 models) (drb_score_msac)."""
+    kernel = kernel or _MSAC_KERNEL
     matches = _f32(matches)
     B, N, _ = matches.shape
     models = _f32(models).reshape(B, -1, 9)
@@ -309,9 +338,17 @@ def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, bes
     if best is None:
         best = torch.zeros(B, dtype=torch.int64, device=matches.device)
     lib = _lib.load()
-    check(lib.drb_score_msac(_p(matches), _p(models), _p(None if count is None else _i32(count)),
-                             _p(None if ids is None else _i32(ids)), _p(thr), B, M, N, _p(scores), _p(best),
-                             _stream()), "drb_score_msac")
+    count = None if count is None else _i32(count)
+    ids = None if ids is None else _i32(ids)
+    if kernel == "stream":
+        ws = score_workspace(B, M, N, matches.device)
+        check(lib.drb_score_msac_stream(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N, _p(scores),
+                                        _p(best), _p(ws), ws.numel() * 8, _stream()), "drb_score_msac_stream")
+    elif kernel == "block":
+        check(lib.drb_score_msac(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N, _p(scores), _p(best),
+                                 _stream()), "drb_score_msac")
+    else:
+        raise _lib.DrbError(f"unknown MSAC kernel {kernel!r}")
     return scores, best
 
 

@@ -24,6 +24,7 @@
 #ifndef DRB_H_
 #define DRB_H_
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -139,6 +140,19 @@ int drb_solve_rigid3_backward(const float* points, const int32_t* idx, int B, in
 int drb_score_msac(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
                    const float* thr, int B, int M, int N,
                    float* scores, unsigned long long* best_packed, void* stream);
+/* The same contract on a work queue (score_stream.cu): persistent one-warp CTAs pull (32 models x 192
+ * correspondences) units from an atomic counter, so no warp idles while another still has work; the pieces
+ * of a model block are summed in piece order by the warp that delivers the last one (the scores do not
+ * depend on the schedule).  B <= 1024.  Needs a 16-byte aligned workspace of
+ * drb_score_msac_workspace_bytes(B, M, N) bytes whose first drb_score_msac_workspace_zeroed_bytes(B, M)
+ * bytes are ZERO on entry; the kernel leaves them zero, so one memset serves every later call that uses
+ * the workspace on the same stream.                                                              */
+size_t drb_score_msac_workspace_bytes(int B, int M, int N);
+size_t drb_score_msac_workspace_zeroed_bytes(int B, int M);
+int drb_score_msac_stream(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
+                          const float* thr, int B, int M, int N,
+                          float* scores, unsigned long long* best_packed, void* workspace,
+                          size_t workspace_bytes, void* stream);
 /* Decode best_packed and produce the winner's model, score, id and inlier mask
  * (d2 < (1.5 thr)^2, msac_score.py:44) -- the only mask ransac.py:116-118 ever uses.
  * models_dense[B,Md,9] is indexed by best id.  best_id[B], best_score[B], best_model[B,9],
