@@ -252,7 +252,9 @@ def main():
                     help="batches in flight in the end-to-end service (engine.E5TestService)")
     ap.add_argument("--e2e-graph", type=int, default=int(os.environ.get("DRB_E2E_GRAPH", "1")),
                     help="1: each service slot replays one CUDA graph (copy-in, kernels, copy-out) per batch")
-    ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "2")),
+    ap.add_argument("--value-graph", type=int, default=int(os.environ.get("DRB_VALUE_GRAPH", "1")),
+                    help="1: the device-resident steps replay one CUDA graph per stream")
+    ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "3")),
                     help="CUDA streams the K device-resident steps are issued over (1 = strictly serial)")
     ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "1")),
                     help="sub-batches on separate CUDA streams (measured: 1 is fastest, profiles/r1_notes.md)")
@@ -280,36 +282,28 @@ def main():
     matches_h, logits_h, thr_h, E_gt = make_inputs(B, N, seed=1234 + 1000 * rank)   # pairs shard over ranks
     matches_h, logits_h, thr_h = matches_h.pin_memory(), logits_h.pin_memory(), thr_h.pin_memory()
     matches, logits, thr = matches_h.to(dev), logits_h.to(dev), thr_h.to(dev)
-    # L2 policy for `value`: the steps cycle through NB copies of the inputs at distinct addresses, 168 MB in
-    # all (> the 126 MB L2), so a step never finds its inputs cached by an earlier one; the roofline pass
-    # below (one kernel timed alone) flushes L2 with a 256 MB write instead.
+    # L2 policy for `value`: every step copies its (packed) inputs from one of NB places in HBM, 168 MB in all
+    # (> the 126 MB L2), so a step never finds its inputs cached by an earlier one; the roofline pass below
+    # (one kernel timed alone) flushes L2 with a 256 MB write instead.
     NB = 128
-    matches_all = matches.unsqueeze(0).repeat(NB, 1, 1, 1)
-    logits_all = logits.unsqueeze(0).repeat(NB, 1, 1)
+    packed_all = torch.cat((matches.flatten(), logits.flatten(), thr)).unsqueeze(0).repeat(NB, 1)   # [NB, n_in]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
     S = max(1, args.value_streams)
     main_stream = torch.cuda.current_stream()
-    side = [torch.cuda.Stream(device=dev) for _ in range(S)]
+    dsvc = engine.E5TestService(B, N, K, dev, slots=S, seed=42 + rank, graph=bool(args.value_graph), host_io=False)
 
     def run_steps(n, first):
-        """n independent steps (fresh Philox offset each), issued round-robin over S streams: the latency-bound
-        5-point kernel of one step overlaps the FMA-bound scoring kernel of the previous one."""
+        """n independent steps (fresh Philox offset each) through engine.E5TestService(host_io=False): issued
+        round-robin over S streams (one CUDA graph per stream when --value-graph 1), so the latency-bound
+        5-point kernel of one step overlaps the FMA-bound scoring kernel of the previous one.  Every step
+        first copies ITS inputs, device to device, from one of NB distinct places in HBM."""
         fork = torch.cuda.Event()
         fork.record(main_stream)
-        outs = []
-        for st in side:
-            st.wait_event(fork)
+        dsvc.after(fork)
         for i in range(n):
-            j = (first + i) % NB
-            with torch.cuda.stream(side[i % S]):
-                outs.append(engine.ransac_e5_test(matches_all[j], logits_all[j], K, thr, seed=42 + rank,
-                                                  offset=first + i, streams=args.streams,
-                                                  scorer="block" if S > 1 else None))
-                if len(outs) > 2 * S:
-                    outs.pop(0)
-        for st in side:
-            main_stream.wait_stream(st)
-        return outs[-1]
+            dsvc.submit(packed=packed_all[(first + i) % NB])
+        dsvc.join(main_stream)
+        return dsvc.dev_out[(n - 1) % S]
 
     def barrier():
         torch.cuda.synchronize()
@@ -346,7 +340,7 @@ def main():
         out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i, streams=args.streams)
         ev[i][1].record()
     barrier()
-    ms_serial = sum(a.elapsed_time(b) for a, b in ev) / args.steps
+    ms_serial = sorted(a.elapsed_time(b) for a, b in ev)[args.steps // 2]      # median
 
     # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
     # engine.E5TestService: every step copies ITS inputs from pinned host memory (one packed buffer: matches |
@@ -437,10 +431,11 @@ def main():
                     pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N,
                     noise="in-kernel Philox4x32-10; sets drawn without replacement from softmax(logits) "
                           "(= Gumbel top-5 in law, drb_sample_sets)",
-                    l2="`value`: steps cycle through 128 copies of the inputs at distinct addresses (168 MB > L2); "
+                    l2="`value`: every step copies its inputs (device to device, inside the timed region) from one "
+                       "of 128 distinct places in HBM, 168 MB in all (> L2); "
                        "serial_ms_per_step and the roofline pass: L2 flushed by a 256 MB write before each launch; "
                        "e2e re-copies its inputs from the host every step",
-                    value_streams=S, serial_ms_per_step=ms_serial,
+                    value_streams=S, value_graph=bool(args.value_graph), serial_ms_per_step=ms_serial,
                     e2e_mode=f"engine.E5TestService(graph={bool(args.e2e_graph)}), {args.e2e_slots} batches in flight "
                              "(one stream each; a CUDA graph per slot when graph=True): packed H2D per step, one packed D2H of (model, id, score, #inliers) "
                              "per step, results read on the host before a slot is reused",

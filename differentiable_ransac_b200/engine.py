@@ -344,9 +344,12 @@ class E5TestService:
     the FMA-bound scoring kernel of batch i leaves idle (measured on B200, cfg2: 0.309 -> 0.256 ms per batch
     with two slots, profiles/r1_notes.md)."""
 
-    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False):
+    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False, host_io=True):
         self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
         self.graph = bool(graph)
+        # host_io=False: batches are already on the device -- submit(slot, packed=<device tensor>) copies the
+        # packed batch into the slot (device to device) and results stay on the device (`dev_out[slot]`)
+        self.host_io = bool(host_io)
         self.device = torch.device(device)
         self.slots = int(slots)
         self.n_in = B * N * 4 + B * N + B
@@ -354,6 +357,7 @@ class E5TestService:
         self.host_in = [torch.empty(self.n_in, dtype=torch.float32).pin_memory() for _ in range(self.slots)]
         self.host_out = [torch.empty(self.n_out, dtype=torch.float32).pin_memory() for _ in range(self.slots)]
         self.dev_in = [torch.empty(self.n_in, dtype=torch.float32, device=self.device) for _ in range(self.slots)]
+        self.dev_out = [torch.empty(self.n_out, dtype=torch.float32, device=self.device) for _ in range(self.slots)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.compute = [torch.cuda.Stream(device=self.device) for _ in range(self.slots)]
         self.copied = [torch.cuda.Event() for _ in range(self.slots)]
@@ -385,10 +389,11 @@ class E5TestService:
         ks.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=ks):
-            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            if self.host_io:
+                self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
             _, packed = self._body(slot, 0, self.counters[slot])
             self.counters[slot].add_(self.slots)
-            self.host_out[slot].copy_(packed, non_blocking=True)
+            (self.host_out if self.host_io else self.dev_out)[slot].copy_(packed, non_blocking=True)
         self.graphs[slot] = g
 
     def stage(self, slot, matches, logits, thr):
@@ -400,14 +405,29 @@ class E5TestService:
         buf[B * N * 4: B * N * 5].copy_(logits.reshape(-1))
         buf[B * N * 5:].copy_(thr.reshape(-1))
 
-    def submit(self, slot=None):
-        """Enqueue the batch staged in `host_in[slot]`; returns the slot."""
+    def submit(self, slot=None, packed=None):
+        """Enqueue the batch staged in `host_in[slot]` (host_io) or given as one packed device tensor
+        (matches | logits | thr, `n_in` floats; host_io=False); returns the slot."""
         if slot is None:
             slot = self.step % self.slots
-        if self.busy[slot]:
+        if self.busy[slot] and self.host_io:
             self.done[slot].synchronize()          # the slot's previous results must have been collected
         B, N = self.B, self.N
         cs, ks = self.copy_stream, self.compute[slot]
+        if not self.host_io:
+            if self.graph and self.graphs[slot] is None:
+                self._capture(slot)
+            with torch.cuda.stream(ks):            # in order on the slot's stream: no events needed
+                self.dev_in[slot].copy_(packed, non_blocking=True)
+                if self.graph:
+                    self.graphs[slot].replay()
+                else:
+                    _, out = self._body(slot, self.step, None)
+                    self.dev_out[slot].copy_(out, non_blocking=True)
+                self.done[slot].record(ks)
+            self.busy[slot] = True
+            self.step += 1
+            return slot
         if self.graph:
             if self.graphs[slot] is None:
                 self._capture(slot)
@@ -432,11 +452,12 @@ class E5TestService:
         return slot
 
     def result(self, slot):
-        """Wait for the slot's batch; -> dict of host tensors (views of the slot's pinned output buffer)."""
+        """Wait for the slot's batch; -> dict of tensors: views of the slot's pinned output buffer (host_io) or
+        of its device output buffer."""
         self.done[slot].synchronize()
         self.busy[slot] = False
         B = self.B
-        out = self.host_out[slot]
+        out = (self.host_out if self.host_io else self.dev_out)[slot]
         return dict(best_model=out[: 9 * B].view(B, 3, 3), best_id=out[9 * B: 10 * B].to(torch.int32),
                     best_score=out[10 * B: 11 * B], ninl=out[11 * B: 12 * B].to(torch.int32))
 

@@ -17,6 +17,12 @@ noise = synth.gumbel_noise((B, K, N), seed=3)
 m, E, lg, thr, noise = m.to(DEV), E.to(DEV), lg.to(DEV), thr.to(DEV), noise.to(DEV)
 for kw in (dict(), dict(noise=noise), dict(sampler="gumbel")):
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, **kw)
+for scorer in ("block", "stream"):       # both MSAC kernels; the queue kernel with a block cut into several pieces
+    out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, scorer=scorer)
+svc = engine.E5TestService(B, N, K, DEV, slots=2, seed=1, graph=False, host_io=False)
+for _ in range(3):
+    svc.submit(packed=torch.cat((m.flatten(), lg.flatten(), thr)))
+svc.drain()
 out8 = engine.ransac_f8_test(m, lg, K, thr)
 ops.solve_f7(m, ops.sample_sets(lg, K, 7))
 mm = m.clone().requires_grad_(True)

@@ -39,9 +39,32 @@ def test_service_matches_direct_call(slots, graph):
     svc.drain()
     assert len(got) == len(batches)
     for j, (matches, logits, thr) in enumerate(batches):
-        want = engine.ransac_e5_test(matches.to(DEV), logits.to(DEV), K, thr.to(DEV), seed=11, offset=j)
+        want = engine.ransac_e5_test(matches.to(DEV), logits.to(DEV), K, thr.to(DEV), seed=11, offset=j,
+                                     scorer="block" if slots > 1 else None)   # the kernel the service picks
         torch.cuda.synchronize()
         assert torch.equal(got[j]["best_id"], want["best_id"].cpu())
         assert torch.equal(got[j]["best_score"], want["best_score"].cpu())
         assert torch.equal(got[j]["best_model"], want["best_model"].cpu())
         assert torch.equal(got[j]["ninl"], want["ninl"].cpu())
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_device_resident_service_matches_direct_call(graph):
+    from differentiable_ransac_b200 import engine, synth
+
+    B, N, K, slots = 4, 600, 64, 2
+    svc = engine.E5TestService(B, N, K, DEV, slots=slots, seed=5, graph=graph, host_io=False)
+    batches = []
+    for j in range(4):
+        matches, _, _ = synth.relative_pose_batch(B, N, seed=70 + j, noise=5e-4)
+        logits = synth.logits_regime(B, N, "L0", seed=80 + j)
+        thr = torch.full((B,), 0.75 / 800.0)
+        batches.append((matches.to(DEV), logits.to(DEV), thr.to(DEV)))
+    for j, (m, lg, thr) in enumerate(batches):
+        slot = svc.submit(packed=torch.cat((m.flatten(), lg.flatten(), thr)))
+        got = {k: v.clone() for k, v in svc.result(slot).items()}
+        want = engine.ransac_e5_test(m, lg, K, thr, seed=5, offset=j, scorer="block")
+        torch.cuda.synchronize()
+        assert torch.equal(got["best_id"], want["best_id"])
+        assert torch.equal(got["best_score"], want["best_score"])
+        assert torch.equal(got["best_model"], want["best_model"])
