@@ -237,7 +237,7 @@ def run_reference_arm(args):
                                   sample=f"{args.steps} step(s) of 1 pair x {K} hyps x {N} corrs, {cores} threads "
                                          f"(fastest of a sweep; host has {host_cores} cores)"),
                 e2e=dict(value=value, unit="hypotheses/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line))
+    return line
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -259,8 +259,22 @@ def main():
     ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "1")),
                     help="sub-batches on separate CUDA streams (measured: 1 is fastest, profiles/r1_notes.md)")
     args = ap.parse_args()
-    if args.impl == "reference":
-        return run_reference_arm(args)
+    # stdout carries exactly one JSON line: everything else a library prints there while we run (NCCL's version
+    # banner, for one) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+    try:
+        line = run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+    finally:
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        os.close(real_stdout)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -455,10 +469,10 @@ def main():
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_reference_throughput()
         line["accuracy"] = auc_parity(dev)
-    print(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    return line
 
 
 if __name__ == "__main__":
