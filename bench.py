@@ -268,8 +268,6 @@ def main():
                     help="1: the device-resident steps replay one CUDA graph per stream")
     ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "3")),
                     help="CUDA streams the K device-resident steps are issued over (1 = strictly serial)")
-    ap.add_argument("--streams", type=int, default=int(os.environ.get("DRB_STREAMS", "1")),
-                    help="sub-batches on separate CUDA streams (measured: 1 is fastest, profiles/r1_notes.md)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything else a library prints there while we run (NCCL's version
     # banner, for one) goes to stderr
@@ -363,7 +361,7 @@ def run_ours(args):
     for i in range(args.steps):
         flush.fill_(float(i))
         ev[i][0].record()
-        out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i, streams=args.streams)
+        out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i)
         ev[i][1].record()
     barrier()
     ms_serial = sorted(a.elapsed_time(b) for a, b in ev)[args.steps // 2]      # median
@@ -464,11 +462,10 @@ def run_ours(args):
                     e2e_mode=f"engine.E5TestService(graph={bool(args.e2e_graph)}), {args.e2e_slots} batches in flight "
                              "(one stream each; a CUDA graph per slot when graph=True): packed H2D per step, one packed D2H of (model, id, score, #inliers) "
                              "per step, results read on the host before a slot is reused",
-                    streams=args.streams,
                     parallelism=f"pairs sharded over {world} GPU(s)"),
         clocks=clock_info,
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-        gpu_launches=4 * max(1, args.streams) * args.steps,
+        gpu_launches=4 * args.steps,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                       traffic=load_traffic(msac_name),
                       kernel=msac_name, kernel_ms=score_ms, algorithmic_bytes=score_bytes,

@@ -13,6 +13,7 @@
 #include "../../include/drb.h"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
+#include "msac_records.cuh"
 #include "sampson.cuh"
 #include "tile_pipe.cuh"
 
@@ -26,7 +27,6 @@ constexpr int kMsacThreads = 32;
 constexpr int kMsacTile = 192;
 constexpr int kTileRigid = 768;   // 3-D correspondences (24 B) per stage
 
-template <bool SCHED>
 __global__ void __launch_bounds__(kMsacThreads)
 score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ models,
                   const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
@@ -50,14 +50,12 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     }
     const float t = 1.5f * __ldg(thr + b);
     const float inv_thr2 = 1.f / (t * t);
-    float acc0 = 0.f, acc1 = 0.f;
 
     // model coefficients as packed broadcast operands (ptxas folds the splat into the FFMA2
     // scalar-broadcast operand form, so these cost no extra registers)
     pk2 mp[9];
     DRB_UNROLL
     for (int i = 0; i < 9; ++i) mp[i] = pk2_splat(m[i]);
-    const pk2 neg_inv = pk2_splat(-inv_thr2), one = pk2_splat(1.f);
     pk2 acc = pk2_splat(0.f), accB = pk2_splat(0.f);
 
     TilePipe<4, kMsacTile> pipe(tiles, bars, matches + (size_t)b * N * 4, N);
@@ -65,128 +63,18 @@ score_msac_kernel(const float* __restrict__ matches, const float* __restrict__ m
     for (int tI = 0; tI < pipe.n_tiles; ++tI) {
         float4* tile = reinterpret_cast<float4*>(const_cast<float*>(pipe.acquire(tI)));
         const int np = pipe.tile_items(tI);
-        const int npairs = np >> 1;
-        // interleave each pair of correspondences in place:
-        // (x1p y1p x2p y2p | x1q y1q x2q y2q) -> (x1p x1q y1p y1q | x2p x2q y2p y2q)
-        for (int i = threadIdx.x; i < npairs; i += kMsacThreads) {
-            const float4 p = tile[2 * i], q = tile[2 * i + 1];
-            tile[2 * i] = make_float4(p.x, q.x, p.y, q.y);
-            tile[2 * i + 1] = make_float4(p.z, q.z, p.w, q.w);
-        }
+        // records of two correspondences, padded with NaN to an even count (a full tile is 96 records)
+        const int recs_even = msac_interleave(tile, np, threadIdx.x, kMsacThreads);
         __syncthreads();
-        if (active && SCHED) {
-            // Hand-ordered variant: two point-pairs (A, B) per trip, packed ops pinned in program order so
-            // that instructions sharing a source (Y1 three times, X1 three times, Y2 twice, X2 twice) are
-            // adjacent and the operand-reuse cache can serve them; groups of A and B alternate so that a
-            // result is never consumed by the very next instruction.
+        if (active) {
             const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tile);
-            int i = 0;
-            for (; i + 1 < npairs; i += 2) {
-                const ulonglong2 a1 = t2[2 * i], a2 = t2[2 * i + 1], b1 = t2[2 * i + 2], b2 = t2[2 * i + 3];
-                const pk2 AX1 = a1.x, AY1 = a1.y, AX2 = a2.x, AY2 = a2.y;
-                const pk2 BX1 = b1.x, BY1 = b1.y, BX2 = b2.x, BY2 = b2.y;
-                const pk2 At0 = pk2_fma_v(mp[1], AY1, mp[2]);
-                const pk2 At1 = pk2_fma_v(mp[4], AY1, mp[5]);
-                const pk2 At2 = pk2_fma_v(mp[7], AY1, mp[8]);
-                const pk2 Bt0 = pk2_fma_v(mp[1], BY1, mp[2]);
-                const pk2 Bt1 = pk2_fma_v(mp[4], BY1, mp[5]);
-                const pk2 Bt2 = pk2_fma_v(mp[7], BY1, mp[8]);
-                const pk2 AE0 = pk2_fma_v(mp[0], AX1, At0);
-                const pk2 AE1 = pk2_fma_v(mp[3], AX1, At1);
-                const pk2 AE2 = pk2_fma_v(mp[6], AX1, At2);
-                const pk2 BE0 = pk2_fma_v(mp[0], BX1, Bt0);
-                const pk2 BE1 = pk2_fma_v(mp[3], BX1, Bt1);
-                const pk2 BE2 = pk2_fma_v(mp[6], BX1, Bt2);
-                const pk2 Au0 = pk2_fma_v(mp[3], AY2, mp[6]);
-                const pk2 Au1 = pk2_fma_v(mp[4], AY2, mp[7]);
-                const pk2 Bu0 = pk2_fma_v(mp[3], BY2, mp[6]);
-                const pk2 Bu1 = pk2_fma_v(mp[4], BY2, mp[7]);
-                const pk2 AF0 = pk2_fma_v(mp[0], AX2, Au0);
-                const pk2 AF1 = pk2_fma_v(mp[1], AX2, Au1);
-                const pk2 BF0 = pk2_fma_v(mp[0], BX2, Bu0);
-                const pk2 BF1 = pk2_fma_v(mp[1], BX2, Bu1);
-                const pk2 Ar0 = pk2_fma_v(AY2, AE1, AE2);
-                const pk2 Br0 = pk2_fma_v(BY2, BE1, BE2);
-                const pk2 Aj0 = pk2_mul_v(AF1, AF1);
-                const pk2 Bj0 = pk2_mul_v(BF1, BF1);
-                const pk2 AR = pk2_fma_v(AX2, AE0, Ar0);
-                const pk2 BR = pk2_fma_v(BX2, BE0, Br0);
-                const pk2 Aj1 = pk2_fma_v(AF0, AF0, Aj0);
-                const pk2 Bj1 = pk2_fma_v(BF0, BF0, Bj0);
-                const pk2 Aj2 = pk2_fma_v(AE1, AE1, Aj1);
-                const pk2 Bj2 = pk2_fma_v(BE1, BE1, Bj1);
-                const pk2 AJ = pk2_fma_v(AE0, AE0, Aj2);
-                const pk2 BJ = pk2_fma_v(BE0, BE0, Bj2);
-                const pk2 AR2 = pk2_mul_v(AR, AR);
-                const pk2 BR2 = pk2_mul_v(BR, BR);
-                float ajl, ajh, bjl, bjh;
-                pk2_split(AJ, ajl, ajh);
-                pk2_split(BJ, bjl, bjh);
-                const pk2 AU = pk2_mul(AR2, pk2_make(rcp_approx(ajl), rcp_approx(ajh)));
-                const pk2 BU = pk2_mul(BR2, pk2_make(rcp_approx(bjl), rcp_approx(bjh)));
-                // 1 - u / thr^2 <= 1 always, so the saturating FMA is the clamp max(., 0) (and NaN -> 0)
-                float aul, auh, bul, buh;
-                pk2_split(AU, aul, auh);
-                pk2_split(BU, bul, buh);
-                acc = pk2_add(acc, pk2_make(fma_sat(aul, -inv_thr2, 1.f), fma_sat(auh, -inv_thr2, 1.f)));
-                accB = pk2_add(accB, pk2_make(fma_sat(bul, -inv_thr2, 1.f), fma_sat(buh, -inv_thr2, 1.f)));
-            }
-            for (; i < npairs; ++i) {
-                const ulonglong2 a1 = t2[2 * i], a2 = t2[2 * i + 1];
-                const pk2 X1 = a1.x, Y1 = a1.y, X2 = a2.x, Y2 = a2.y;
-                const pk2 E0 = pk2_fma(mp[0], X1, pk2_fma(mp[1], Y1, mp[2]));
-                const pk2 E1 = pk2_fma(mp[3], X1, pk2_fma(mp[4], Y1, mp[5]));
-                const pk2 E2 = pk2_fma(mp[6], X1, pk2_fma(mp[7], Y1, mp[8]));
-                const pk2 F0 = pk2_fma(mp[0], X2, pk2_fma(mp[3], Y2, mp[6]));
-                const pk2 F1 = pk2_fma(mp[1], X2, pk2_fma(mp[4], Y2, mp[7]));
-                const pk2 R = pk2_fma(X2, E0, pk2_fma(Y2, E1, E2));
-                const pk2 J = pk2_fma(E0, E0, pk2_fma(E1, E1, pk2_fma(F0, F0, pk2_mul(F1, F1))));
-                float jl, jh;
-                pk2_split(J, jl, jh);
-                const pk2 U = pk2_mul(pk2_mul(R, R), pk2_make(rcp_approx(jl), rcp_approx(jh)));
-                float tl, th;
-                pk2_split(pk2_fma(U, neg_inv, one), tl, th);
-                acc = pk2_add(acc, pk2_make(fmaxf(tl, 0.f), fmaxf(th, 0.f)));
-            }
-            if (np & 1) {
-                const float4 p = tile[np - 1];
-                const Sampson a = sampson(m, p.x, p.y, p.z, p.w);
-                acc0 += fmaxf(fmaf(-(a.r * a.r) * rcp_approx(a.j), inv_thr2, 1.f), 0.f);
-            }
-        } else if (active) {
-            const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(tile);
-#pragma unroll 2
-            for (int i = 0; i < npairs; ++i) {
-                const ulonglong2 a1 = t2[2 * i], a2 = t2[2 * i + 1];
-                const pk2 X1 = a1.x, Y1 = a1.y, X2 = a2.x, Y2 = a2.y;
-                const pk2 E0 = pk2_fma(mp[0], X1, pk2_fma(mp[1], Y1, mp[2]));
-                const pk2 E1 = pk2_fma(mp[3], X1, pk2_fma(mp[4], Y1, mp[5]));
-                const pk2 E2 = pk2_fma(mp[6], X1, pk2_fma(mp[7], Y1, mp[8]));
-                const pk2 F0 = pk2_fma(mp[0], X2, pk2_fma(mp[3], Y2, mp[6]));
-                const pk2 F1 = pk2_fma(mp[1], X2, pk2_fma(mp[4], Y2, mp[7]));
-                const pk2 R = pk2_fma(X2, E0, pk2_fma(Y2, E1, E2));
-                const pk2 J = pk2_fma(E0, E0, pk2_fma(E1, E1, pk2_fma(F0, F0, pk2_mul(F1, F1))));
-                float jl, jh;
-                pk2_split(J, jl, jh);
-                const pk2 U = pk2_mul(pk2_mul(R, R), pk2_make(rcp_approx(jl), rcp_approx(jh)));
-                float tl, th;
-                pk2_split(pk2_fma(U, neg_inv, one), tl, th);
-                acc = pk2_add(acc, pk2_make(fmaxf(tl, 0.f), fmaxf(th, 0.f)));
-            }
-            if (np & 1) {  // odd tail of the last tile (never interleaved)
-                const float4 p = tile[np - 1];
-                const Sampson a = sampson(m, p.x, p.y, p.z, p.w);
-                acc0 += fmaxf(fmaf(-(a.r * a.r) * rcp_approx(a.j), inv_thr2, 1.f), 0.f);
-            }
+            for (int i = 0; i < recs_even; i += 2) msac_two_records(t2 + 2 * i, mp, -inv_thr2, acc, accB);
         }
         pipe.release(tI);
     }
-    {
-        float lo, hi;
-        pk2_split(pk2_add(acc, accB), lo, hi);
-        acc1 = lo + hi;
-    }
-    const float score = acc0 + acc1;
+    float lo, hi;
+    pk2_split(pk2_add(acc, accB), lo, hi);
+    const float score = lo + hi;
     if (active && scores) scores[(size_t)b * M + mi] = score;
     unsigned long long key = active ? pack_best(score, ids ? ids[(size_t)b * M + mi] : mi) : 0ull;
     DRB_UNROLL
@@ -426,17 +314,8 @@ extern "C" int drb_score_msac(const float* matches, const float* models, const i
     if (!matches || !models || !thr || !best_packed) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || M <= 0 || N <= 0 || (M + kMsacThreads - 1) / kMsacThreads > 65535) return DRB_ERR_BAD_SHAPE;
     dim3 grid(B, (M + kMsacThreads - 1) / kMsacThreads);
-    // DRB_MSAC_SCHED=0 selects the compiler-scheduled inner loop (kept for A/B measurements)
-    static const bool sched = []() {
-        const char* e = getenv("DRB_MSAC_SCHED");
-        return e == nullptr || e[0] != '0';
-    }();
-    if (sched)
-        score_msac_kernel<true><<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N,
-                                                                                 scores, best_packed);
-    else
-        score_msac_kernel<false><<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N,
-                                                                                  scores, best_packed);
+    score_msac_kernel<<<grid, kMsacThreads, 0, (cudaStream_t)stream>>>(matches, models, count, ids, thr, M, N, scores,
+                                                                       best_packed);
     DRB_CHECK_LAUNCH();
 }
 

@@ -21,6 +21,7 @@
 #include "../../include/drb.h"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
+#include "msac_records.cuh"
 #include "sampson.cuh"
 #include "tile_pipe.cuh"
 
@@ -30,61 +31,6 @@ constexpr int kSsLanes = 32;       // models per block (one warp)
 constexpr int kSsPiece = 96;       // records (2 correspondences each) per work unit = one bulk copy of 3 KB
 constexpr int kSsRing = 2;         // pieces in flight per warp (6 KB, as the one-CTA-per-block kernel)
 constexpr int kSsSmemFloats = kSsRing * kSsPiece * 8;
-
-// Two records (A, B = four correspondences) against the thread's model: packed Sampson residuals and the
-// soft-MSAC increment.  Same hand-grouped order as score_msac_kernel<true> (operands shared by neighbours).
-__device__ __forceinline__ void ss_two_records(const ulonglong2* t2, const pk2* mp, pk2 neg_inv, pk2 one, pk2& acc,
-                                               pk2& accB) {
-    const ulonglong2 a1 = t2[0], a2 = t2[1], b1 = t2[2], b2 = t2[3];
-    const pk2 AX1 = a1.x, AY1 = a1.y, AX2 = a2.x, AY2 = a2.y;
-    const pk2 BX1 = b1.x, BY1 = b1.y, BX2 = b2.x, BY2 = b2.y;
-    const pk2 At0 = pk2_fma_v(mp[1], AY1, mp[2]);
-    const pk2 At1 = pk2_fma_v(mp[4], AY1, mp[5]);
-    const pk2 At2 = pk2_fma_v(mp[7], AY1, mp[8]);
-    const pk2 Bt0 = pk2_fma_v(mp[1], BY1, mp[2]);
-    const pk2 Bt1 = pk2_fma_v(mp[4], BY1, mp[5]);
-    const pk2 Bt2 = pk2_fma_v(mp[7], BY1, mp[8]);
-    const pk2 AE0 = pk2_fma_v(mp[0], AX1, At0);
-    const pk2 AE1 = pk2_fma_v(mp[3], AX1, At1);
-    const pk2 AE2 = pk2_fma_v(mp[6], AX1, At2);
-    const pk2 BE0 = pk2_fma_v(mp[0], BX1, Bt0);
-    const pk2 BE1 = pk2_fma_v(mp[3], BX1, Bt1);
-    const pk2 BE2 = pk2_fma_v(mp[6], BX1, Bt2);
-    const pk2 Au0 = pk2_fma_v(mp[3], AY2, mp[6]);
-    const pk2 Au1 = pk2_fma_v(mp[4], AY2, mp[7]);
-    const pk2 Bu0 = pk2_fma_v(mp[3], BY2, mp[6]);
-    const pk2 Bu1 = pk2_fma_v(mp[4], BY2, mp[7]);
-    const pk2 AF0 = pk2_fma_v(mp[0], AX2, Au0);
-    const pk2 AF1 = pk2_fma_v(mp[1], AX2, Au1);
-    const pk2 BF0 = pk2_fma_v(mp[0], BX2, Bu0);
-    const pk2 BF1 = pk2_fma_v(mp[1], BX2, Bu1);
-    const pk2 Ar0 = pk2_fma_v(AY2, AE1, AE2);
-    const pk2 Br0 = pk2_fma_v(BY2, BE1, BE2);
-    const pk2 Aj0 = pk2_mul_v(AF1, AF1);
-    const pk2 Bj0 = pk2_mul_v(BF1, BF1);
-    const pk2 AR = pk2_fma_v(AX2, AE0, Ar0);
-    const pk2 BR = pk2_fma_v(BX2, BE0, Br0);
-    const pk2 Aj1 = pk2_fma_v(AF0, AF0, Aj0);
-    const pk2 Bj1 = pk2_fma_v(BF0, BF0, Bj0);
-    const pk2 Aj2 = pk2_fma_v(AE1, AE1, Aj1);
-    const pk2 Bj2 = pk2_fma_v(BE1, BE1, Bj1);
-    const pk2 AJ = pk2_fma_v(AE0, AE0, Aj2);
-    const pk2 BJ = pk2_fma_v(BE0, BE0, Bj2);
-    const pk2 AR2 = pk2_mul_v(AR, AR);
-    const pk2 BR2 = pk2_mul_v(BR, BR);
-    float ajl, ajh, bjl, bjh;
-    pk2_split(AJ, ajl, ajh);
-    pk2_split(BJ, bjl, bjh);
-    const pk2 AU = pk2_mul(AR2, pk2_make(rcp_approx(ajl), rcp_approx(ajh)));
-    const pk2 BU = pk2_mul(BR2, pk2_make(rcp_approx(bjl), rcp_approx(bjh)));
-    // 1 - u / thr^2 <= 1 always, so the saturating FMA is the clamp max(., 0) (and NaN -> 0)
-    float aul, auh, bul, buh, nci, dummy;
-    pk2_split(AU, aul, auh);
-    pk2_split(BU, bul, buh);
-    pk2_split(neg_inv, nci, dummy);
-    acc = pk2_add(acc, pk2_make(fma_sat(aul, nci, 1.f), fma_sat(auh, nci, 1.f)));
-    accB = pk2_add(accB, pk2_make(fma_sat(bul, nci, 1.f), fma_sat(buh, nci, 1.f)));
-}
 
 __device__ __forceinline__ int ss_count(const int32_t* count, int b, int M) {
     return count ? min(max(__ldg(count + b), 0), M) : M;
@@ -163,7 +109,6 @@ score_msac_stream_kernel(const float* __restrict__ matches, const float* __restr
     __syncwarp();
     uint32_t bar_phase = 0;   // bit i = parity to wait for on bars[i]
     float4* ring_f4 = reinterpret_cast<float4*>(smem);
-    const float nanf_ = __int_as_float(0x7fc00000);
 
     // The first unit of every warp is fixed (unit w: no 4 736 simultaneous first pops of one counter); later
     // ones come from the queue.  The next unit is popped, and its correspondences requested, before the
@@ -194,34 +139,17 @@ score_msac_stream_kernel(const float* __restrict__ matches, const float* __restr
             for (int i = 0; i < 9; ++i) mp[i] = pk2_splat(__ldg(src + i));
         }
         const float tt = 1.5f * __ldg(thr + b);
-        const pk2 nc = pk2_splat(-1.f / (tt * tt)), one = pk2_splat(1.f);
+        const float nci = -1.f / (tt * tt);
 
         float4* cf4 = ring_f4 + slot * kSsPiece * 2;
         mbar_wait(&bars[slot], (bar_phase >> slot) & 1u);
         bar_phase ^= 1u << slot;
-        // interleave in place: (x1p y1p x2p y2p | x1q y1q x2q y2q) -> (x1p x1q y1p y1q | x2p x2q y2p y2q);
-        // a correspondence past the end becomes NaN (contributes exactly 0)
         const int pts = min(2 * kSsPiece, N - 2 * cur.j * kSsPiece);
-        const int recs = (pts + 1) >> 1;
-        DRB_UNROLL
-        for (int k = 0; k < kSsPiece / 32; ++k) {
-            const int i = lane + 32 * k;
-            if (i < recs) {
-                const float4 p = cf4[2 * i];
-                float4 q = cf4[2 * i + 1];
-                if (2 * i + 1 >= pts) q = make_float4(nanf_, nanf_, nanf_, nanf_);
-                cf4[2 * i] = make_float4(p.x, q.x, p.y, q.y);
-                cf4[2 * i + 1] = make_float4(p.z, q.z, p.w, q.w);
-            } else if (i == recs && (recs & 1)) {   // pad to an even number of records
-                cf4[2 * i] = make_float4(nanf_, nanf_, nanf_, nanf_);
-                cf4[2 * i + 1] = make_float4(nanf_, nanf_, nanf_, nanf_);
-            }
-        }
+        const int recs_even = msac_interleave(cf4, pts, lane, kSsLanes);   // even capacity 96 > recs when padded
         __syncwarp();
         pk2 acc = pk2_splat(0.f), accB = pk2_splat(0.f);
         const ulonglong2* t2 = reinterpret_cast<const ulonglong2*>(cf4);
-        const int recs_even = (recs + 1) & ~1;
-        for (int i = 0; i < recs_even; i += 2) ss_two_records(t2 + 2 * i, mp, nc, one, acc, accB);
+        for (int i = 0; i < recs_even; i += 2) msac_two_records(t2 + 2 * i, mp, nci, acc, accB);
         __syncwarp();   // every lane is done with this slot before lane 0 refills it
         float lo, hi;
         pk2_split(pk2_add(acc, accB), lo, hi);

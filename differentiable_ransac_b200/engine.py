@@ -31,18 +31,8 @@ def _draw(logits, K, s, tau, noise, seed, offset, sampler, offset_dev=None):
     return ops.sample(logits, K, s, tau, **_noise_args(noise, seed, offset))[0]
 
 
-_SIDE_STREAMS = {}
-
-
-def _side_streams(device, n):
-    key = (torch.device(device).index, n)
-    if key not in _SIDE_STREAMS:
-        _SIDE_STREAMS[key] = [torch.cuda.Stream(device=device) for _ in range(n)]
-    return _SIDE_STREAMS[key]
-
-
 def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False,
-                   sampler="sets", streams=1, offset_dev=None, scorer=None):
+                   sampler="sets", offset_dev=None, scorer=None):
     """matches [B,N,4], logits [B,N], thr [B] (normalised threshold, ransac.py:49-53).
     Returns dict(best_model [B,3,3], best_hyp [B], best_slot [B], best_score [B], mask [B,N] bool,
     ninl [B], idx [B,K,5], models [B,K,10,3,3], nsol [B,K] (, scores [B,K*10] in compact order,
@@ -51,26 +41,8 @@ def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     scorer: "stream" (default; persistent work-queue kernel: lowest latency for one call, and it keeps every SM
     busy when there are few models) or "block" (one CTA per 32 models: its CTAs retire one by one, which lets
     the kernels of an independent call on another stream move in -- what pipelined callers want, see
-    E5TestService).
-
-    streams > 1 splits the pairs into that many sub-batches issued on separate CUDA streams: the
-    5-point kernel is latency-bound (one thread per hypothesis, ~7 warps per SM), so its idle issue
-    slots are filled by the scoring kernel of the other sub-batch."""
+    E5TestService)."""
     B = matches.shape[0]
-    if streams > 1 and B >= 2 * streams and noise is None and not want_scores:
-        main = torch.cuda.current_stream()
-        ready = torch.cuda.Event()
-        ready.record(main)
-        parts = []
-        bounds = [(B * c // streams, B * (c + 1) // streams) for c in range(streams)]
-        for c, st in enumerate(_side_streams(matches.device, streams)):
-            b0, b1 = bounds[c]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                parts.append(ransac_e5_test(matches[b0:b1], logits[b0:b1], K, thr[b0:b1], tau, None, seed,
-                                            int(offset) + (c << 32), False, sampler, 1))
-            main.wait_stream(st)
-        return {k: torch.cat([p[k] for p in parts]) for k in parts[0]}
     idx = _draw(logits, K, 5, tau, noise, seed, offset, sampler, offset_dev)
     best0, cc0 = ops.zeroed_counters(B, matches.device)
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True, ccount=cc0)
