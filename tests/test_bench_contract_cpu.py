@@ -1,0 +1,47 @@
+"""bench.py contract checks that need no GPU: the reference arm prints exactly one JSON line on stdout with the
+keys the driver reads, on the same workload / metric / unit as the CUDA arm, and the CUDA arm refuses to run
+without a device (no CPU fallback)."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def _run(*args):
+    return subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), *args], capture_output=True, text=True,
+                          cwd=ROOT, timeout=600)
+
+
+def test_reference_arm_prints_one_json_line():
+    p = _run("--impl", "reference", "--steps", "1", "--warmup", "0")
+    assert p.returncode == 0, p.stderr[-2000:]
+    lines = [l for l in p.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "hypotheses_per_sec" and d["unit"] == "hypotheses/s"
+    assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0
+    assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    sys.path.insert(0, ROOT)
+    import bench
+
+    assert d["config"]["workload"] == bench.WORKLOAD_NAME
+
+
+def test_reference_arm_other_ranks_print_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2",
+                        "--steps", "1", "--warmup", "0"], capture_output=True, text=True, cwd=ROOT, env=env,
+                       timeout=120)
+    assert p.returncode == 0 and p.stdout.strip() == ""
+
+
+def test_cuda_arm_needs_a_device():
+    import torch
+
+    if torch.cuda.is_available():
+        return
+    p = _run("--steps", "1", "--warmup", "0")
+    assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
