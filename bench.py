@@ -35,6 +35,7 @@ WORKLOAD = dict(B=32, K=1000, N=2000, sample_size=5, slots=10, threshold_px=0.75
 ALGO_BYTES_PER_HYP = 442.0
 WORKLOAD_NAME = ("cfg2: Essential 5PC (Nister), 32 pairs x 1000 hyps x 2000 corrs per GPU, fwd only, "
                  "test-mode semantics (sample -> solve -> MSAC -> arg-max + winner mask)")
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # non-tensor FP32 FMA peak of a B200 at its 1965 MHz boost: 74.4
 REF_BUDGET_S = 150.0      # the reference arm sizes its per-step sample so that the whole run stays below this
 ALGO_FLOP_PER_HYP = 0.82e6
 
@@ -472,9 +473,11 @@ def run_ours(args):
                       peak_source=peak_src, models_scored=n_valid,
                       note="FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops",
                       fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,
+                      fp32_peak_tflops=FP32_PEAK_TFLOPS,
+                      fp32_frac=flops_score / (score_ms / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
                       step_algorithmic_gbs=ALGO_BYTES_PER_HYP * B * K / (ms_per_step / 1e3) / 1e9, **shares),
     )
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
         line["cpu_baseline"] = cpu_reference_throughput()
         line["accuracy"] = auc_parity(dev)
     if dist is not None:
