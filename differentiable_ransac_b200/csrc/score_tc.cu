@@ -1,0 +1,435 @@
+// Soft-MSAC scoring on the 5th-generation tensor cores (EXPERIMENTAL, opt-in: ops.score_msac(kernel="tc")).
+//
+// Replaces the same reference lines as score.cu / score_stream.cu -- scorings/msac_score.py:12-55 (Sampson
+// residuals of all N correspondences against all M models, soft inlier score) and the arg-max of
+// ransac.py:114 -- with the same C-ABI contract (drb_score_msac_tc in include/drb.h).
+//
+// Why: the FP32 kernels spend ~20 FMA-pipe instructions per (model, correspondence) and sit at ~62 % of the
+// FP32 peak.  Twelve of those instructions evaluate two polynomials in the
+// correspondence's coordinates whose coefficients depend only on the model -- r = x2' M x1 and the Sampson
+// denominator j -- i.e. a contraction over 15 monomials (msac_tc_layout.cuh).  Here that contraction runs on
+// tcgen05 (3xTF32 split, fp32 accumulation in tensor memory) and the CUDA cores keep only the epilogue
+// r^2 / j -> clamp -> sum: 3 packed + 2 scalar FMA-pipe instructions and 2 reciprocals per two pairs.
+//
+// Two launches:
+//   msac_tc_features_kernel   one thread per correspondence: the 48-float operand row (monomials, hi/lo TF32
+//                             words), written straight in the shared-memory image of its 128-row tile, so the
+//                             scorer fetches a tile with ONE 24 KB bulk copy (no tensor map)
+//   score_msac_tc_kernel      persistent, one CTA per SM, 12 warps:
+//       warp 0      producer: cp.async.bulk of the correspondence tiles into a 4-stage ring
+//       warp 1      allocates the 512 TMEM columns; one lane issues 6 x tcgen05.mma (128 x 256 x 8, tf32) per
+//                   tile into one of two 256-column accumulators and commits to the mbarriers
+//       warps 2-3   build the model operand (coefficient rows, hi/lo words) of the NEXT unit in the second B
+//                   buffer while the current unit is being scored
+//       warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns, r^2 * rcp(j), FFMA.SAT, per-thread sums over
+//                   the unit's tiles, then a butterfly reduce-scatter over the 32 lanes and a fixed-order sum
+//                   of the four lane quarters (the scores do not depend on the schedule)
+//   A unit = (pair, 128 consecutive models); units are dealt round-robin to the CTAs.
+//
+// Status: compiles for sm_100a, operand images / column mapping / descriptors checked on the host
+// (tests/test_host_math.py::test_msac_tc_*); NOT yet run on a GPU (written after the round's GPU budget was
+// spent) -- hence opt-in, with its GPU parity test gated by DRB_EXPERIMENTAL=1.
+#include <cuda_runtime.h>
+
+#include "../../include/drb.h"
+#include "drb_common.cuh"
+#include "f32x2.cuh"
+#include "msac_tc_layout.cuh"
+#include "sampson.cuh"
+#include "tile_pipe.cuh"
+
+namespace drb {
+namespace tc {
+
+constexpr int kStagesA = 4;
+constexpr int kWarps = 12;
+constexpr int kThreads = kWarps * 32;
+constexpr int kWarpProducer = 0;
+constexpr int kWarpMma = 1;
+constexpr int kWarpBuild0 = 2;       // warps 2, 3
+constexpr int kBuildThreads = 64;
+constexpr int kWarpEpi0 = 4;         // warps 4 .. 11
+constexpr int kEpiThreads = 256;
+constexpr int kTmemCols = 512;       // two accumulators of kTileN columns
+constexpr int kMaxPairs = 1024;
+
+// dynamic shared memory carve-up (bytes)
+constexpr int kOffA = 0;
+constexpr int kOffB = kOffA + kStagesA * kABytes;            //  98304
+constexpr int kOffBars = kOffB + 2 * kBBytes;                // 196608
+constexpr int kNumBars = 2 * kStagesA + 2 + 2 + 2 + 2;        // a_full/a_empty, d_full, d_empty, b_full, b_empty
+constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+constexpr int kOffPrefix = kOffTmemPtr + 16;
+constexpr int kOffPart = kOffPrefix + (kMaxPairs + 1) * 4 + 12;
+constexpr int kSmemBytes = kOffPart + 2 * 2 * 4 * 64 * 4;    // part[parity][half][quarter][64]
+static_assert(kOffPart % 16 == 0, "alignment");
+static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+
+// ---- tcgen05 wrappers (PTX as in cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp, tmem_allocator_sm100.hpp) ---
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// D[tmem] (+)= A[smem] * B[smem]',  one thread issues
+__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ring position: stage index + phase bit
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1u;
+        }
+    }
+};
+
+// unit u -> (pair, model tile): prefix[b] = number of model tiles of the pairs before b
+__device__ __forceinline__ void unit_of(const int* prefix, int B, int u, int& b, int& mt) {
+    int lo = 0, hi = B;   // largest b with prefix[b] <= u
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (prefix[mid] <= u) lo = mid; else hi = mid;
+    }
+    b = lo;
+    mt = u - prefix[lo];
+}
+
+// ---- launch 1: correspondences -> operand images ------------------------------------------------------
+// images[b][t] = the kABytes image of correspondences [128 t, 128 t + 128) of pair b; rows past N are zero
+// (the scorer's epilogue masks them).
+__global__ void __launch_bounds__(kTileM)
+msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, float* __restrict__ images) {
+    const int b = blockIdx.y, t = blockIdx.x, row = threadIdx.x;
+    const int n = t * kTileM + row;
+    float row48[kK];
+    if (n < N) {
+        const float4 p = __ldg(reinterpret_cast<const float4*>(matches) + (size_t)b * N + n);
+        float f[kFeat];
+        features(p.x, p.y, p.z, p.w, f);
+        operand_row(f, true, row48);
+    } else {
+        DRB_UNROLL
+        for (int k = 0; k < kK; ++k) row48[k] = 0.f;
+    }
+    float* img = images + ((size_t)b * tiles + t) * (kABytes / 4);
+    DRB_UNROLL
+    for (int c = 0; c < kK / 4; ++c)
+        *reinterpret_cast<float4*>(img + image_index(row, 4 * c)) =
+            make_float4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
+}
+
+// ---- launch 2 -----------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1)
+score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__ models,
+                     const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
+                     int B, int M, int N, int tiles, float* __restrict__ scores,
+                     unsigned long long* __restrict__ best_packed) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = bars + kStagesA;
+    uint64_t* d_full = bars + 2 * kStagesA;
+    uint64_t* d_empty = d_full + 2;
+    uint64_t* b_full = d_empty + 2;
+    uint64_t* b_empty = b_full + 2;
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
+    int* prefix = reinterpret_cast<int*>(smem + kOffPrefix);
+    float* part = reinterpret_cast<float*>(smem + kOffPart);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    // ---- one-time setup ---------------------------------------------------------------------------------
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStagesA; ++i) {
+            mbar_init(&a_full[i], 1);     // the producer's arrive.expect_tx
+            mbar_init(&a_empty[i], 1);    // tcgen05.commit
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&d_full[i], 1);                  // tcgen05.commit
+            mbar_init(&d_empty[i], kEpiThreads / 32);  // one arrival per epilogue warp
+            mbar_init(&b_full[i], kBuildThreads / 32); // one arrival per builder warp
+            mbar_init(&b_empty[i], 1);                 // tcgen05.commit
+        }
+        fence_barrier_init();
+        fence_proxy_async();
+    }
+    if (warp == kWarpEpi0) {
+        // model tiles per pair, exclusive prefix over the pairs (one warp, 32 pairs per round)
+        int carry = 0;
+        for (int base = 0; base < B; base += 32) {
+            const int b = base + lane;
+            int v = 0;
+            if (b < B) {
+                const int cnt = count ? min(__ldg(count + b), M) : M;
+                v = (max(cnt, 0) + kTileModels - 1) / kTileModels;
+            }
+            int inc = v;
+            DRB_UNROLL
+            for (int o = 1; o < 32; o <<= 1) {
+                const int up = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += up;
+            }
+            if (b < B) prefix[b] = carry + inc - v;
+            carry += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) prefix[B] = carry;
+    }
+    if (warp == kWarpMma) tmem_alloc(tmem_ptr, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+    const int n_units = prefix[B];
+
+    if (warp == kWarpProducer) {
+        // ===== producer: correspondence tiles of every unit of this CTA, in unit order =====
+        if (lane == 0) {
+            Ring ra;
+#pragma unroll 1
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                int b, mt;
+                unit_of(prefix, B, u, b, mt);
+                const float* src = images + (size_t)b * tiles * (kABytes / 4);
+#pragma unroll 1
+                for (int t = 0; t < tiles; ++t) {
+                    mbar_wait(&a_empty[ra.idx], ra.phase ^ 1u);
+                    mbar_expect_tx(&a_full[ra.idx], kABytes);
+                    bulk_g2s(smem + kOffA + ra.idx * kABytes, src + (size_t)t * (kABytes / 4), kABytes, &a_full[ra.idx]);
+                    ra.advance(kStagesA);
+                }
+            }
+        }
+    } else if (warp == kWarpMma) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc();
+            Ring ra, rd, rb;
+#pragma unroll 1
+            for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+                mbar_wait(&b_full[rb.idx], rb.phase);
+                const uint64_t bdesc = smem_desc(smem_u32(smem + kOffB + rb.idx * kBBytes));
+#pragma unroll 1
+                for (int t = 0; t < tiles; ++t) {
+                    mbar_wait(&d_empty[rd.idx], rd.phase ^ 1u);
+                    mbar_wait(&a_full[ra.idx], ra.phase);
+                    tc_fence_after();
+                    const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
+                    const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN);
+                    DRB_UNROLL
+                    for (int k = 0; k < kKSteps; ++k)
+                        mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
+                    mma_commit(&a_empty[ra.idx]);   // the stage may be refilled once these MMAs have read it
+                    mma_commit(&d_full[rd.idx]);    // the accumulator is complete
+                    ra.advance(kStagesA);
+                    rd.advance(2);
+                }
+                mma_commit(&b_empty[rb.idx]);       // the model operand may be rebuilt
+                rb.advance(2);
+            }
+        }
+    } else if (warp < kWarpEpi0) {
+        // ===== builders: the model operand of every unit, one buffer ahead of the MMAs =====
+        const int bt = threadIdx.x - kWarpBuild0 * 32;   // 0 .. 63
+        Ring rb;
+#pragma unroll 1
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+            int b, mt;
+            unit_of(prefix, B, u, b, mt);
+            const int cnt = count ? min(__ldg(count + b), M) : M;
+            mbar_wait(&b_empty[rb.idx], rb.phase ^ 1u);
+            float* img = reinterpret_cast<float*>(smem + kOffB + rb.idx * kBBytes);
+            DRB_UNROLL
+            for (int rep = 0; rep < kTileModels / kBuildThreads; ++rep) {
+                const int i = bt + rep * kBuildThreads;   // model of the tile
+                const int mi = mt * kTileModels + i;
+                float m[9];
+                DRB_UNROLL
+                for (int q = 0; q < 9; ++q) m[q] = mi < cnt ? __ldg(models + ((size_t)b * M + mi) * 9 + q) : 0.f;
+                float cr[kFeat], cj[kFeat], row48[kK];
+                coefficients(m, cr, cj);
+                operand_row(cr, false, row48);
+                DRB_UNROLL
+                for (int c = 0; c < kK / 4; ++c)
+                    *reinterpret_cast<float4*>(img + image_index(column_r(i), 4 * c)) =
+                        make_float4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
+                operand_row(cj, false, row48);
+                DRB_UNROLL
+                for (int c = 0; c < kK / 4; ++c)
+                    *reinterpret_cast<float4*>(img + image_index(column_j(i), 4 * c)) =
+                        make_float4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
+            }
+            fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&b_full[rb.idx]);
+            rb.advance(2);
+        }
+    } else {
+        // ===== epilogue =====
+        const int et = threadIdx.x - kWarpEpi0 * 32;   // 0 .. 255
+        const int quarter = warp & 3;                  // the TMEM lanes this warp may read: 32 quarter .. + 31
+        const int half = (warp - kWarpEpi0) >> 2;      // columns 128 half .. + 127 of the accumulator
+        Ring rd;
+        int parity = 0;
+#pragma unroll 1
+        for (int u = blockIdx.x; u < n_units; u += gridDim.x, parity ^= 1) {
+            int b, mt;
+            unit_of(prefix, B, u, b, mt);
+            const int cnt = count ? min(__ldg(count + b), M) : M;
+            const float th = 1.5f * __ldg(thr + b);
+            const float nci = -1.f / (th * th);
+            pk2 acc[32];
+            DRB_UNROLL
+            for (int i = 0; i < 32; ++i) acc[i] = pk2_splat(0.f);
+#pragma unroll 1
+            for (int t = 0; t < tiles; ++t) {
+                mbar_wait(&d_full[rd.idx], rd.phase);
+                __syncwarp();          // tcgen05.ld is .sync.aligned: the warp must be converged
+                tc_fence_after();
+                // a row past N contributes 0: max(0, min(1, u * nci + 0)) with u * nci <= 0 (or NaN -> 0)
+                const float one = (t * kTileM + quarter * 32 + lane < N) ? 1.f : 0.f;
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(rd.idx * kTileN + half * 128);
+                DRB_UNROLL
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                    tmem_ld_wait();
+                    DRB_UNROLL
+                    for (int q = 0; q < 8; ++q) {
+                        const pk2 R = pk2_make(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
+                        const pk2 R2 = pk2_mul(R, R);
+                        const pk2 IJ = pk2_make(rcp_approx(__uint_as_float(v[4 * q + 2])), rcp_approx(__uint_as_float(v[4 * q + 3])));
+                        float u0, u1;
+                        pk2_split(pk2_mul(R2, IJ), u0, u1);
+                        acc[c * 8 + q] = pk2_add(acc[c * 8 + q], pk2_make(fma_sat(u0, nci, one), fma_sat(u1, nci, one)));
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
+                rd.advance(2);
+            }
+            // ---- sum over the 128 lanes: butterfly reduce-scatter inside the warp, then the four quarters -----
+            float a[64];
+            DRB_UNROLL
+            for (int i = 0; i < 32; ++i) pk2_split(acc[i], a[2 * i], a[2 * i + 1]);
+            DRB_UNROLL
+            for (int w = 32, o = 16; o > 0; w >>= 1, o >>= 1) {
+                const bool up = (lane & o) != 0;
+                DRB_UNROLL
+                for (int i = 0; i < w; ++i) {
+                    const float keep = up ? a[w + i] : a[i];
+                    const float send = up ? a[i] : a[w + i];
+                    a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+                }
+            }
+            // this lane now owns models 2 lane, 2 lane + 1 of its half (lane quarter `quarter`)
+            float* pp = part + (size_t)parity * (2 * 4 * 64);
+            pp[(half * 4 + quarter) * 64 + 2 * lane] = a[0];
+            pp[(half * 4 + quarter) * 64 + 2 * lane + 1] = a[1];
+            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            if (et < kTileModels) {
+                const int h = et >> 6, j = et & 63;
+                const float score = ((pp[(h * 4 + 0) * 64 + j] + pp[(h * 4 + 1) * 64 + j]) + pp[(h * 4 + 2) * 64 + j]) +
+                                    pp[(h * 4 + 3) * 64 + j];
+                const int mi = mt * kTileModels + et;
+                const bool live = mi < cnt;
+                if (live && scores) scores[(size_t)b * M + mi] = score;
+                unsigned long long key = live ? pack_best(score, ids ? __ldg(ids + (size_t)b * M + mi) : mi) : 0ull;
+                DRB_UNROLL
+                for (int o = 16; o > 0; o >>= 1) {
+                    const unsigned long long other = __shfl_xor_sync(0xffffffffu, key, o);
+                    key = other > key ? other : key;
+                }
+                if (lane == 0 && key) atomicMax(best_packed + b, key);
+            }
+            // `part` alternates between two halves by unit parity: the barrier of the next unit orders these
+            // reads before the writes of the unit after it
+        }
+    }
+
+    // ---- teardown ---------------------------------------------------------------------------------------
+    tc_fence_before();
+    __syncthreads();
+    if (warp == kWarpMma) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kTmemCols);
+    }
+}
+
+static int tc_sm_count() {
+    static const int sms = []() {
+        int dev = 0, n = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        return n > 0 ? n : 148;
+    }();
+    return sms;
+}
+
+}  // namespace tc
+}  // namespace drb
+
+using namespace drb;
+
+extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
+    if (B <= 0 || N <= 0) return 0;
+    return (size_t)B * ((N + tc::kTileM - 1) / tc::kTileM) * tc::kABytes;
+}
+
+extern "C" int drb_score_msac_tc(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
+                                 const float* thr, int B, int M, int N, float* scores,
+                                 unsigned long long* best_packed, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+    if (!matches || !models || !thr || !best_packed || !workspace) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || B > tc::kMaxPairs || M <= 0 || N <= 0) return DRB_ERR_BAD_SHAPE;
+    if (workspace_bytes < drb_score_msac_tc_workspace_bytes(B, N) || (reinterpret_cast<uintptr_t>(workspace) & 127) ||
+        (reinterpret_cast<uintptr_t>(matches) & 15))
+        return DRB_ERR_BAD_SHAPE;
+    static const cudaError_t attr = cudaFuncSetAttribute(tc::score_msac_tc_kernel,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
+    if (attr != cudaSuccess) return DRB_ERR_CUDA;
+    const int tiles = (N + tc::kTileM - 1) / tc::kTileM;
+    float* images = reinterpret_cast<float*>(workspace);
+    cudaStream_t s = (cudaStream_t)stream;
+    tc::msac_tc_features_kernel<<<dim3(tiles, B), tc::kTileM, 0, s>>>(matches, N, tiles, images);
+    const long long max_units = (long long)B * ((M + tc::kTileModels - 1) / tc::kTileModels);
+    const int grid = (int)(max_units < tc::tc_sm_count() ? max_units : tc::tc_sm_count());
+    tc::score_msac_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles,
+                                                                       scores, best_packed);
+    return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
+}

@@ -327,7 +327,8 @@ _MSAC_KERNEL = os.environ.get("DRB_MSAC_KERNEL", "stream")
 def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None, kernel=None):
     """matches [B,N,4], models [B,M,9|3,3], thr [B] -> scores [B,M] | None, best_packed [B] (int64 view of u64).
     `best` may be a caller-zeroed [B] int64 buffer.  kernel="stream": the evenly split persistent grid
-    (drb_score_msac_stream); "block": one CTA per (pair, 32 models) (drb_score_msac)."""
+    (drb_score_msac_stream); "block": one CTA per (pair, 32 models) (drb_score_msac); "tc": the experimental
+    tensor-core scorer (drb_score_msac_tc), never chosen by default."""
     kernel = kernel or _MSAC_KERNEL
     matches = _f32(matches)
     B, N, _ = matches.shape
@@ -347,6 +348,12 @@ def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, bes
     elif kernel == "block":
         check(lib.drb_score_msac(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N, _p(scores), _p(best),
                                  _stream()), "drb_score_msac")
+    elif kernel == "tc":
+        # experimental tensor-core scorer (csrc/score_tc.cu): opt-in only, see DESIGN.md section 10
+        nbytes = int(lib.drb_score_msac_tc_workspace_bytes(B, N))
+        ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=matches.device)
+        check(lib.drb_score_msac_tc(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N, _p(scores),
+                                    _p(best), _p(ws), ws.numel() * 8, _stream()), "drb_score_msac_tc")
     else:
         raise _lib.DrbError(f"unknown MSAC kernel {kernel!r}")
     return scores, best

@@ -13,6 +13,7 @@
 #include "rigid_math.cuh"
 #include "refit_math.cuh"
 #include "pose_math.cuh"
+#include "msac_tc_layout.cuh"
 
 namespace {
 template <class T>
@@ -217,6 +218,120 @@ int hc_pose_loss(const double* E, const float* matches, int N, double dist, cons
     err[1] = et.v;
     for (int i = 0; i < 9; ++i) grad[i] = 0.5 * (er.d[i] + et.d[i]);
     return best;
+}
+
+// ---- tensor-core scorer (score_tc.cu): the operand images, descriptors and column mapping on the host ----
+// A software model of what the kernel asks the hardware to do: the operands are read back from the images
+// THROUGH THE DESCRIPTOR FIELDS (start address, leading / stride byte offsets of the canonical K-major
+// no-swizzle layout, M and N of the instruction descriptor), eight K values per MMA step, TF32 inputs (low 13
+// bits ignored), fp32 accumulation; the epilogue follows the kernel's thread mapping (lane quarter, column
+// half, four 32-column loads of eight model pairs).  Exact division stands in for rcp.approx.
+uint64_t hc_tc_smem_desc(uint32_t addr) { return drb::tc::smem_desc(addr); }
+uint32_t hc_tc_instr_desc(void) { return drb::tc::instr_desc(); }
+int hc_tc_abytes(void) { return drb::tc::kABytes; }
+int hc_tc_bbytes(void) { return drb::tc::kBBytes; }
+
+static float tf32_trunc(float x) {
+    uint32_t u;
+    std::memcpy(&u, &x, 4);
+    u &= 0xffffe000u;
+    std::memcpy(&x, &u, 4);
+    return x;
+}
+
+// element (row, kk) of MMA K step `step` of the operand whose image starts at smem byte address `base`
+static float desc_fetch(const std::vector<float>& smem, uint64_t desc, int row, int kk) {
+    const uint32_t start = (uint32_t)(desc & 0x3fff) << 4;
+    const uint32_t lbo = (uint32_t)((desc >> 16) & 0x3fff) << 4;
+    const uint32_t sbo = (uint32_t)((desc >> 32) & 0x3fff) << 4;
+    const uint32_t addr = start + (row >> 3) * sbo + (kk >> 2) * lbo + (row & 7) * 16 + (kk & 3) * 4;
+    return smem[addr / 4];
+}
+
+int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, float thr, float* scores,
+                      int* lossless) {
+    using namespace drb::tc;
+    const uint32_t idesc = instr_desc();
+    const int mmaN = (int)((idesc >> 17) & 0x3f) << 3, mmaM = (int)((idesc >> 24) & 0x1f) << 4;
+    if (mmaN != kTileN || mmaM != kTileM) return -1;
+    if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2) return -2;   // F32 <- TF32 x TF32
+    if (((idesc >> 15) & 3) != 0) return -3;                                                         // both K-major
+    const uint32_t a_addr = 0x400, b_addr = 0x400 + kABytes;      // a made-up shared-memory carve-up
+    std::vector<float> smem((b_addr + kBBytes) / 4, 0.f);
+    const int tiles = (N + kTileM - 1) / kTileM;
+    const float th = 1.5f * thr, nci = -1.f / (th * th);
+    *lossless = 1;
+    for (int m0 = 0; m0 < M; m0 += kTileModels) {
+        // the builder warps
+        for (int i = 0; i < kTileModels; ++i) {
+            float m[9], cr[kFeat], cj[kFeat], row48[kK];
+            for (int q = 0; q < 9; ++q) m[q] = (m0 + i < M) ? models[(size_t)(m0 + i) * 9 + q] : 0.f;
+            coefficients(m, cr, cj);
+            operand_row(cr, false, row48);
+            for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_r(i), k)] = row48[k];
+            operand_row(cj, false, row48);
+            for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_j(i), k)] = row48[k];
+        }
+        std::vector<double> total(kTileModels, 0.0);
+        std::vector<float> lane_sum((size_t)kTileM * kTileModels, 0.f);   // per epilogue thread (lane, model)
+        for (int t = 0; t < tiles; ++t) {
+            // msac_tc_features_kernel
+            for (int row = 0; row < kTileM; ++row) {
+                const int n = t * kTileM + row;
+                float row48[kK];
+                if (n < N) {
+                    float f[kFeat];
+                    features(matches[n * 4], matches[n * 4 + 1], matches[n * 4 + 2], matches[n * 4 + 3], f);
+                    operand_row(f, true, row48);
+                } else {
+                    for (int k = 0; k < kK; ++k) row48[k] = 0.f;
+                }
+                for (int k = 0; k < kK; ++k) smem[a_addr / 4 + image_index(row, k)] = row48[k];
+            }
+            // the MMA warp: six K steps through the descriptors
+            std::vector<float> D((size_t)kTileM * kTileN, 0.f);
+            const uint64_t adesc = smem_desc(a_addr), bdesc = smem_desc(b_addr);
+            for (int s = 0; s < kKSteps; ++s) {
+                const uint64_t ad = smem_desc_kstep(adesc, s), bd = smem_desc_kstep(bdesc, s);
+                for (int r = 0; r < kTileM; ++r)
+                    for (int c = 0; c < kTileN; ++c) {
+                        float acc = s ? D[(size_t)r * kTileN + c] : 0.f;
+                        for (int kk = 0; kk < kMmaK; ++kk) {
+                            const float a = desc_fetch(smem, ad, r, kk), b = desc_fetch(smem, bd, c, kk);
+                            if (a != a || b != b) { acc = a * b; continue; }
+                            if (tf32_trunc(a) != a || tf32_trunc(b) != b) *lossless = 0;
+                            acc += tf32_trunc(a) * tf32_trunc(b);
+                        }
+                        D[(size_t)r * kTileN + c] = acc;
+                    }
+            }
+            // the epilogue warps
+            for (int quarter = 0; quarter < 4; ++quarter)
+                for (int half = 0; half < 2; ++half)
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int row = quarter * 32 + lane;
+                        const float one = (t * kTileM + row < N) ? 1.f : 0.f;
+                        for (int c = 0; c < 4; ++c)
+                            for (int q = 0; q < 8; ++q)
+                                for (int h = 0; h < 2; ++h) {
+                                    const int col = half * 128 + c * 32 + 4 * q;
+                                    const float r = D[(size_t)row * kTileN + col + h];
+                                    const float j = D[(size_t)row * kTileN + col + 2 + h];
+                                    const float u = (r * r) * (1.f / j);
+                                    float v = u * nci + one;
+                                    v = (v != v) ? 0.f : (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));   // FFMA.SAT
+                                    const int model = half * 64 + 2 * (c * 8 + q) + h;
+                                    lane_sum[(size_t)row * kTileModels + model] += v;
+                                }
+                    }
+        }
+        for (int i = 0; i < kTileModels; ++i) {
+            float q4[4] = {0.f, 0.f, 0.f, 0.f};
+            for (int row = 0; row < kTileM; ++row) q4[row >> 5] += lane_sum[(size_t)row * kTileModels + i];
+            if (m0 + i < M) scores[m0 + i] = ((q4[0] + q4[1]) + q4[2]) + q4[3];
+        }
+    }
+    return 0;
 }
 
 int hc_roots_f32(const float* coef, float* roots) { return drb::real_roots_deg10<float>(coef, roots); }

@@ -2,6 +2,7 @@
 tests/hostcheck -- the same templates the CUDA kernels instantiate -- against the oracle and
 the reference-generated golden fixtures.  No GPU needed; test infrastructure only."""
 import ctypes
+import os
 
 import numpy as np
 import pytest
@@ -235,3 +236,107 @@ def test_pose_loss_value_and_gradient_against_reference_autograd(lib, golden):
             assert abs(grad - want).max() < 1e-7 * abs(want).max()
             total += err.mean()
         assert abs(total / M - float(g[f"loss_{i}"])) < 1e-9
+
+
+# ---- tensor-core scorer (csrc/score_tc.cu, experimental): operand images, descriptors, column mapping ----
+def _tc_scores(lib, matches, models, thr):
+    m = np.ascontiguousarray(matches.numpy().astype(np.float32))
+    md = np.ascontiguousarray(models.reshape(-1, 9).numpy().astype(np.float32))
+    out = np.full(md.shape[0], -1.0, dtype=np.float32)
+    lossless = ctypes.c_int(0)
+    rc = lib.hc_msac_tc_scores(vp(m), m.shape[0], vp(md), md.shape[0], ctypes.c_float(thr), vp(out),
+                               ctypes.byref(lossless))
+    assert rc == 0, rc
+    assert lossless.value == 1          # every operand word is an exact TF32: the hardware's truncation is a no-op
+    return torch.from_numpy(out)
+
+
+@pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (128, 20)])
+def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K):
+    """The 3xTF32 contraction over 15 monomials, built and decoded exactly as score_tc.cu does it (images ->
+    descriptors -> 128 x 256 x 8 MMA steps -> epilogue thread mapping), gives the soft-MSAC scores of
+    msac_score.py:12-55 within the path's 1e-4 relative bar (ragged tails of points and of models included)."""
+    from differentiable_ransac_b200 import synth
+    from oracle import scoring
+
+    matches, _, _ = synth.relative_pose_batch(1, N, seed=77, noise=5e-4)
+    matches = matches[0]
+    g = torch.Generator().manual_seed(N)
+    idx = torch.stack([torch.randperm(N, generator=g)[:5] for _ in range(K)])
+    inl = torch.arange(N - int(0.3 * N), N)
+    idx[: K // 3] = inl[torch.stack([torch.randperm(len(inl), generator=g)[:5] for _ in range(K // 3)])]
+    E = nister.five_point(matches[idx].double())
+    E = E[trace_constraint_residual(E) < 1e-8].float()
+    assert E.shape[0] > 128 or N < 2000   # more than one model tile at the headline size
+    thr = 0.75 / 800.0
+    want, _ = scoring.msac_score(matches.double(), E.double(), thr)
+    got = _tc_scores(lib, matches, E, thr)
+    rel = (got.double() - want).abs() / want.clamp_min(1.0)
+    assert rel.max() < 1e-4, rel.max()
+    assert int(got.argmax()) == int(want.argmax())
+    fp32, _ = scoring.msac_score(matches, E, thr)
+    assert (got - fp32).abs().max() / fp32.max() < 1e-4
+
+
+def test_msac_tc_nan_models_score_zero(lib):
+    from differentiable_ransac_b200 import synth
+
+    matches, E_gt, _ = synth.relative_pose_batch(1, 300, seed=5)
+    models = torch.stack([E_gt[0], torch.full((3, 3), float("nan")), E_gt[0] / E_gt[0].norm()])
+    got = _tc_scores(lib, matches[0], models, 0.75 / 800.0)
+    assert got[1] == 0.0 and got[0] > 10 and abs(float(got[0] - got[2])) < 1e-3 * float(got[0])
+
+
+def test_msac_tc_descriptors_match_the_cutlass_bitfields(lib, tmp_path):
+    """smem / instruction descriptor words against cute::UMMA::SmemDescriptor / InstrDescriptor compiled on the
+    host from the CUTLASS headers vendored in the image (skipped when they are absent)."""
+    import glob
+    import subprocess
+    import sysconfig
+
+    cands = glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "*", "data", "cutlass", "include")) + \
+        glob.glob(os.path.join(sysconfig.get_paths()["purelib"], "*", "3rdparty", "cutlass", "include"))
+    cands = [c for c in cands if os.path.exists(os.path.join(c, "cute", "arch", "mma_sm100_desc.hpp"))]
+    if not cands or not os.path.isdir("/usr/local/cuda/include"):
+        pytest.skip("no CUTLASS headers in this image")
+    src = tmp_path / "desc_ref.cpp"
+    src.write_text(r'''
+#include <cstdint>
+#include <cute/arch/mma_sm100_desc.hpp>
+extern "C" uint64_t ref_smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    cute::UMMA::SmemDescriptor d;
+    d.desc_ = 0;
+    d.version_ = 1;
+    d.lbo_mode_ = 0;
+    d.layout_type_ = uint8_t(cute::UMMA::LayoutType::SWIZZLE_NONE);
+    d.start_address_ = uint16_t(addr >> 4);
+    d.base_offset_ = 0;
+    d.stride_byte_offset_ = sbo_bytes >> 4;
+    d.leading_byte_offset_ = lbo_bytes >> 4;
+    return d.desc_;
+}
+extern "C" uint32_t ref_instr_desc_tf32(int M, int N) {
+    cute::UMMA::InstrDescriptor d;
+    d.desc_ = 0;
+    d.a_format_ = uint8_t(cute::UMMA::F16F32Format::TF32);
+    d.b_format_ = uint8_t(cute::UMMA::F16F32Format::TF32);
+    d.c_format_ = uint8_t(cute::UMMA::CFormat::F32);
+    d.m_dim_ = M >> 4;
+    d.n_dim_ = N >> 3;
+    d.a_major_ = uint8_t(cute::UMMA::Major::K);
+    d.b_major_ = uint8_t(cute::UMMA::Major::K);
+    return d.desc_;
+}
+''')
+    so = tmp_path / "desc_ref.so"
+    subprocess.check_call(["g++", "-std=c++17", "-shared", "-fPIC", "-I", cands[0], "-I", "/usr/local/cuda/include",
+                           str(src), "-o", str(so)])
+    ref = ctypes.CDLL(str(so))
+    ref.ref_smem_desc.restype = ctypes.c_uint64
+    ref.ref_instr_desc_tf32.restype = ctypes.c_uint32
+    lib.hc_tc_smem_desc.restype = ctypes.c_uint64
+    lib.hc_tc_instr_desc.restype = ctypes.c_uint32
+    for addr in (0x0, 0x400, 0x18000, 0x2fc00):
+        assert lib.hc_tc_smem_desc(addr) == ref.ref_smem_desc(addr, 128, 1536)
+    assert lib.hc_tc_instr_desc() == ref.ref_instr_desc_tf32(128, 256)
+    assert lib.hc_tc_abytes() == 16 * 1536 and lib.hc_tc_bbytes() == 32 * 1536
