@@ -362,7 +362,8 @@ def run_ours(args):
     for i in range(args.steps):
         flush.fill_(float(i))
         ev[i][0].record()
-        out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i)
+        out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i,
+                                    scorer=dsvc.scorer if str(dsvc.scorer).startswith("tc") else None)
         ev[i][1].record()
     barrier()
     ms_serial = sorted(a.elapsed_time(b) for a, b in ev)[args.steps // 2]      # median
@@ -412,8 +413,10 @@ def run_ours(args):
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
     n_valid = int(cc.sum().item())
     reps = 10
-    msac_kernel = "block" if S > 1 else "stream"      # the kernel the timed steps above ran
-    msac_name = {"block": "score_msac_kernel", "stream": "score_msac_stream_kernel"}[msac_kernel]
+    msac_kernel = dsvc.scorer or ops._MSAC_KERNEL     # the kernel the timed steps above ran
+    msac_name = {"block": "score_msac_kernel", "stream": "score_msac_stream_kernel"}.get(msac_kernel,
+                                                                                           "score_msac_tc_kernel")
+    launches_per_step = 5 if msac_name == "score_msac_tc_kernel" else 4   # tc: operand images + scorer
     for _ in range(3):
         ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True, kernel=msac_kernel)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -433,6 +436,10 @@ def run_ours(args):
                                                            kernel=msac_kernel)),
                      ("score_msac_stream", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
                                                                   want_scores=False, kernel="stream")),
+                     ("score_msac_block", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
+                                                                 want_scores=False, kernel="block")),
+                     ("score_msac_tc", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
+                                                              want_scores=False, kernel="tc")),
                      ):
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         fn()
@@ -460,18 +467,22 @@ def run_ours(args):
                        "serial_ms_per_step and the roofline pass: L2 flushed by a 256 MB write before each launch; "
                        "e2e re-copies its inputs from the host every step",
                     value_streams=S, value_graph=bool(args.value_graph), serial_ms_per_step=ms_serial,
+                    scorer=msac_name,
                     e2e_mode=f"engine.E5TestService(graph={bool(args.e2e_graph)}), {args.e2e_slots} batches in flight "
                              "(one stream each; a CUDA graph per slot when graph=True): packed H2D per step, one packed D2H of (model, id, score, #inliers) "
                              "per step, results read on the host before a slot is reused",
                     parallelism=f"pairs sharded over {world} GPU(s)"),
         clocks=clock_info,
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
-        gpu_launches=4 * args.steps,
+        gpu_launches=launches_per_step * args.steps,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                       traffic=load_traffic(msac_name),
                       kernel=msac_name, kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,
-                      note="FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops",
+                      note=("FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops" if launches_per_step == 4 else
+                            "not HBM bound: the contraction runs on tcgen05 (3 BF16 words per operand), the epilogue is "
+                            "SFU-bound; fp32_tflops counts the 37 flop per (model, correspondence) of the FP32 formula "
+                            "as useful work, so it can exceed the FP32 pipe's peak (DESIGN.md section 10)"),
                       fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,
                       fp32_peak_tflops=FP32_PEAK_TFLOPS,
                       fp32_frac=flops_score / (score_ms / 1e3) / 1e12 / FP32_PEAK_TFLOPS,

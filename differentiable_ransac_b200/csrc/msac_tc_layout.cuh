@@ -157,5 +157,95 @@ DRB_HD void operand_row(const float* v, bool a_side, float* row48) {
     }
 }
 
+// ---- BF16 variant (6 partial products) ----------------------------------------------------------------
+// A TF32 word carries 11 significant bits, so hi + lo keeps 22 of the 24 bits of an fp32 and the scores sit
+// ~4x further from fp64 than the fp32 formula (measured: 1.4e-4 relative at worst over the 1.4e5 models of
+// cfg2).  Three BF16 words w0 + w1 + w2 (8 bits each) represent an fp32 EXACTLY, and the six partial products
+// of order <= 2 leave 2^-23: fp32-level scores for the same MMA time, because a BF16 MMA step covers K = 16
+// in the cycles a TF32 step covers K = 8.  K = 96 = 6 blocks of 16 BF16 = the same 192 bytes per row:
+//
+//   A = [ w0 | w0 | w0 | w1 | w1 | w2 ],   B = [ w0 | w1 | w2 | w0 | w1 | w0 ]
+//
+// A 32-bit word of the row holds two consecutive K elements (the lower one in the low half), so word w of a
+// row sits at image_index(row, w) in both variants; only the words, the instruction descriptor and the MMA
+// kind differ.
+constexpr int kK16 = 6 * kBlk;                 // 96
+
+DRB_HD uint16_t bf16_rn(float x) {
+#if defined(__CUDA_ARCH__)
+    uint16_t h;
+    asm("cvt.rn.bf16.f32 %0, %1;" : "=h"(h) : "f"(x));
+    return h;
+#else
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7f800000u) == 0x7f800000u) return (uint16_t)((u >> 16) | ((u & 0xffffu) ? 0x40u : 0u));   // Inf / NaN
+    u += 0x7fffu + ((u >> 16) & 1u);           // round to nearest even
+    return (uint16_t)(u >> 16);
+#endif
+}
+DRB_HD float bf16_value(uint16_t h) {
+    const uint32_t u = (uint32_t)h << 16;
+    float f;
+#if defined(__CUDA_ARCH__)
+    f = __uint_as_float(u);
+#else
+    memcpy(&f, &u, 4);
+#endif
+    return f;
+}
+DRB_HD void bf16_split3(float x, uint16_t* w) {
+    w[0] = bf16_rn(x);
+    const float r1 = x - bf16_value(w[0]);     // exact
+    w[1] = bf16_rn(r1);
+    const float r2 = r1 - bf16_value(w[1]);    // exact
+    w[2] = bf16_rn(r2);
+}
+// the 48 32-bit words of one operand row (v = 15 values)
+DRB_HD void operand_row_bf16(const float* v, bool a_side, uint32_t* row48w) {
+    uint16_t e[kK16];
+    DRB_UNROLL
+    for (int i = 0; i < kBlk; ++i) {
+        uint16_t w[3] = {0, 0, 0};
+        if (i < kFeat) bf16_split3(v[i], w);
+        // block order of the word index: A (0,0,0,1,1,2), B (0,1,2,0,1,0)
+        e[0 * kBlk + i] = w[0];
+        e[1 * kBlk + i] = a_side ? w[0] : w[1];
+        e[2 * kBlk + i] = a_side ? w[0] : w[2];
+        e[3 * kBlk + i] = a_side ? w[1] : w[0];
+        e[4 * kBlk + i] = w[1];
+        e[5 * kBlk + i] = a_side ? w[2] : w[0];
+    }
+    DRB_UNROLL
+    for (int w = 0; w < kK; ++w) row48w[w] = (uint32_t)e[2 * w] | ((uint32_t)e[2 * w + 1] << 16);
+}
+// Instruction descriptor of kind::f16 with BF16 operands, fp32 accumulate, K-major A and B
+DRB_HD uint32_t instr_desc_bf16() {
+    uint32_t d = 0;
+    d |= 1u << 4;                              // D format: F32
+    d |= 1u << 7;                              // A format: BF16
+    d |= 1u << 10;                             // B format: BF16
+    d |= (uint32_t)(kTileN >> 3) << 17;
+    d |= (uint32_t)(kTileM >> 4) << 24;
+    return d;
+}
+// TF32 variant as 32-bit words, so both variants share the image writers
+DRB_HD void operand_row_words(const float* v, bool a_side, bool bf16, uint32_t* row48w) {
+    if (bf16) {
+        operand_row_bf16(v, a_side, row48w);
+    } else {
+        float row48[kK];
+        operand_row(v, a_side, row48);
+        DRB_UNROLL
+        for (int k = 0; k < kK; ++k) {
+#if defined(__CUDA_ARCH__)
+            row48w[k] = __float_as_uint(row48[k]);
+#else
+            memcpy(&row48w[k], &row48[k], 4);
+#endif
+        }
+    }
+}
+
 }  // namespace tc
 }  // namespace drb

@@ -87,6 +87,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread has completed
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -132,30 +142,32 @@ __device__ __forceinline__ void unit_of(const int* prefix, int B, int u, int& b,
 // ---- launch 1: correspondences -> operand images ------------------------------------------------------
 // images[b][t] = the kABytes image of correspondences [128 t, 128 t + 128) of pair b; rows past N are zero
 // (the scorer's epilogue masks them).
+template <bool BF16>
 __global__ void __launch_bounds__(kTileM)
-msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, float* __restrict__ images) {
+msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, uint32_t* __restrict__ images) {
     const int b = blockIdx.y, t = blockIdx.x, row = threadIdx.x;
     const int n = t * kTileM + row;
-    float row48[kK];
+    uint32_t row48[kK];
     if (n < N) {
         const float4 p = __ldg(reinterpret_cast<const float4*>(matches) + (size_t)b * N + n);
         float f[kFeat];
         features(p.x, p.y, p.z, p.w, f);
-        operand_row(f, true, row48);
+        operand_row_words(f, true, BF16, row48);
     } else {
         DRB_UNROLL
-        for (int k = 0; k < kK; ++k) row48[k] = 0.f;
+        for (int k = 0; k < kK; ++k) row48[k] = 0u;
     }
-    float* img = images + ((size_t)b * tiles + t) * (kABytes / 4);
+    uint32_t* img = images + ((size_t)b * tiles + t) * (kABytes / 4);
     DRB_UNROLL
     for (int c = 0; c < kK / 4; ++c)
-        *reinterpret_cast<float4*>(img + image_index(row, 4 * c)) =
-            make_float4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
+        *reinterpret_cast<uint4*>(img + image_index(row, 4 * c)) =
+            make_uint4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
 }
 
 // ---- launch 2 -----------------------------------------------------------------------------------------
+template <bool BF16>
 __global__ void __launch_bounds__(kThreads, 1)
-score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__ models,
+score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restrict__ models,
                      const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
                      int B, int M, int N, int tiles, float* __restrict__ scores,
                      unsigned long long* __restrict__ best_packed) {
@@ -224,7 +236,7 @@ score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
                 int b, mt;
                 unit_of(prefix, B, u, b, mt);
-                const float* src = images + (size_t)b * tiles * (kABytes / 4);
+                const uint32_t* src = images + (size_t)b * tiles * (kABytes / 4);
 #pragma unroll 1
                 for (int t = 0; t < tiles; ++t) {
                     mbar_wait(&a_empty[ra.idx], ra.phase ^ 1u);
@@ -237,7 +249,7 @@ score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__
     } else if (warp == kWarpMma) {
         // ===== MMA issuer =====
         if (lane == 0) {
-            const uint32_t idesc = instr_desc();
+            const uint32_t idesc = BF16 ? instr_desc_bf16() : instr_desc();
             Ring ra, rd, rb;
 #pragma unroll 1
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
@@ -251,8 +263,10 @@ score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__
                     const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
                     const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN);
                     DRB_UNROLL
-                    for (int k = 0; k < kKSteps; ++k)
-                        mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < kKSteps; ++k) {
+                        if (BF16) mma_bf16(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
+                        else mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
+                    }
                     mma_commit(&a_empty[ra.idx]);   // the stage may be refilled once these MMAs have read it
                     mma_commit(&d_full[rd.idx]);    // the accumulator is complete
                     ra.advance(kStagesA);
@@ -272,7 +286,7 @@ score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__
             unit_of(prefix, B, u, b, mt);
             const int cnt = count ? min(__ldg(count + b), M) : M;
             mbar_wait(&b_empty[rb.idx], rb.phase ^ 1u);
-            float* img = reinterpret_cast<float*>(smem + kOffB + rb.idx * kBBytes);
+            uint32_t* img = reinterpret_cast<uint32_t*>(smem + kOffB + rb.idx * kBBytes);
             DRB_UNROLL
             for (int rep = 0; rep < kTileModels / kBuildThreads; ++rep) {
                 const int i = bt + rep * kBuildThreads;   // model of the tile
@@ -280,18 +294,19 @@ score_msac_tc_kernel(const float* __restrict__ images, const float* __restrict__
                 float m[9];
                 DRB_UNROLL
                 for (int q = 0; q < 9; ++q) m[q] = mi < cnt ? __ldg(models + ((size_t)b * M + mi) * 9 + q) : 0.f;
-                float cr[kFeat], cj[kFeat], row48[kK];
+                float cr[kFeat], cj[kFeat];
+                uint32_t row48[kK];
                 coefficients(m, cr, cj);
-                operand_row(cr, false, row48);
+                operand_row_words(cr, false, BF16, row48);
                 DRB_UNROLL
                 for (int c = 0; c < kK / 4; ++c)
-                    *reinterpret_cast<float4*>(img + image_index(column_r(i), 4 * c)) =
-                        make_float4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
-                operand_row(cj, false, row48);
+                    *reinterpret_cast<uint4*>(img + image_index(column_r(i), 4 * c)) =
+                        make_uint4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
+                operand_row_words(cj, false, BF16, row48);
                 DRB_UNROLL
                 for (int c = 0; c < kK / 4; ++c)
-                    *reinterpret_cast<float4*>(img + image_index(column_j(i), 4 * c)) =
-                        make_float4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
+                    *reinterpret_cast<uint4*>(img + image_index(column_j(i), 4 * c)) =
+                        make_uint4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
             }
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
             __syncwarp();
@@ -411,8 +426,27 @@ extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
     return (size_t)B * ((N + tc::kTileM - 1) / tc::kTileM) * tc::kABytes;
 }
 
+namespace drb {
+namespace tc {
+template <bool BF16>
+static int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr,
+                  int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
+    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc_kernel<BF16>,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
+    if (attr != cudaSuccess) return DRB_ERR_CUDA;
+    const int tiles = (N + kTileM - 1) / kTileM;
+    msac_tc_features_kernel<BF16><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
+    const long long max_units = (long long)B * ((M + kTileModels - 1) / kTileModels);
+    const int grid = (int)(max_units < tc_sm_count() ? max_units : tc_sm_count());
+    score_msac_tc_kernel<BF16><<<grid, kThreads, kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
+                                                                  best_packed);
+    return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
+}
+}  // namespace tc
+}  // namespace drb
+
 extern "C" int drb_score_msac_tc(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
-                                 const float* thr, int B, int M, int N, float* scores,
+                                 const float* thr, int B, int M, int N, int words, float* scores,
                                  unsigned long long* best_packed, void* workspace, size_t workspace_bytes,
                                  void* stream) {
     if (!matches || !models || !thr || !best_packed || !workspace) return DRB_ERR_NULL_POINTER;
@@ -420,16 +454,9 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     if (workspace_bytes < drb_score_msac_tc_workspace_bytes(B, N) || (reinterpret_cast<uintptr_t>(workspace) & 127) ||
         (reinterpret_cast<uintptr_t>(matches) & 15))
         return DRB_ERR_BAD_SHAPE;
-    static const cudaError_t attr = cudaFuncSetAttribute(tc::score_msac_tc_kernel,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes);
-    if (attr != cudaSuccess) return DRB_ERR_CUDA;
-    const int tiles = (N + tc::kTileM - 1) / tc::kTileM;
-    float* images = reinterpret_cast<float*>(workspace);
+    if (words != 2 && words != 3) return DRB_ERR_UNSUPPORTED;
+    uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
-    tc::msac_tc_features_kernel<<<dim3(tiles, B), tc::kTileM, 0, s>>>(matches, N, tiles, images);
-    const long long max_units = (long long)B * ((M + tc::kTileModels - 1) / tc::kTileModels);
-    const int grid = (int)(max_units < tc::tc_sm_count() ? max_units : tc::tc_sm_count());
-    tc::score_msac_tc_kernel<<<grid, tc::kThreads, tc::kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles,
-                                                                       scores, best_packed);
-    return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
+    return words == 3 ? tc::launch<true>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s)
+                      : tc::launch<false>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
 }

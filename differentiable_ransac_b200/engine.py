@@ -13,7 +13,14 @@ from __future__ import annotations
 
 import torch
 
+import os
+
 from . import ops
+
+# Scorer of the pipelined service (E5TestService with more than one slot): "block" (FP32, one CTA per 32 models:
+# its CTAs retire one by one, so the next batch's kernels move in under its tail), "stream" (FP32 work queue) or
+# "tc" (tensor cores, csrc/score_tc.cu).
+SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "block")
 
 
 def _noise_args(noise, seed, offset):
@@ -316,8 +323,10 @@ class E5TestService:
     the FMA-bound scoring kernel of batch i leaves idle (measured on B200, cfg2: 0.309 -> 0.256 ms per batch
     with two slots, profiles/r1_notes.md)."""
 
-    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False, host_io=True):
+    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False, host_io=True, scorer=None):
         self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
+        # one slot: whatever a single call uses (ops default); several: SERVICE_SCORER unless the caller says
+        self.scorer = scorer if scorer is not None else (SERVICE_SCORER if int(slots) > 1 else None)
         self.graph = bool(graph)
         # host_io=False: batches are already on the device -- submit(slot, packed=<device tensor>) copies the
         # packed batch into the slot (device to device) and results stay on the device (`dev_out[slot]`)
@@ -350,7 +359,7 @@ class E5TestService:
         buf = self.dev_in[slot]
         o = ransac_e5_test(buf[: B * N * 4].view(B, N, 4), buf[B * N * 4: B * N * 5].view(B, N), self.K,
                            buf[B * N * 5:], seed=self.seed, offset=offset, offset_dev=offset_dev,
-                           scorer="block" if self.slots > 1 else None)
+                           scorer=self.scorer)
         return o, torch.cat((o["best_model"].flatten(), o["best_id"].float(), o["best_score"], o["ninl"].float()))
 
     def _capture(self, slot):

@@ -157,13 +157,15 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
  * contraction on the tensor cores (score_tc.cu).  r = x2' M x1 and the Sampson denominator are two polynomials
  * in the correspondence's coordinates, i.e. inner products of 15 monomials with per-model coefficients; a
  * (128 correspondences x 128 models) tile is one 128 x 256 x 48 tcgen05 MMA (3xTF32 split operands, fp32
- * accumulation in tensor memory) and the CUDA cores keep r^2 / j -> clamp -> sum.  Scores agree with
- * drb_score_msac to ~5e-5 relative (22-bit operand words).  B <= 1024; matches 16-byte aligned.  Needs a
+ * accumulation in tensor memory) and the CUDA cores keep r^2 / j -> clamp -> sum.  words = 2: operands split
+ * into two TF32 words, three partial products (22-bit operands: scores within ~1.4e-4 relative of
+ * drb_score_msac); words = 3: three BF16 words, six partial products (exact operands: fp32-level scores) for
+ * the same MMA time.  B <= 1024; matches 16-byte aligned.  Needs a
  * 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents irrelevant on entry:
  * the call writes the operand images of the correspondences there first).                         */
 size_t drb_score_msac_tc_workspace_bytes(int B, int N);
 int drb_score_msac_tc(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
-                      const float* thr, int B, int M, int N,
+                      const float* thr, int B, int M, int N, int words,
                       float* scores, unsigned long long* best_packed, void* workspace,
                       size_t workspace_bytes, void* stream);
 /* Decode best_packed and produce the winner's model, score, id and inlier mask

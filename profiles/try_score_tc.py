@@ -1,6 +1,6 @@
-"""First contact of the experimental tensor-core scorer with hardware: three parity cases of growing size against
-the FP32 block kernel, then the cfg2 timing.  Every line is flushed (and appended to gpurun_out/tc_try.jsonl) so a
-hang shows how far it got.  Run under `timeout`."""
+"""Hardware check of the tensor-core scorer (csrc/score_tc.cu), both operand splits: parity cases of growing size
+(ragged counts, empty pairs, more pairs than a warp) against the FP32 block kernel, then the cfg2 timing.  Every
+line is flushed (and appended to gpurun_out/tc_try.jsonl) so a hang shows how far it got.  Run under `timeout`."""
 import json
 import os
 import sys
@@ -22,25 +22,36 @@ def say(**kw):
     os.fsync(LOG.fileno())
 
 
+def ids_of(best):
+    return [(0xFFFFFFFF - (int(k) & 0xFFFFFFFF)) if int(k) else -1 for k in best.cpu()]
+
+
 from differentiable_ransac_b200 import ops, synth  # noqa: E402
 
 dev = "cuda"
-say(stage="start", t=time.time())
-for (B, M, N) in ((1, 5, 3), (2, 33, 64), (3, 300, 2500)):
-    matches, _, _ = synth.relative_pose_batch(B, max(N, 8), seed=5 + N)
-    matches = matches[:, :N].contiguous().to(dev)
-    gen = torch.Generator().manual_seed(M)
-    models = torch.randn(B, M, 3, 3, generator=gen)
-    models = (models / models.flatten(-2).norm(dim=-1)[..., None, None]).to(dev)
-    thr = (torch.rand(B, generator=gen) * 0.05 + 0.002).to(dev)
-    s_ref, b_ref = ops.score_msac(matches, models, thr, kernel="block")
-    torch.cuda.synchronize()
-    say(stage="launch tc", case=[B, M, N])
-    s_tc, b_tc = ops.score_msac(matches, models, thr, kernel="tc")
-    torch.cuda.synchronize()
-    rel = (s_tc - s_ref).abs() / s_ref.clamp_min(1.0)
-    say(stage="done", case=[B, M, N], max_rel=float(rel.max()), same_best=bool((b_tc == b_ref).all()),
-        tc_head=[float(x) for x in s_tc.flatten()[:4]], ref_head=[float(x) for x in s_ref.flatten()[:4]])
+KERNELS = sys.argv[1].split(",") if len(sys.argv) > 1 else ["tc_tf32", "tc_bf16"]
+say(stage="start", t=time.time(), kernels=KERNELS)
+CASES = [(1, 5, 3, None), (2, 33, 64, None), (3, 70, 257, [70, 0, 41]), (3, 300, 2500, [300, 0, 129]),
+         (4, 1000, 2000, [1000, 517, 1, 32]), (40, 200, 500, None)]
+for kern in KERNELS:
+    for (B, M, N, counts) in CASES:
+        matches, _, _ = synth.relative_pose_batch(B, max(N, 8), seed=5 + N)
+        matches = matches[:, :N].contiguous().to(dev)
+        gen = torch.Generator().manual_seed(M)
+        models = torch.randn(B, M, 3, 3, generator=gen)
+        models = (models / models.flatten(-2).norm(dim=-1)[..., None, None]).to(dev)
+        thr = (torch.rand(B, generator=gen) * 0.05 + 0.002).to(dev)
+        count = None if counts is None else torch.tensor(counts, dtype=torch.int32, device=dev)
+        ids = torch.stack([torch.randperm(4 * M + 7, generator=gen)[:M] for _ in range(B)]).int().to(dev)
+        s_ref, b_ref = ops.score_msac(matches, models, thr, count=count, ids=ids, kernel="block")
+        torch.cuda.synchronize()
+        s_tc, b_tc = ops.score_msac(matches, models, thr, count=count, ids=ids, kernel=kern)
+        s_2, b_2 = ops.score_msac(matches, models, thr, count=count, ids=ids, kernel=kern)
+        torch.cuda.synchronize()
+        live = torch.arange(M, device=dev)[None] < (count[:, None] if count is not None else M)
+        rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
+        say(stage="parity", kernel=kern, case=[B, M, N, counts], max_rel=float(rel.max()),
+            same_ids=ids_of(b_tc) == ids_of(b_ref), deterministic=bool(torch.equal(s_tc[live], s_2[live]) and torch.equal(b_tc, b_2)))
 
 import bench  # noqa: E402
 
@@ -50,15 +61,15 @@ m, lg, thr = matches_h.to(dev), logits_h.to(dev), thr_h.to(dev)
 idx = ops.sample_sets(lg, K, 5, seed=7, offset=0)
 models, nsol, cm, cid, cc = ops.solve_e5(m, idx, compact=True)
 s_ref, b_ref = ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=True, kernel="block")
-torch.cuda.synchronize()
-say(stage="launch tc", case="cfg2")
-s_tc, b_tc = ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=True, kernel="tc")
-torch.cuda.synchronize()
 live = torch.arange(cm.shape[1], device=dev)[None] < cc[:, None]
-rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
-say(stage="done", case="cfg2", max_rel=float(rel.max()), same_best=int((b_tc == b_ref).sum()), pairs=B)
+for kern in KERNELS:
+    s_tc, b_tc = ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=True, kernel=kern)
+    torch.cuda.synchronize()
+    rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
+    say(stage="parity", kernel=kern, case="cfg2", max_rel=float(rel.max()), mean_rel=float(rel.mean()),
+        same_ids=sum(int(a == b) for a, b in zip(ids_of(b_tc), ids_of(b_ref))), pairs=B)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
-for kern in ("block", "stream", "tc"):
+for kern in ["block", "stream"] + KERNELS:
     for _ in range(3):
         ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=False, kernel=kern)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]

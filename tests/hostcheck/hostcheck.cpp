@@ -239,52 +239,61 @@ static float tf32_trunc(float x) {
     return x;
 }
 
-// element (row, kk) of MMA K step `step` of the operand whose image starts at smem byte address `base`
-static float desc_fetch(const std::vector<float>& smem, uint64_t desc, int row, int kk) {
+// element (row, kk) of one MMA K step of the operand described by `desc`: 32-bit containers (tf32, 8 per step)
+// or 16-bit ones (bf16, 16 per step); either way a 16-byte chunk per row and two chunks per step
+static float desc_fetch(const std::vector<uint32_t>& smem, uint64_t desc, int row, int kk, bool bf16) {
     const uint32_t start = (uint32_t)(desc & 0x3fff) << 4;
     const uint32_t lbo = (uint32_t)((desc >> 16) & 0x3fff) << 4;
     const uint32_t sbo = (uint32_t)((desc >> 32) & 0x3fff) << 4;
-    const uint32_t addr = start + (row >> 3) * sbo + (kk >> 2) * lbo + (row & 7) * 16 + (kk & 3) * 4;
-    return smem[addr / 4];
+    const int per_chunk = bf16 ? 8 : 4, bytes = bf16 ? 2 : 4;
+    const uint32_t addr = start + (row >> 3) * sbo + (kk / per_chunk) * lbo + (row & 7) * 16 + (kk % per_chunk) * bytes;
+    const uint32_t w = smem[addr / 4];
+    if (bf16) return drb::tc::bf16_value((uint16_t)((addr & 2) ? (w >> 16) : (w & 0xffffu)));
+    float f;
+    std::memcpy(&f, &w, 4);
+    return f;
 }
 
-int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, float thr, float* scores,
+int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, float thr, int words, float* scores,
                       int* lossless) {
     using namespace drb::tc;
-    const uint32_t idesc = instr_desc();
+    const bool bf16 = words == 3;
+    const uint32_t idesc = bf16 ? instr_desc_bf16() : instr_desc();
     const int mmaN = (int)((idesc >> 17) & 0x3f) << 3, mmaM = (int)((idesc >> 24) & 0x1f) << 4;
     if (mmaN != kTileN || mmaM != kTileM) return -1;
-    if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != 2 || ((idesc >> 10) & 7) != 2) return -2;   // F32 <- TF32 x TF32
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != fmt || ((idesc >> 10) & 7) != fmt) return -2;
     if (((idesc >> 15) & 3) != 0) return -3;                                                         // both K-major
+    const int step_k = bf16 ? 16 : 8;
     const uint32_t a_addr = 0x400, b_addr = 0x400 + kABytes;      // a made-up shared-memory carve-up
-    std::vector<float> smem((b_addr + kBBytes) / 4, 0.f);
+    std::vector<uint32_t> smem((b_addr + kBBytes) / 4, 0u);
     const int tiles = (N + kTileM - 1) / kTileM;
     const float th = 1.5f * thr, nci = -1.f / (th * th);
     *lossless = 1;
     for (int m0 = 0; m0 < M; m0 += kTileModels) {
         // the builder warps
         for (int i = 0; i < kTileModels; ++i) {
-            float m[9], cr[kFeat], cj[kFeat], row48[kK];
+            float m[9], cr[kFeat], cj[kFeat];
+            uint32_t row48[kK];
             for (int q = 0; q < 9; ++q) m[q] = (m0 + i < M) ? models[(size_t)(m0 + i) * 9 + q] : 0.f;
             coefficients(m, cr, cj);
-            operand_row(cr, false, row48);
+            operand_row_words(cr, false, bf16, row48);
             for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_r(i), k)] = row48[k];
-            operand_row(cj, false, row48);
+            operand_row_words(cj, false, bf16, row48);
             for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_j(i), k)] = row48[k];
         }
-        std::vector<double> total(kTileModels, 0.0);
         std::vector<float> lane_sum((size_t)kTileM * kTileModels, 0.f);   // per epilogue thread (lane, model)
         for (int t = 0; t < tiles; ++t) {
             // msac_tc_features_kernel
             for (int row = 0; row < kTileM; ++row) {
                 const int n = t * kTileM + row;
-                float row48[kK];
+                uint32_t row48[kK];
                 if (n < N) {
                     float f[kFeat];
                     features(matches[n * 4], matches[n * 4 + 1], matches[n * 4 + 2], matches[n * 4 + 3], f);
-                    operand_row(f, true, row48);
+                    operand_row_words(f, true, bf16, row48);
                 } else {
-                    for (int k = 0; k < kK; ++k) row48[k] = 0.f;
+                    for (int k = 0; k < kK; ++k) row48[k] = 0u;
                 }
                 for (int k = 0; k < kK; ++k) smem[a_addr / 4 + image_index(row, k)] = row48[k];
             }
@@ -296,11 +305,11 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
                 for (int r = 0; r < kTileM; ++r)
                     for (int c = 0; c < kTileN; ++c) {
                         float acc = s ? D[(size_t)r * kTileN + c] : 0.f;
-                        for (int kk = 0; kk < kMmaK; ++kk) {
-                            const float a = desc_fetch(smem, ad, r, kk), b = desc_fetch(smem, bd, c, kk);
+                        for (int kk = 0; kk < step_k; ++kk) {
+                            const float a = desc_fetch(smem, ad, r, kk, bf16), b = desc_fetch(smem, bd, c, kk, bf16);
                             if (a != a || b != b) { acc = a * b; continue; }
-                            if (tf32_trunc(a) != a || tf32_trunc(b) != b) *lossless = 0;
-                            acc += tf32_trunc(a) * tf32_trunc(b);
+                            if (!bf16 && (tf32_trunc(a) != a || tf32_trunc(b) != b)) *lossless = 0;
+                            acc += a * b;
                         }
                         D[(size_t)r * kTileN + c] = acc;
                     }
@@ -332,6 +341,13 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
         }
     }
     return 0;
+}
+uint32_t hc_tc_instr_desc_bf16(void) { return drb::tc::instr_desc_bf16(); }
+// w0 + w1 + w2 of the BF16 split (exactness check)
+double hc_tc_bf16_sum(float x) {
+    uint16_t w[3];
+    drb::tc::bf16_split3(x, w);
+    return (double)drb::tc::bf16_value(w[0]) + (double)drb::tc::bf16_value(w[1]) + (double)drb::tc::bf16_value(w[2]);
 }
 
 int hc_roots_f32(const float* coef, float* roots) { return drb::real_roots_deg10<float>(coef, roots); }

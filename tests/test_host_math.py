@@ -239,20 +239,21 @@ def test_pose_loss_value_and_gradient_against_reference_autograd(lib, golden):
 
 
 # ---- tensor-core scorer (csrc/score_tc.cu, experimental): operand images, descriptors, column mapping ----
-def _tc_scores(lib, matches, models, thr):
+def _tc_scores(lib, matches, models, thr, words=2):
     m = np.ascontiguousarray(matches.numpy().astype(np.float32))
     md = np.ascontiguousarray(models.reshape(-1, 9).numpy().astype(np.float32))
     out = np.full(md.shape[0], -1.0, dtype=np.float32)
     lossless = ctypes.c_int(0)
-    rc = lib.hc_msac_tc_scores(vp(m), m.shape[0], vp(md), md.shape[0], ctypes.c_float(thr), vp(out),
+    rc = lib.hc_msac_tc_scores(vp(m), m.shape[0], vp(md), md.shape[0], ctypes.c_float(thr), words, vp(out),
                                ctypes.byref(lossless))
     assert rc == 0, rc
     assert lossless.value == 1          # every operand word is an exact TF32: the hardware's truncation is a no-op
     return torch.from_numpy(out)
 
 
+@pytest.mark.parametrize("words", [2, 3])
 @pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (128, 20)])
-def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K):
+def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K, words):
     """The 3xTF32 contraction over 15 monomials, built and decoded exactly as score_tc.cu does it (images ->
     descriptors -> 128 x 256 x 8 MMA steps -> epilogue thread mapping), gives the soft-MSAC scores of
     msac_score.py:12-55 within the path's 1e-4 relative bar (ragged tails of points and of models included)."""
@@ -270,20 +271,21 @@ def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K):
     assert E.shape[0] > 128 or N < 2000   # more than one model tile at the headline size
     thr = 0.75 / 800.0
     want, _ = scoring.msac_score(matches.double(), E.double(), thr)
-    got = _tc_scores(lib, matches, E, thr)
+    got = _tc_scores(lib, matches, E, thr, words)
     rel = (got.double() - want).abs() / want.clamp_min(1.0)
-    assert rel.max() < 1e-4, rel.max()
+    assert rel.max() < (1e-4 if words == 2 else 3e-5), rel.max()
     assert int(got.argmax()) == int(want.argmax())
     fp32, _ = scoring.msac_score(matches, E, thr)
     assert (got - fp32).abs().max() / fp32.max() < 1e-4
 
 
-def test_msac_tc_nan_models_score_zero(lib):
+@pytest.mark.parametrize("words", [2, 3])
+def test_msac_tc_nan_models_score_zero(lib, words):
     from differentiable_ransac_b200 import synth
 
     matches, E_gt, _ = synth.relative_pose_batch(1, 300, seed=5)
     models = torch.stack([E_gt[0], torch.full((3, 3), float("nan")), E_gt[0] / E_gt[0].norm()])
-    got = _tc_scores(lib, matches[0], models, 0.75 / 800.0)
+    got = _tc_scores(lib, matches[0], models, 0.75 / 800.0, words)
     assert got[1] == 0.0 and got[0] > 10 and abs(float(got[0] - got[2])) < 1e-3 * float(got[0])
 
 
@@ -327,6 +329,18 @@ extern "C" uint32_t ref_instr_desc_tf32(int M, int N) {
     d.b_major_ = uint8_t(cute::UMMA::Major::K);
     return d.desc_;
 }
+extern "C" uint32_t ref_instr_desc_bf16(int M, int N) {
+    cute::UMMA::InstrDescriptor d;
+    d.desc_ = 0;
+    d.a_format_ = uint8_t(cute::UMMA::F16F32Format::BF16);
+    d.b_format_ = uint8_t(cute::UMMA::F16F32Format::BF16);
+    d.c_format_ = uint8_t(cute::UMMA::CFormat::F32);
+    d.m_dim_ = M >> 4;
+    d.n_dim_ = N >> 3;
+    d.a_major_ = uint8_t(cute::UMMA::Major::K);
+    d.b_major_ = uint8_t(cute::UMMA::Major::K);
+    return d.desc_;
+}
 ''')
     so = tmp_path / "desc_ref.so"
     subprocess.check_call(["g++", "-std=c++17", "-shared", "-fPIC", "-I", cands[0], "-I", "/usr/local/cuda/include",
@@ -339,4 +353,17 @@ extern "C" uint32_t ref_instr_desc_tf32(int M, int N) {
     for addr in (0x0, 0x400, 0x18000, 0x2fc00):
         assert lib.hc_tc_smem_desc(addr) == ref.ref_smem_desc(addr, 128, 1536)
     assert lib.hc_tc_instr_desc() == ref.ref_instr_desc_tf32(128, 256)
+    lib.hc_tc_instr_desc_bf16.restype = ctypes.c_uint32
+    ref.ref_instr_desc_bf16.restype = ctypes.c_uint32
+    assert lib.hc_tc_instr_desc_bf16() == ref.ref_instr_desc_bf16(128, 256)
     assert lib.hc_tc_abytes() == 16 * 1536 and lib.hc_tc_bbytes() == 32 * 1536
+
+
+def test_msac_tc_bf16_split_is_exact(lib):
+    """Three BF16 words represent every fp32 exactly (the premise of the six-product variant)."""
+    lib.hc_tc_bf16_sum.restype = ctypes.c_double
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([rng.standard_normal(2000).astype(np.float32) * np.float32(10.0) ** rng.integers(-6, 4, 2000),
+                         np.array([0.0, 1.0, -1.0, 1 / 3, 0.1, 1e-3, 123456.789], dtype=np.float32)])
+    for x in xs.astype(np.float32):
+        assert lib.hc_tc_bf16_sum(ctypes.c_float(float(x))) == float(x)
