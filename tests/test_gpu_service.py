@@ -40,7 +40,7 @@ def test_service_matches_direct_call(slots, graph):
     assert len(got) == len(batches)
     for j, (matches, logits, thr) in enumerate(batches):
         want = engine.ransac_e5_test(matches.to(DEV), logits.to(DEV), K, thr.to(DEV), seed=11, offset=j,
-                                     scorer="block" if slots > 1 else None)   # the kernel the service picks
+                                     scorer=svc.scorer)   # the kernel the service picks
         torch.cuda.synchronize()
         assert torch.equal(got[j]["best_id"], want["best_id"].cpu())
         assert torch.equal(got[j]["best_score"], want["best_score"].cpu())
@@ -63,7 +63,7 @@ def test_device_resident_service_matches_direct_call(graph):
     for j, (m, lg, thr) in enumerate(batches):
         slot = svc.submit(packed=torch.cat((m.flatten(), lg.flatten(), thr)))
         got = {k: v.clone() for k, v in svc.result(slot).items()}
-        want = engine.ransac_e5_test(m, lg, K, thr, seed=5, offset=j, scorer="block")
+        want = engine.ransac_e5_test(m, lg, K, thr, seed=5, offset=j, scorer=svc.scorer)
         torch.cuda.synchronize()
         assert torch.equal(got["best_id"], want["best_id"])
         assert torch.equal(got["best_score"], want["best_score"])
