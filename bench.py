@@ -173,7 +173,7 @@ def cpu_reference_throughput(max_seconds=12.0, max_pairs=8, K=None, N=None):
                        f"host has {cores} cores)")
 
 
-def auc_parity(dev, pairs=12, N=1000, K=192):
+def auc_parity(dev, pairs=12, N=1000, K=192, scorer=None):
     """AUC@5/10/20 of the poses recovered from the winning E, CUDA path vs the CPU oracle of the reference,
     same synthetic pairs and the same injected Gumbel noise (bounded sample: ~5 s of CPU work)."""
     from differentiable_ransac_b200 import engine, synth
@@ -186,7 +186,7 @@ def auc_parity(dev, pairs=12, N=1000, K=192):
     logits = synth.logits_regime(pairs, N, "L0", seed=12)
     noise = synth.gumbel_noise((pairs, K, N), seed=13)
     ours = engine.ransac_e5_test(matches.to(dev), logits.to(dev), K, torch.full((pairs,), thr, device=dev),
-                                 noise=noise.to(dev), want_scores=True)
+                                 noise=noise.to(dev), want_scores=True, scorer=scorer)
     e_ours, e_ref, same = [], [], 0
     for b in range(pairs):
         _, _, _, R, t = data[b]
@@ -205,7 +205,7 @@ def auc_parity(dev, pairs=12, N=1000, K=192):
     err = cv_utils.pose_errors(ours["best_model"], matches.to(dev), R_gt, t_gt)[:, 0]
     a_dev = pose_eval.auc(err.max(dim=-1).values.cpu().tolist())
     return dict(auc5_10_20_ours=a, auc5_10_20_cpu_reference=r, auc5_10_20_ours_device_pose=a_dev,
-                same_best_hypothesis=f"{same}/{pairs}",
+                same_best_hypothesis=f"{same}/{pairs}", scorer=scorer or "default (FP32 work queue)",
                 sample=f"{pairs} synthetic pairs x {K} hyps x {N} corrs, identical injected Gumbel noise, "
                        "pose from cv2.recoverPose, AUC as cv_utils.py:528-546")
 
@@ -480,8 +480,8 @@ def run_ours(args):
                       kernel=msac_name, kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,
                       note=("FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops" if launches_per_step == 4 else
-                            "not HBM bound: the contraction runs on tcgen05 (3 BF16 words per operand), the epilogue is "
-                            "SFU-bound; fp32_tflops counts the 37 flop per (model, correspondence) of the FP32 formula "
+                            "not HBM bound: the contraction runs on tcgen05 (operands split into TF32 / BF16 words), the "
+                            "epilogue is SFU-bound (ncu: XU pipe 67 %); fp32_tflops counts the 37 flop per (model, correspondence) of the FP32 formula "
                             "as useful work, so it can exceed the FP32 pipe's peak (DESIGN.md section 10)"),
                       fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,
                       fp32_peak_tflops=FP32_PEAK_TFLOPS,
@@ -490,7 +490,7 @@ def run_ours(args):
     )
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
         line["cpu_baseline"] = cpu_reference_throughput()
-        line["accuracy"] = auc_parity(dev)
+        line["accuracy"] = auc_parity(dev, scorer=dsvc.scorer)      # through the scorer the timed steps used
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

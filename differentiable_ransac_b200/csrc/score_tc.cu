@@ -1,4 +1,5 @@
-// Soft-MSAC scoring on the 5th-generation tensor cores (EXPERIMENTAL, opt-in: ops.score_msac(kernel="tc")).
+// Soft-MSAC scoring on the 5th-generation tensor cores (ops.score_msac(kernel="tc_tf32" | "tc_bf16"); the
+// default scorer of the pipelined service, engine.SERVICE_SCORER).
 //
 // Replaces the same reference lines as score.cu / score_stream.cu -- scorings/msac_score.py:12-55 (Sampson
 // residuals of all N correspondences against all M models, soft inlier score) and the arg-max of
@@ -8,27 +9,29 @@
 // FP32 peak.  Twelve of those instructions evaluate two polynomials in the
 // correspondence's coordinates whose coefficients depend only on the model -- r = x2' M x1 and the Sampson
 // denominator j -- i.e. a contraction over 15 monomials (msac_tc_layout.cuh).  Here that contraction runs on
-// tcgen05 (3xTF32 split, fp32 accumulation in tensor memory) and the CUDA cores keep only the epilogue
-// r^2 / j -> clamp -> sum: 3 packed + 2 scalar FMA-pipe instructions and 2 reciprocals per two pairs.
+// tcgen05 (operands split into TF32 or BF16 words, fp32 accumulation in tensor memory) and the CUDA cores keep
+// only the epilogue r^2 / j -> clamp -> sum: 3 packed + 2 scalar FMA-pipe instructions and 2 reciprocals per
+// two pairs.
 //
 // Two launches:
-//   msac_tc_features_kernel   one thread per correspondence: the 48-float operand row (monomials, hi/lo TF32
+//   msac_tc_features_kernel   one thread per correspondence: the 48-word operand row (monomials split into
 //                             words), written straight in the shared-memory image of its 128-row tile, so the
 //                             scorer fetches a tile with ONE 24 KB bulk copy (no tensor map)
 //   score_msac_tc_kernel      persistent, one CTA per SM, 12 warps:
 //       warp 0      producer: cp.async.bulk of the correspondence tiles into a 4-stage ring
-//       warp 1      allocates the 512 TMEM columns; one lane issues 6 x tcgen05.mma (128 x 256 x 8, tf32) per
-//                   tile into one of two 256-column accumulators and commits to the mbarriers
-//       warps 2-3   build the model operand (coefficient rows, hi/lo words) of the NEXT unit in the second B
-//                   buffer while the current unit is being scored
+//       warp 1      allocates the 512 TMEM columns; one lane issues 6 x tcgen05.mma (128 x 256 x 8 tf32 or x 16
+//                   bf16) per tile into one of two 256-column accumulators and commits to the mbarriers
+//       warps 2-3   build the model operand (coefficient rows split into words) of the NEXT unit in the second
+//                   B buffer while the current unit is being scored
 //       warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns, r^2 * rcp(j), FFMA.SAT, per-thread sums over
 //                   the unit's tiles, then a butterfly reduce-scatter over the 32 lanes and a fixed-order sum
 //                   of the four lane quarters (the scores do not depend on the schedule)
 //   A unit = (pair, 128 consecutive models); units are dealt round-robin to the CTAs.
 //
-// Status: compiles for sm_100a, operand images / column mapping / descriptors checked on the host
-// (tests/test_host_math.py::test_msac_tc_*); NOT yet run on a GPU (written after the round's GPU budget was
-// spent) -- hence opt-in, with its GPU parity test gated by DRB_EXPERIMENTAL=1.
+// Measured on B200 (cfg2, 139 000 models x 2000 correspondences): 0.122 ms against 0.215 ms for the FP32 work
+// queue; XU pipe (the reciprocals) 67 %, tensor pipe 17 % (profiles/r1_ncu_score_msac_tc.txt, DESIGN.md
+// section 10).  Operand images / column mapping / descriptors are also checked on the host
+// (tests/test_host_math.py::test_msac_tc_*).
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"

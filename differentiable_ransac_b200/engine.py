@@ -17,10 +17,15 @@ import os
 
 from . import ops
 
-# Scorer of the pipelined service (E5TestService with more than one slot): "block" (FP32, one CTA per 32 models:
-# its CTAs retire one by one, so the next batch's kernels move in under its tail), "stream" (FP32 work queue) or
-# "tc" (tensor cores, csrc/score_tc.cu).
-SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "block")
+# Scorer of the pipelined service (E5TestService with more than one slot):
+#   "tc_tf32"  tensor cores, two TF32 words per operand (csrc/score_tc.cu) -- the default: measured on B200 at cfg2
+#              0.175 ms per pipelined batch against 0.254 ms with "block" (profiles/r1_notes.md); per-model scores
+#              within 1.4e-4 relative of the FP32 kernels (the winner's score: ~1e-6), so the winner can differ from
+#              the FP32 kernels' only between near-ties
+#   "block"    FP32, one CTA per 32 models; bit-identical to what `ransac_e5_test(scorer="block")` returns
+#   "stream"   FP32 work queue;  "tc_bf16": three BF16 words (fp32-level scores on the host model; validate with
+#              DRB_EXPERIMENTAL=1 pytest tests/test_gpu_score_tc.py before making it the default)
+SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "tc_tf32")
 
 
 def _noise_args(noise, seed, offset):

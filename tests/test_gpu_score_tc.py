@@ -1,10 +1,12 @@
-"""GPU tests of the EXPERIMENTAL tensor-core soft-MSAC scorer (drb_score_msac_tc, csrc/score_tc.cu) against the CPU
-oracle (oracle/scoring.py <- scorings/msac_score.py:12-55) and the FP32 kernel (drb_score_msac).
+"""GPU tests of the tensor-core soft-MSAC scorer (drb_score_msac_tc, csrc/score_tc.cu) against the CPU oracle
+(oracle/scoring.py <- scorings/msac_score.py:12-55) and the FP32 kernel (drb_score_msac).
 
-The kernel was written after round 1's GPU budget was spent and has never run on hardware, so these tests
-are opt-in: set DRB_EXPERIMENTAL=1.  Each case runs in a CHILD process under a timeout -- a wrong mbarrier
-phase in a warp-specialised kernel is a hang, not an exception, and must not take the test session (or the
-GPU box) with it.  Its host model is tested on the CPU in test_host_math.py::test_msac_tc_*."""
+Two tiers.  (1) The TF32 variant ("tc_tf32", the pipelined service's default) ran on a B200 at the end of round 1
+(profiles/r1_score_tc_first_contact.jsonl): its cases here are the ones measured then, with the tolerance the
+3xTF32 split allows.  (2) Everything else -- the BF16 variant beyond one small case, the oracle-level 1e-4 bar at
+the headline size -- has NOT been confirmed on hardware yet and is opt-in: DRB_EXPERIMENTAL=1, each case in a
+CHILD process under a timeout (a wrong mbarrier phase in a warp-specialised kernel is a hang, not an exception).
+The kernel's host model is tested on the CPU in test_host_math.py::test_msac_tc_*."""
 import os
 import subprocess
 import sys
@@ -17,11 +19,77 @@ ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
 
 
 @pytest.fixture(scope="module", autouse=True)
-def _need_gpu_and_opt_in():
+def _need_gpu():
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
+
+
+def _ids(best):
+    return [(0xFFFFFFFF - (int(k) & 0xFFFFFFFF)) if int(k) else -1 for k in best.cpu()]
+
+
+# ---- tier 1: the TF32 variant, cases and margins as measured on the B200 -------------------------------------
+@pytest.mark.parametrize("B,M,N,counts", [(1, 5, 3, None), (2, 33, 64, None), (3, 300, 2500, None),
+                                          (3, 70, 257, [70, 41, 9])])
+def test_tc_tf32_matches_the_fp32_kernel(B, M, N, counts):
+    from differentiable_ransac_b200 import ops, synth
+
+    dev = "cuda"
+    matches, _, _ = synth.relative_pose_batch(B, max(N, 8), seed=5 + N)
+    matches = matches[:, :N].contiguous().to(dev)
+    gen = torch.Generator().manual_seed(M)
+    models = torch.randn(B, M, 3, 3, generator=gen)
+    models = (models / models.flatten(-2).norm(dim=-1)[..., None, None]).to(dev)
+    thr = (torch.rand(B, generator=gen) * 0.05 + 0.002).to(dev)
+    count = None if counts is None else torch.tensor(counts, dtype=torch.int32, device=dev)
+    s_ref, b_ref = ops.score_msac(matches, models, thr, count=count, kernel="block")
+    s_tc, b_tc = ops.score_msac(matches, models, thr, count=count, kernel="tc_tf32")
+    s_2, b_2 = ops.score_msac(matches, models, thr, count=count, kernel="tc_tf32")
+    torch.cuda.synchronize()
+    cnt = torch.full((B,), M, device=dev) if count is None else count
+    live = torch.arange(M, device=dev)[None, :] < cnt[:, None]
+    rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
+    assert float(rel.max()) < 1e-4            # measured 2e-6 .. 5e-6 on these cases
+    assert torch.equal(s_tc[live], s_2[live]) and torch.equal(b_tc, b_2)      # schedule-independent sums
+    for b in range(B):
+        if int(cnt[b]) == 0:
+            assert int(b_tc[b]) == 0
+            continue
+        # the winner is the FP32 kernel's, or a model whose FP32 score is within the split's error of it
+        i_tc, i_ref = _ids(b_tc)[b], _ids(b_ref)[b]
+        assert i_tc == i_ref or float(s_ref[b, i_ref] - s_ref[b, i_tc]) <= 2e-4 * max(1.0, float(s_ref[b, i_ref]))
+
+
+def test_tc_tf32_headline_shape():
+    """cfg2's compact model list (32 pairs, ~139 000 models, 2000 correspondences): measured 1.4e-4 relative at
+    worst against the FP32 kernel -- rare low-score models; the 22-bit operand words are the limit."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    from differentiable_ransac_b200 import ops
+
+    dev = "cuda"
+    B, K, N = 32, 1000, 2000
+    matches_h, logits_h, thr_h, _ = bench.make_inputs(B, N, seed=1234)
+    m, lg, thr = matches_h.to(dev), logits_h.to(dev), thr_h.to(dev)
+    idx = ops.sample_sets(lg, K, 5, seed=7, offset=0)
+    _, _, cm, cid, cc = ops.solve_e5(m, idx, compact=True)
+    s_ref, b_ref = ops.score_msac(m, cm, thr, count=cc, ids=cid, kernel="block")
+    s_tc, b_tc = ops.score_msac(m, cm, thr, count=cc, ids=cid, kernel="tc_tf32")
+    torch.cuda.synchronize()
+    live = torch.arange(cm.shape[1], device=dev)[None] < cc[:, None]
+    rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
+    assert float(rel.max()) < 5e-4 and float(rel.mean()) < 2e-5
+    best_ref = torch.where(live, s_ref, torch.full_like(s_ref, -1.0)).max(dim=1).values
+    best_tc = torch.where(live, s_tc, torch.full_like(s_tc, -1.0)).max(dim=1).values
+    assert float(((best_tc - best_ref).abs() / best_ref).max()) < 5e-5       # the winners' scores
+
+
+# ---- tier 2: not yet confirmed on hardware (opt-in) --------------------------------------------------------------
+@pytest.fixture()
+def _opt_in():
     if os.environ.get("DRB_EXPERIMENTAL", "0") != "1":
-        pytest.skip("experimental kernel: set DRB_EXPERIMENTAL=1")
+        pytest.skip("not yet confirmed on hardware: set DRB_EXPERIMENTAL=1")
 
 
 CHILD = r"""
@@ -29,6 +97,7 @@ import sys, torch
 sys.path.insert(0, {root!r})
 from differentiable_ransac_b200 import ops, synth
 from oracle import scoring
+KERNEL = {kernel!r}
 B, M, N, counts = {case!r}
 matches, _, _ = synth.relative_pose_batch(B, max(N, 8), seed=5 + N)
 matches = matches[:, :N].contiguous()
@@ -41,8 +110,8 @@ ids = torch.stack([torch.randperm(4 * M + 7, generator=gen)[:M] for _ in range(B
 dev = "cuda"
 args = (matches.to(dev), models.to(dev), thr.to(dev))
 kw = dict(count=None if count is None else count.to(dev), ids=ids.to(dev))
-s_tc, b_tc = ops.score_msac(*args, kernel="tc", **kw)
-s_again, b_again = ops.score_msac(*args, kernel="tc", **kw)
+s_tc, b_tc = ops.score_msac(*args, kernel=KERNEL, **kw)
+s_again, b_again = ops.score_msac(*args, kernel=KERNEL, **kw)
 s_ref, b_ref = ops.score_msac(*args, kernel="block", **kw)
 torch.cuda.synchronize()
 assert torch.equal(s_tc.isnan(), s_again.isnan())
@@ -54,7 +123,7 @@ for b in range(B):
     want, _ = scoring.msac_score(matches[b].double(), models[b, :c].double(), float(thr[b]))
     got = s_tc[b, :c].cpu().double()
     rel = (got - want).abs() / want.clamp_min(1.0)
-    assert rel.max() < 1e-4, (b, float(rel.max()))
+    assert rel.max() < (1e-4 if KERNEL == "tc_bf16" else 5e-4), (b, float(rel.max()))
     assert torch.equal(s_tc[b, :c], s_again[b, :c]), "not deterministic"
     key = int(b_tc[b]) & 0xFFFFFFFFFFFFFFFF
     best_id = 0xFFFFFFFF - (key & 0xFFFFFFFF)
@@ -75,8 +144,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("kernel", ["tc_bf16", "tc_tf32"])
 @pytest.mark.parametrize("case", CASES)
-def test_tc_kernel_matches_oracle(case):
-    r = subprocess.run([sys.executable, "-c", CHILD.format(root=ROOT, case=case)], capture_output=True, text=True,
-                       timeout=180)
+def test_tc_kernel_matches_oracle(case, kernel, _opt_in):
+    r = subprocess.run([sys.executable, "-c", CHILD.format(root=ROOT, case=case, kernel=kernel)], capture_output=True,
+                       text=True, timeout=180)
     assert r.returncode == 0 and r.stdout.strip().endswith("OK"), (r.stdout[-500:], r.stderr[-2000:])
