@@ -49,6 +49,9 @@ DRB_HD int image_index(int row, int k) { return ((row >> 3) * kSBO + (k >> 2) * 
 // (r_2g, r_2g+1, j_2g, j_2g+1) so that the epilogue finds two models side by side in an aligned register pair
 DRB_HD int column_r(int i) { return 4 * (i >> 1) + (i & 1); }
 DRB_HD int column_j(int i) { return 4 * (i >> 1) + 2 + (i & 1); }
+// Pair-reciprocal variant: the two j columns of a group are SWAPPED, (r_2g, r_2g+1, j_2g+1, j_2g), so that the
+// epilogue's (1/j_2g, 1/j_2g+1) = rcp(j_2g j_2g+1) * (j_2g+1, j_2g) needs one reciprocal and no register moves
+DRB_HD int column_j_swapped(int i) { return 4 * (i >> 1) + 2 + ((i & 1) ^ 1); }
 
 // ---- descriptors ------------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address, LBO, SBO in 16-byte units,
@@ -142,6 +145,27 @@ DRB_HD void coefficients(const float* m, float* cr, float* cj) {
     cj[12] = 2.f * (m[0] * m[6] + m[1] * m[7]);
     cj[13] = 2.f * (m[3] * m[6] + m[4] * m[7]);
     cj[14] = (m[2] * m[2] + m[5] * m[5]) + (m[6] * m[6] + m[7] * m[7]);
+}
+
+// Coefficient rows of model i of a tile as the scorer's builder warps write them.  With the pair reciprocal a
+// model's 1/j is computed from the product with its neighbour's j, so a column that is not a real model must not
+// poison its neighbour: an absent model (past the pair's count) becomes r = 0, j = 1, and a model with a
+// non-finite coefficient becomes r = 1e18, j = 1 (its own terms clamp to 0 exactly as NaN terms do, its
+// neighbour's are untouched).  Without the pair reciprocal absent models are all-zero rows and NaN stays NaN.
+DRB_HD void model_rows(const float* m, bool present, bool pair, float* cr, float* cj) {
+    bool finite = true;
+    DRB_UNROLL
+    for (int q = 0; q < 9; ++q) finite = finite && (t_abs(m[q]) <= 3.0e38f);   // false for NaN and Inf
+    if (present && (finite || !pair)) {
+        coefficients(m, cr, cj);
+        return;
+    }
+    DRB_UNROLL
+    for (int i = 0; i < kFeat; ++i) cr[i] = cj[i] = 0.f;
+    if (pair) {
+        cj[kFeat - 1] = 1.f;
+        if (present) cr[kFeat - 1] = 1.0e18f;
+    }
 }
 
 // One operand row: the three K blocks of 16 (v = 15 values), A side [hi | lo | hi], B side [hi | hi | lo].

@@ -168,7 +168,7 @@ msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, uin
 }
 
 // ---- launch 2 -----------------------------------------------------------------------------------------
-template <bool BF16>
+template <bool BF16, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restrict__ models,
                      const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
@@ -299,7 +299,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 for (int q = 0; q < 9; ++q) m[q] = mi < cnt ? __ldg(models + ((size_t)b * M + mi) * 9 + q) : 0.f;
                 float cr[kFeat], cj[kFeat];
                 uint32_t row48[kK];
-                coefficients(m, cr, cj);
+                model_rows(m, mi < cnt, PAIR, cr, cj);
                 operand_row_words(cr, false, BF16, row48);
                 DRB_UNROLL
                 for (int c = 0; c < kK / 4; ++c)
@@ -308,7 +308,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 operand_row_words(cj, false, BF16, row48);
                 DRB_UNROLL
                 for (int c = 0; c < kK / 4; ++c)
-                    *reinterpret_cast<uint4*>(img + image_index(column_j(i), 4 * c)) =
+                    *reinterpret_cast<uint4*>(img + image_index(PAIR ? column_j_swapped(i) : column_j(i), 4 * c)) =
                         make_uint4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
             }
             fence_proxy_async();   // generic-proxy stores -> visible to the tensor core's async-proxy reads
@@ -350,10 +350,19 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                     for (int q = 0; q < 8; ++q) {
                         const pk2 R = pk2_make(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
                         const pk2 R2 = pk2_mul(R, R);
-                        const pk2 IJ = pk2_make(rcp_approx(__uint_as_float(v[4 * q + 2])), rcp_approx(__uint_as_float(v[4 * q + 3])));
-                        float u0, u1;
-                        pk2_split(pk2_mul(R2, IJ), u0, u1);
-                        acc[c * 8 + q] = pk2_add(acc[c * 8 + q], pk2_make(fma_sat(u0, nci, one), fma_sat(u1, nci, one)));
+                        if (PAIR) {
+                            // columns (r0, r1, j1, j0): (1/j0, 1/j1) = rcp(j0 j1) (j1, j0) -- one reciprocal per two pairs
+                            const float ja = __uint_as_float(v[4 * q + 2]), jb = __uint_as_float(v[4 * q + 3]);
+                            const float tn = rcp_approx(ja * jb) * nci;
+                            float w0, w1;
+                            pk2_split(pk2_mul(R2, pk2_make(ja, jb)), w0, w1);
+                            acc[c * 8 + q] = pk2_add(acc[c * 8 + q], pk2_make(fma_sat(w0, tn, one), fma_sat(w1, tn, one)));
+                        } else {
+                            const pk2 IJ = pk2_make(rcp_approx(__uint_as_float(v[4 * q + 2])), rcp_approx(__uint_as_float(v[4 * q + 3])));
+                            float u0, u1;
+                            pk2_split(pk2_mul(R2, IJ), u0, u1);
+                            acc[c * 8 + q] = pk2_add(acc[c * 8 + q], pk2_make(fma_sat(u0, nci, one), fma_sat(u1, nci, one)));
+                        }
                     }
                 }
                 tc_fence_before();
@@ -431,17 +440,17 @@ extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
 
 namespace drb {
 namespace tc {
-template <bool BF16>
+template <bool BF16, bool PAIR>
 static int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr,
                   int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc_kernel<BF16>,
+    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc_kernel<BF16, PAIR>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (attr != cudaSuccess) return DRB_ERR_CUDA;
     const int tiles = (N + kTileM - 1) / kTileM;
     msac_tc_features_kernel<BF16><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kTileModels - 1) / kTileModels);
     const int grid = (int)(max_units < tc_sm_count() ? max_units : tc_sm_count());
-    score_msac_tc_kernel<BF16><<<grid, kThreads, kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
+    score_msac_tc_kernel<BF16, PAIR><<<grid, kThreads, kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
                                                                   best_packed);
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
@@ -457,9 +466,13 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     if (workspace_bytes < drb_score_msac_tc_workspace_bytes(B, N) || (reinterpret_cast<uintptr_t>(workspace) & 127) ||
         (reinterpret_cast<uintptr_t>(matches) & 15))
         return DRB_ERR_BAD_SHAPE;
-    if (words != 2 && words != 3) return DRB_ERR_UNSUPPORTED;
+    // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair (not yet measured on hardware)
+    const int split = words & 15, pair = words & 16;
+    if ((split != 2 && split != 3) || (words & ~31)) return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
-    return words == 3 ? tc::launch<true>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s)
-                      : tc::launch<false>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
+#define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
+    if (pair) return split == 3 ? tc::launch<true, true>(DRB_TC_ARGS) : tc::launch<false, true>(DRB_TC_ARGS);
+    return split == 3 ? tc::launch<true, false>(DRB_TC_ARGS) : tc::launch<false, false>(DRB_TC_ARGS);
+#undef DRB_TC_ARGS
 }

@@ -322,6 +322,7 @@ def solve_rigid3_backward(points, idx, g_model, flag=True):
 
 # ---- scoring -----------------------------------------------------------------------------------
 _MSAC_KERNEL = os.environ.get("DRB_MSAC_KERNEL", "stream")
+_TC_WORDS = {"tc": 3, "tc_bf16": 3, "tc_tf32": 2, "tc_bf16p": 3 + 16, "tc_tf32p": 2 + 16}
 
 
 def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None, kernel=None):
@@ -348,13 +349,14 @@ def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, bes
     elif kernel == "block":
         check(lib.drb_score_msac(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N, _p(scores), _p(best),
                                  _stream()), "drb_score_msac")
-    elif kernel in ("tc", "tc_bf16", "tc_tf32"):
+    elif kernel in _TC_WORDS:
         # experimental tensor-core scorer (csrc/score_tc.cu): opt-in only, see DESIGN.md section 10.
-        # "tc" = "tc_bf16": three BF16 words per operand (fp32-level scores); "tc_tf32": two TF32 words
+        # "tc" = "tc_bf16": three BF16 words per operand (fp32-level scores); "tc_tf32": two TF32 words;
+        # a trailing "p": one reciprocal per model pair (not yet measured on hardware)
         nbytes = int(lib.drb_score_msac_tc_workspace_bytes(B, N))
         ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=matches.device)
         check(lib.drb_score_msac_tc(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N,
-                                    2 if kernel == "tc_tf32" else 3, _p(scores), _p(best), _p(ws), ws.numel() * 8,
+                                    _TC_WORDS[kernel], _p(scores), _p(best), _p(ws), ws.numel() * 8,
                                     _stream()), "drb_score_msac_tc")
     else:
         raise _lib.DrbError(f"unknown MSAC kernel {kernel!r}")

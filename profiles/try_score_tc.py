@@ -29,7 +29,7 @@ def ids_of(best):
 from differentiable_ransac_b200 import ops, synth  # noqa: E402
 
 dev = "cuda"
-KERNELS = sys.argv[1].split(",") if len(sys.argv) > 1 else ["tc_tf32", "tc_bf16"]
+KERNELS = sys.argv[1].split(",") if len(sys.argv) > 1 else ["tc_tf32", "tc_bf16", "tc_tf32p", "tc_bf16p"]
 say(stage="start", t=time.time(), kernels=KERNELS)
 CASES = [(1, 5, 3, None), (2, 33, 64, None), (3, 70, 257, [70, 0, 41]), (3, 300, 2500, [300, 0, 129]),
          (4, 1000, 2000, [1000, 517, 1, 32]), (40, 200, 500, None)]
@@ -48,7 +48,8 @@ for kern in KERNELS:
         s_tc, b_tc = ops.score_msac(matches, models, thr, count=count, ids=ids, kernel=kern)
         s_2, b_2 = ops.score_msac(matches, models, thr, count=count, ids=ids, kernel=kern)
         torch.cuda.synchronize()
-        live = torch.arange(M, device=dev)[None] < (count[:, None] if count is not None else M)
+        cnt = torch.full((B,), M, device=dev) if count is None else count
+        live = torch.arange(M, device=dev)[None, :] < cnt[:, None]          # [B, M]
         rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
         say(stage="parity", kernel=kern, case=[B, M, N, counts], max_rel=float(rel.max()),
             same_ids=ids_of(b_tc) == ids_of(b_ref), deterministic=bool(torch.equal(s_tc[live], s_2[live]) and torch.equal(b_tc, b_2)))

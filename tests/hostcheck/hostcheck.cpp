@@ -257,7 +257,7 @@ static float desc_fetch(const std::vector<uint32_t>& smem, uint64_t desc, int ro
 int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, float thr, int words, float* scores,
                       int* lossless) {
     using namespace drb::tc;
-    const bool bf16 = words == 3;
+    const bool bf16 = (words & 15) == 3, pair = (words & 16) != 0;
     const uint32_t idesc = bf16 ? instr_desc_bf16() : instr_desc();
     const int mmaN = (int)((idesc >> 17) & 0x3f) << 3, mmaM = (int)((idesc >> 24) & 0x1f) << 4;
     if (mmaN != kTileN || mmaM != kTileM) return -1;
@@ -276,11 +276,12 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
             float m[9], cr[kFeat], cj[kFeat];
             uint32_t row48[kK];
             for (int q = 0; q < 9; ++q) m[q] = (m0 + i < M) ? models[(size_t)(m0 + i) * 9 + q] : 0.f;
-            coefficients(m, cr, cj);
+            model_rows(m, m0 + i < M, pair, cr, cj);
             operand_row_words(cr, false, bf16, row48);
             for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_r(i), k)] = row48[k];
             operand_row_words(cj, false, bf16, row48);
-            for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_j(i), k)] = row48[k];
+            for (int k = 0; k < kK; ++k)
+                smem[b_addr / 4 + image_index(pair ? column_j_swapped(i) : column_j(i), k)] = row48[k];
         }
         std::vector<float> lane_sum((size_t)kTileM * kTileModels, 0.f);   // per epilogue thread (lane, model)
         for (int t = 0; t < tiles; ++t) {
@@ -321,17 +322,24 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
                         const int row = quarter * 32 + lane;
                         const float one = (t * kTileM + row < N) ? 1.f : 0.f;
                         for (int c = 0; c < 4; ++c)
-                            for (int q = 0; q < 8; ++q)
+                            for (int q = 0; q < 8; ++q) {
+                                const int col = half * 128 + c * 32 + 4 * q;
+                                const float ja = D[(size_t)row * kTileN + col + 2], jb = D[(size_t)row * kTileN + col + 3];
+                                const float tn = (1.f / (ja * jb)) * nci;        // pair variant: one reciprocal
                                 for (int h = 0; h < 2; ++h) {
-                                    const int col = half * 128 + c * 32 + 4 * q;
                                     const float r = D[(size_t)row * kTileN + col + h];
-                                    const float j = D[(size_t)row * kTileN + col + 2 + h];
-                                    const float u = (r * r) * (1.f / j);
-                                    float v = u * nci + one;
+                                    float v;
+                                    if (pair) {
+                                        v = ((r * r) * (h ? jb : ja)) * tn + one;     // columns (r0, r1, j1, j0)
+                                    } else {
+                                        const float j = h ? jb : ja;
+                                        v = ((r * r) * (1.f / j)) * nci + one;
+                                    }
                                     v = (v != v) ? 0.f : (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));   // FFMA.SAT
                                     const int model = half * 64 + 2 * (c * 8 + q) + h;
                                     lane_sum[(size_t)row * kTileModels + model] += v;
                                 }
+                            }
                     }
         }
         for (int i = 0; i < kTileModels; ++i) {

@@ -251,7 +251,7 @@ def _tc_scores(lib, matches, models, thr, words=2):
     return torch.from_numpy(out)
 
 
-@pytest.mark.parametrize("words", [2, 3])
+@pytest.mark.parametrize("words", [2, 3, 2 + 16, 3 + 16])
 @pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (128, 20)])
 def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K, words):
     """The 3xTF32 contraction over 15 monomials, built and decoded exactly as score_tc.cu does it (images ->
@@ -273,19 +273,21 @@ def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K, words):
     want, _ = scoring.msac_score(matches.double(), E.double(), thr)
     got = _tc_scores(lib, matches, E, thr, words)
     rel = (got.double() - want).abs() / want.clamp_min(1.0)
-    assert rel.max() < (1e-4 if words == 2 else 3e-5), rel.max()
+    assert rel.max() < (1e-4 if words & 15 == 2 else 3e-5), rel.max()
     assert int(got.argmax()) == int(want.argmax())
     fp32, _ = scoring.msac_score(matches, E, thr)
     assert (got - fp32).abs().max() / fp32.max() < 1e-4
 
 
-@pytest.mark.parametrize("words", [2, 3])
+@pytest.mark.parametrize("words", [2, 3, 2 + 16, 3 + 16])
 def test_msac_tc_nan_models_score_zero(lib, words):
     from differentiable_ransac_b200 import synth
 
     matches, E_gt, _ = synth.relative_pose_batch(1, 300, seed=5)
     models = torch.stack([E_gt[0], torch.full((3, 3), float("nan")), E_gt[0] / E_gt[0].norm()])
     got = _tc_scores(lib, matches[0], models, 0.75 / 800.0, words)
+    # the NaN model scores 0 and -- pair reciprocal included -- leaves its column neighbour (model 0) alone;
+    # model 2's neighbour is an absent model (odd count)
     assert got[1] == 0.0 and got[0] > 10 and abs(float(got[0] - got[2])) < 1e-3 * float(got[0])
 
 
