@@ -45,14 +45,12 @@ namespace drb {
 namespace tc {
 
 constexpr int kStagesA = 4;
-constexpr int kWarps = 12;
-constexpr int kThreads = kWarps * 32;
 constexpr int kWarpProducer = 0;
 constexpr int kWarpMma = 1;
 constexpr int kWarpBuild0 = 2;       // warps 2, 3
 constexpr int kBuildThreads = 64;
-constexpr int kWarpEpi0 = 4;         // warps 4 .. 11
-constexpr int kEpiThreads = 256;
+constexpr int kWarpEpi0 = 4;         // epilogue warps 4 .. 4 + EPI - 1 (EPI = 8, or 16: not yet measured)
+constexpr int threads_of(int epi_warps) { return (kWarpEpi0 + epi_warps) * 32; }
 constexpr int kTmemCols = 512;       // two accumulators of kTileN columns
 constexpr int kMaxPairs = 1024;
 
@@ -168,8 +166,8 @@ msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, uin
 }
 
 // ---- launch 2 -----------------------------------------------------------------------------------------
-template <bool BF16, bool PAIR>
-__global__ void __launch_bounds__(kThreads, 1)
+template <bool BF16, bool PAIR, int EPI>
+__global__ void __launch_bounds__(threads_of(EPI), 1)
 score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restrict__ models,
                      const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
                      int B, int M, int N, int tiles, float* __restrict__ scores,
@@ -196,7 +194,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&d_full[i], 1);                  // tcgen05.commit
-            mbar_init(&d_empty[i], kEpiThreads / 32);  // one arrival per epilogue warp
+            mbar_init(&d_empty[i], EPI);               // one arrival per epilogue warp
             mbar_init(&b_full[i], kBuildThreads / 32); // one arrival per builder warp
             mbar_init(&b_empty[i], 1);                 // tcgen05.commit
         }
@@ -318,9 +316,12 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
         }
     } else {
         // ===== epilogue =====
-        const int et = threadIdx.x - kWarpEpi0 * 32;   // 0 .. 255
+        // EPI / 4 warps share a lane quarter; each takes kCols = 256 / (EPI / 4) consecutive columns of the
+        // accumulator = kCols / 2 models, in kChunks loads of 32 columns (8 model pairs each)
+        constexpr int kParts = EPI / 4, kCols = kTileN / kParts, kChunks = kCols / 32, kAcc = kChunks * 8;
+        const int et = threadIdx.x - kWarpEpi0 * 32;   // 0 .. 32 EPI - 1
         const int quarter = warp & 3;                  // the TMEM lanes this warp may read: 32 quarter .. + 31
-        const int half = (warp - kWarpEpi0) >> 2;      // columns 128 half .. + 127 of the accumulator
+        const int half = (warp - kWarpEpi0) >> 2;      // this warp's column part: columns kCols half .. + kCols - 1
         Ring rd;
         int parity = 0;
 #pragma unroll 1
@@ -330,9 +331,9 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
             const int cnt = count ? min(__ldg(count + b), M) : M;
             const float th = 1.5f * __ldg(thr + b);
             const float nci = -1.f / (th * th);
-            pk2 acc[32];
+            pk2 acc[kAcc];
             DRB_UNROLL
-            for (int i = 0; i < 32; ++i) acc[i] = pk2_splat(0.f);
+            for (int i = 0; i < kAcc; ++i) acc[i] = pk2_splat(0.f);
 #pragma unroll 1
             for (int t = 0; t < tiles; ++t) {
                 mbar_wait(&d_full[rd.idx], rd.phase);
@@ -340,9 +341,9 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 tc_fence_after();
                 // a row past N contributes 0: max(0, min(1, u * nci + 0)) with u * nci <= 0 (or NaN -> 0)
                 const float one = (t * kTileM + quarter * 32 + lane < N) ? 1.f : 0.f;
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(rd.idx * kTileN + half * 128);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(rd.idx * kTileN + half * kCols);
                 DRB_UNROLL
-                for (int c = 0; c < 4; ++c) {
+                for (int c = 0; c < kChunks; ++c) {
                     uint32_t v[32];
                     tmem_ld32(taddr + (uint32_t)(c * 32), v);
                     tmem_ld_wait();
@@ -371,11 +372,11 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 rd.advance(2);
             }
             // ---- sum over the 128 lanes: butterfly reduce-scatter inside the warp, then the four quarters -----
-            float a[64];
+            float a[2 * kAcc];
             DRB_UNROLL
-            for (int i = 0; i < 32; ++i) pk2_split(acc[i], a[2 * i], a[2 * i + 1]);
+            for (int i = 0; i < kAcc; ++i) pk2_split(acc[i], a[2 * i], a[2 * i + 1]);
             DRB_UNROLL
-            for (int w = 32, o = 16; o > 0; w >>= 1, o >>= 1) {
+            for (int w = kAcc, o = 16; o > 0; w >>= 1, o >>= 1) {
                 const bool up = (lane & o) != 0;
                 DRB_UNROLL
                 for (int i = 0; i < w; ++i) {
@@ -384,15 +385,16 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                     a[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
                 }
             }
-            // this lane now owns models 2 lane, 2 lane + 1 of its half (lane quarter `quarter`)
-            float* pp = part + (size_t)parity * (2 * 4 * 64);
-            pp[(half * 4 + quarter) * 64 + 2 * lane] = a[0];
-            pp[(half * 4 + quarter) * 64 + 2 * lane + 1] = a[1];
-            asm volatile("bar.sync 1, %0;" ::"n"(kEpiThreads) : "memory");
+            // this lane now owns kPer = kAcc / 16 consecutive models of its part: kPer lane .. kPer lane + kPer - 1
+            // (lane quarter `quarter`); part[parity][quarter][model of the tile]
+            constexpr int kPer = kAcc / 16;
+            float* pp = part + (size_t)parity * (4 * kTileModels);
+            DRB_UNROLL
+            for (int i = 0; i < kPer; ++i) pp[quarter * kTileModels + half * (kCols / 2) + kPer * lane + i] = a[i];
+            asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
             if (et < kTileModels) {
-                const int h = et >> 6, j = et & 63;
-                const float score = ((pp[(h * 4 + 0) * 64 + j] + pp[(h * 4 + 1) * 64 + j]) + pp[(h * 4 + 2) * 64 + j]) +
-                                    pp[(h * 4 + 3) * 64 + j];
+                const float score = ((pp[0 * kTileModels + et] + pp[1 * kTileModels + et]) + pp[2 * kTileModels + et]) +
+                                    pp[3 * kTileModels + et];
                 const int mi = mt * kTileModels + et;
                 const bool live = mi < cnt;
                 if (live && scores) scores[(size_t)b * M + mi] = score;
@@ -440,17 +442,17 @@ extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
 
 namespace drb {
 namespace tc {
-template <bool BF16, bool PAIR>
+template <bool BF16, bool PAIR, int EPI>
 static int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr,
                   int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc_kernel<BF16, PAIR>,
+    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc_kernel<BF16, PAIR, EPI>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (attr != cudaSuccess) return DRB_ERR_CUDA;
     const int tiles = (N + kTileM - 1) / kTileM;
     msac_tc_features_kernel<BF16><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kTileModels - 1) / kTileModels);
     const int grid = (int)(max_units < tc_sm_count() ? max_units : tc_sm_count());
-    score_msac_tc_kernel<BF16, PAIR><<<grid, kThreads, kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
+    score_msac_tc_kernel<BF16, PAIR, EPI><<<grid, threads_of(EPI), kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
                                                                   best_packed);
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
@@ -466,13 +468,17 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     if (workspace_bytes < drb_score_msac_tc_workspace_bytes(B, N) || (reinterpret_cast<uintptr_t>(workspace) & 127) ||
         (reinterpret_cast<uintptr_t>(matches) & 15))
         return DRB_ERR_BAD_SHAPE;
-    // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair (not yet measured on hardware)
-    const int split = words & 15, pair = words & 16;
-    if ((split != 2 && split != 3) || (words & ~31)) return DRB_ERR_UNSUPPORTED;
+    // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair; + 32 = 16 epilogue warps instead
+    // of 8 (the last two not yet measured on hardware)
+    const int split = words & 15;
+    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0;
+    if ((split != 2 && split != 3) || (words & ~63)) return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
 #define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
-    if (pair) return split == 3 ? tc::launch<true, true>(DRB_TC_ARGS) : tc::launch<false, true>(DRB_TC_ARGS);
-    return split == 3 ? tc::launch<true, false>(DRB_TC_ARGS) : tc::launch<false, false>(DRB_TC_ARGS);
+#define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16>(DRB_TC_ARGS) : tc::launch<BF, PR, 8>(DRB_TC_ARGS))
+    if (pair) return split == 3 ? DRB_TC_PICK(true, true) : DRB_TC_PICK(false, true);
+    return split == 3 ? DRB_TC_PICK(true, false) : DRB_TC_PICK(false, false);
+#undef DRB_TC_PICK
 #undef DRB_TC_ARGS
 }

@@ -322,7 +322,10 @@ def solve_rigid3_backward(points, idx, g_model, flag=True):
 
 # ---- scoring -----------------------------------------------------------------------------------
 _MSAC_KERNEL = os.environ.get("DRB_MSAC_KERNEL", "stream")
+# tensor-core scorer variants -> the `words` argument of drb_score_msac_tc: operand split (2 TF32 / 3 BF16 words),
+# "p" = one reciprocal per model pair (+16), "_e16" = 16 epilogue warps instead of 8 (+32)
 _TC_WORDS = {"tc": 3, "tc_bf16": 3, "tc_tf32": 2, "tc_bf16p": 3 + 16, "tc_tf32p": 2 + 16}
+_TC_WORDS.update({k + "_e16": v + 32 for k, v in list(_TC_WORDS.items()) if k != "tc"})
 
 
 def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None, kernel=None):
@@ -352,7 +355,7 @@ def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, bes
     elif kernel in _TC_WORDS:
         # experimental tensor-core scorer (csrc/score_tc.cu): opt-in only, see DESIGN.md section 10.
         # "tc" = "tc_bf16": three BF16 words per operand (fp32-level scores); "tc_tf32": two TF32 words;
-        # a trailing "p": one reciprocal per model pair (not yet measured on hardware)
+        # a trailing "p": one reciprocal per model pair; "_e16": 16 epilogue warps (neither measured on hardware yet)
         nbytes = int(lib.drb_score_msac_tc_workspace_bytes(B, N))
         ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=matches.device)
         check(lib.drb_score_msac_tc(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N,

@@ -162,7 +162,8 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
  * drb_score_msac); words = 3: three BF16 words, six partial products (exact operands: fp32-level scores) for
  * the same MMA time; words + 16: one reciprocal per PAIR of neighbouring models, rcp(j0 j1) (j1, j0), which halves
  * the work of the pipe that bounds the kernel (a model with a non-finite coefficient then scores 0 without
- * touching its neighbour; not yet measured on hardware).  B <= 1024; matches 16-byte aligned.  Needs a
+ * touching its neighbour); words + 32: 16 epilogue warps per CTA instead of 8 (more warps to hide the latency of
+ * the tensor-memory loads and the SFU) -- neither of the two measured on hardware yet.  B <= 1024; matches 16-byte aligned.  Needs a
  * 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents irrelevant on entry:
  * the call writes the operand images of the correspondences there first).                         */
 size_t drb_score_msac_tc_workspace_bytes(int B, int N);

@@ -144,7 +144,7 @@ CASES = [
 ]
 
 
-@pytest.mark.parametrize("kernel", ["tc_bf16", "tc_tf32", "tc_bf16p", "tc_tf32p"])
+@pytest.mark.parametrize("kernel", ["tc_bf16", "tc_tf32", "tc_bf16p", "tc_tf32p", "tc_tf32_e16", "tc_bf16p_e16"])
 @pytest.mark.parametrize("case", CASES)
 def test_tc_kernel_matches_oracle(case, kernel, _opt_in):
     r = subprocess.run([sys.executable, "-c", CHILD.format(root=ROOT, case=case, kernel=kernel)], capture_output=True,
