@@ -23,7 +23,7 @@
 //                   bf16) per tile into one of two 256-column accumulators and commits to the mbarriers
 //       warps 2-3   build the model operand (coefficient rows split into words) of the NEXT unit in the second
 //                   B buffer while the current unit is being scored
-//       warps 4-11  epilogue: tcgen05.ld 32 lanes x 32 columns, r^2 * rcp(j), FFMA.SAT, per-thread sums over
+//       warps 4-11  (4-19 in the 16-warp variant) epilogue: tcgen05.ld 32 lanes x 32 columns, r^2 * rcp(j), FFMA.SAT, per-thread sums over
 //                   the unit's tiles, then a butterfly reduce-scatter over the 32 lanes and a fixed-order sum
 //                   of the four lane quarters (the scores do not depend on the schedule)
 //   A unit = (pair, 128 consecutive models); units are dealt round-robin to the CTAs.
@@ -62,7 +62,7 @@ constexpr int kNumBars = 2 * kStagesA + 2 + 2 + 2 + 2;        // a_full/a_empty,
 constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
 constexpr int kOffPrefix = kOffTmemPtr + 16;
 constexpr int kOffPart = kOffPrefix + (kMaxPairs + 1) * 4 + 12;
-constexpr int kSmemBytes = kOffPart + 2 * 2 * 4 * 64 * 4;    // part[parity][half][quarter][64]
+constexpr int kSmemBytes = kOffPart + 2 * 4 * kTileModels * 4;   // part[unit parity][lane quarter][model of the tile]
 static_assert(kOffPart % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 
