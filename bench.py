@@ -49,6 +49,30 @@ def load_peaks():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def tensor_side(n_models, n_points, kernel_ms, scorer):
+    """tcgen05 work of one launch of the tensor-core scorer: every (128 correspondences x 128 models) tile is six
+    128 x 256 x 8 (TF32) or x 16 (BF16) MMAs, padded tiles included.  Peak: the driver-measured dense BF16 rate
+    (MEASURED_PEAKS.json; TF32 runs at half of it).  Extra keys beside the mandated HBM roofline; never raises."""
+    try:
+        bf16 = "bf16" in scorer or scorer == "tc"
+        tiles = -(-n_points // 128) * -(-n_models // 128)            # lower bound: per-pair tails add a little
+        flop = tiles * 6 * 2.0 * 128 * 256 * (16 if bf16 else 8)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peak = float(json.load(f)["bf16_tflops"])
+            src = "measured dense BF16 (MEASURED_PEAKS.json)"
+        except Exception:
+            peak, src = 2250.0, "nominal dense BF16"
+        if not bf16:
+            peak, src = peak / 2, src + " / 2 for TF32"
+        t = flop / (kernel_ms / 1e3) / 1e12
+        return dict(tensor_tflops=t, tensor_peak_tflops=peak, tensor_frac=t / peak, tensor_peak_source=src,
+                    tensor_note="flops issued on tcgen05, the 3 (TF32) or 6 (BF16) partial products of the split "
+                                "operands included")
+    except Exception as e:                                         # reporting only
+        return dict(tensor_note=f"unavailable: {e}")
+
+
 def load_traffic(kernel):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture."""
     try:
@@ -488,6 +512,8 @@ def run_ours(args):
                       fp32_frac=flops_score / (score_ms / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
                       step_algorithmic_gbs=ALGO_BYTES_PER_HYP * B * K / (ms_per_step / 1e3) / 1e9, **shares),
     )
+    if launches_per_step == 5:
+        line["roofline"].update(tensor_side(n_valid, N, score_ms, str(msac_kernel)))
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
         line["cpu_baseline"] = cpu_reference_throughput()
         line["accuracy"] = auc_parity(dev, scorer=dsvc.scorer)      # through the scorer the timed steps used

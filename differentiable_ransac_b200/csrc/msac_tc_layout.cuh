@@ -253,6 +253,11 @@ DRB_HD uint32_t instr_desc_bf16() {
     d |= (uint32_t)(kTileM >> 4) << 24;
     return d;
 }
+// General form: M x N of the instruction, TF32 or BF16 operands (fp32 accumulate, K-major A and B)
+DRB_HD uint32_t instr_desc_mn(int m, int n, bool bf16) {
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 // TF32 variant as 32-bit words, so both variants share the image writers
 DRB_HD void operand_row_words(const float* v, bool a_side, bool bf16, uint32_t* row48w) {
     if (bf16) {

@@ -39,6 +39,7 @@
 #include "f32x2.cuh"
 #include "msac_tc_layout.cuh"
 #include "sampson.cuh"
+#include "tc_ptx.cuh"
 #include "tile_pipe.cuh"
 
 namespace drb {
@@ -65,80 +66,6 @@ constexpr int kOffPart = kOffPrefix + (kMaxPairs + 1) * 4 + 12;
 constexpr int kSmemBytes = kOffPart + 2 * 4 * kTileModels * 4;   // part[unit parity][lane quarter][model of the tile]
 static_assert(kOffPart % 16 == 0, "alignment");
 static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
-
-// ---- tcgen05 wrappers (PTX as in cute/arch/mma_sm100_umma.hpp, copy_sm100.hpp, tmem_allocator_sm100.hpp) ---
-__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(cols)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// D[tmem] (+)= A[smem] * B[smem]',  one thread issues
-__device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "setp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-        "}\n" ::"r"(tmem_d),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-// the mbarrier receives one arrival when every tcgen05.mma issued so far by this thread has completed
-__device__ __forceinline__ void mma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes (this warp's quarter) x 32 consecutive columns -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-        : "r"(taddr)
-        : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// ring position: stage index + phase bit
-struct Ring {
-    int idx = 0;
-    uint32_t phase = 0;
-    __device__ __forceinline__ void advance(int n) {
-        if (++idx == n) {
-            idx = 0;
-            phase ^= 1u;
-        }
-    }
-};
-
-// unit u -> (pair, model tile): prefix[b] = number of model tiles of the pairs before b
-__device__ __forceinline__ void unit_of(const int* prefix, int B, int u, int& b, int& mt) {
-    int lo = 0, hi = B;   // largest b with prefix[b] <= u
-    while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (prefix[mid] <= u) lo = mid; else hi = mid;
-    }
-    b = lo;
-    mt = u - prefix[lo];
-}
 
 // ---- launch 1: correspondences -> operand images ------------------------------------------------------
 // images[b][t] = the kABytes image of correspondences [128 t, 128 t + 128) of pair b; rows past N are zero
@@ -435,9 +362,20 @@ static int tc_sm_count() {
 
 using namespace drb;
 
+namespace drb {
+namespace tc2 {   // score_tc2.cu: the model-stationary arrangement
+size_t workspace_bytes(int B, int N);
+int dispatch(bool bf16, bool e16, const float* matches, const float* models, const int32_t* count, const int32_t* ids,
+             const float* thr, int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images,
+             cudaStream_t s);
+}  // namespace tc2
+}  // namespace drb
+
 extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
-    return (size_t)B * ((N + tc::kTileM - 1) / tc::kTileM) * tc::kABytes;
+    const size_t v1 = (size_t)B * ((N + tc::kTileM - 1) / tc::kTileM) * tc::kABytes;
+    const size_t v2 = tc2::workspace_bytes(B, N);     // tiles of 80 correspondences: a different padding
+    return v1 > v2 ? v1 : v2;
 }
 
 namespace drb {
@@ -469,12 +407,13 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
         (reinterpret_cast<uintptr_t>(matches) & 15))
         return DRB_ERR_BAD_SHAPE;
     // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair; + 32 = 16 epilogue warps instead
-    // of 8 (the last two not yet measured on hardware)
+    // of 8; + 64 = the model-stationary arrangement of score_tc2.cu (the last three not yet measured on hardware)
     const int split = words & 15;
-    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0;
-    if ((split != 2 && split != 3) || (words & ~63)) return DRB_ERR_UNSUPPORTED;
+    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0;
+    if ((split != 2 && split != 3) || (words & ~127) || (v2 && pair)) return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
+    if (v2) return tc2::dispatch(split == 3, e16, matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
 #define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
 #define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16>(DRB_TC_ARGS) : tc::launch<BF, PR, 8>(DRB_TC_ARGS))
     if (pair) return split == 3 ? DRB_TC_PICK(true, true) : DRB_TC_PICK(false, true);

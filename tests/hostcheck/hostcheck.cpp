@@ -350,6 +350,77 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
     }
     return 0;
 }
+// ---- model-stationary arrangement (score_tc2.cu): A = the models' words in tensor memory (lane = model,
+// column = K index, 16-bit elements two per column), B = a tile of 80 correspondences read through the descriptor,
+// two MMAs per K step (r and j), epilogue lane = model summing over its columns.
+int hc_msac_tc2_scores(const float* matches, int N, const float* models, int M, float thr, int words, float* scores) {
+    using namespace drb::tc;
+    const bool bf16 = (words & 15) == 3;
+    const int kPts = 80, kPtBytes = (kPts / 8) * kSBO;
+    const uint32_t idesc = instr_desc_mn(128, kPts, bf16);
+    if (((int)((idesc >> 17) & 0x3f) << 3) != kPts || ((int)((idesc >> 24) & 0x1f) << 4) != 128) return -1;
+    const uint32_t fmt = bf16 ? 1u : 2u;
+    if (((idesc >> 4) & 3) != 1 || ((idesc >> 7) & 7) != fmt || ((idesc >> 10) & 7) != fmt || ((idesc >> 15) & 3) != 0) return -2;
+    const int step_k = bf16 ? 16 : 8;
+    const uint32_t p_addr = 0x800;
+    std::vector<uint32_t> smem((p_addr + kPtBytes) / 4, 0u);
+    const int tiles = (N + kPts - 1) / kPts;
+    const float th = 1.5f * thr, nci = -1.f / (th * th);
+    for (int m0 = 0; m0 < M; m0 += 128) {
+        // builders: 48 columns of words per model and type
+        std::vector<uint32_t> tm_r(128 * kK), tm_j(128 * kK);
+        for (int i = 0; i < 128; ++i) {
+            float m[9], cr[kFeat], cj[kFeat];
+            for (int q = 0; q < 9; ++q) m[q] = (m0 + i < M) ? models[(size_t)(m0 + i) * 9 + q] : 0.f;
+            model_rows(m, m0 + i < M, false, cr, cj);
+            operand_row_words(cr, false, bf16, &tm_r[i * kK]);
+            operand_row_words(cj, false, bf16, &tm_j[i * kK]);
+        }
+        auto a_elem = [&](const std::vector<uint32_t>& tm, int lane, int col0, int kk) -> float {
+            // K step starting at column col0: element kk -> column col0 + kk (32-bit) or col0 + kk / 2 (16-bit)
+            if (bf16) {
+                const uint32_t w = tm[lane * kK + col0 + kk / 2];
+                return bf16_value((uint16_t)((kk & 1) ? (w >> 16) : (w & 0xffffu)));
+            }
+            float f;
+            std::memcpy(&f, &tm[lane * kK + col0 + kk], 4);
+            return f;
+        };
+        std::vector<float> sum(128, 0.f);
+        for (int t = 0; t < tiles; ++t) {
+            for (int row = 0; row < kPts; ++row) {
+                const int n = t * kPts + row;
+                uint32_t row48[kK];
+                if (n < N) {
+                    float f[kFeat];
+                    features(matches[n * 4], matches[n * 4 + 1], matches[n * 4 + 2], matches[n * 4 + 3], f);
+                    operand_row_words(f, true, bf16, row48);
+                } else {
+                    for (int k = 0; k < kK; ++k) row48[k] = 0u;
+                }
+                for (int k = 0; k < kK; ++k) smem[p_addr / 4 + image_index(row, k)] = row48[k];
+            }
+            const uint64_t bdesc = smem_desc(p_addr);
+            for (int lane = 0; lane < 128; ++lane)
+                for (int c = 0; c < kPts; ++c) {
+                    float r = 0.f, j = 0.f;
+                    for (int s = 0; s < kKSteps; ++s) {
+                        const uint64_t bd = smem_desc_kstep(bdesc, s);
+                        for (int kk = 0; kk < step_k; ++kk) {
+                            const float p = desc_fetch(smem, bd, c, kk, bf16);
+                            r += a_elem(tm_r, lane, 8 * s, kk) * p;
+                            j += a_elem(tm_j, lane, 8 * s, kk) * p;
+                        }
+                    }
+                    float v = ((r * r) * (1.f / j)) * nci + 1.f;
+                    v = (v != v) ? 0.f : (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));   // FFMA.SAT (NaN -> 0: rows past N)
+                    sum[lane] += v;
+                }
+        }
+        for (int i = 0; i < 128 && m0 + i < M; ++i) scores[m0 + i] = sum[i];
+    }
+    return 0;
+}
 uint32_t hc_tc_instr_desc_bf16(void) { return drb::tc::instr_desc_bf16(); }
 // w0 + w1 + w2 of the BF16 split (exactness check)
 double hc_tc_bf16_sum(float x) {

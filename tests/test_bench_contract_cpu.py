@@ -45,3 +45,17 @@ def test_cuda_arm_needs_a_device():
         return
     p = _run("--steps", "1", "--warmup", "0")
     assert p.returncode != 0 and "no CPU fallback" in (p.stderr + p.stdout)
+
+
+def test_tensor_side_arithmetic():
+    """The tcgen05 figures bench.py adds for the tensor-core scorer: pure arithmetic, checked on the cfg2 numbers
+    measured on the B200 (138 910 models x 2000 correspondences in 0.122 ms)."""
+    import bench
+
+    t = bench.tensor_side(138910, 2000, 0.122, "tc_tf32")
+    tiles = 16 * 1086
+    assert abs(t["tensor_tflops"] - tiles * 6 * 2 * 128 * 256 * 8 / 0.122e-3 / 1e12) < 1e-6
+    assert 0.1 < t["tensor_frac"] < 1.0
+    b = bench.tensor_side(138910, 2000, 0.122, "tc_bf16")
+    assert abs(b["tensor_tflops"] / t["tensor_tflops"] - 2.0) < 1e-9 and b["tensor_peak_tflops"] == 2 * t["tensor_peak_tflops"]
+    assert "unavailable" in bench.tensor_side(1, 1, 0.0, "tc_tf32")["tensor_note"]

@@ -369,3 +369,30 @@ def test_msac_tc_bf16_split_is_exact(lib):
                          np.array([0.0, 1.0, -1.0, 1 / 3, 0.1, 1e-3, 123456.789], dtype=np.float32)])
     for x in xs.astype(np.float32):
         assert lib.hc_tc_bf16_sum(ctypes.c_float(float(x))) == float(x)
+
+
+@pytest.mark.parametrize("words", [2, 3])
+@pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (80, 20)])
+def test_msac_tc2_model_stationary_arrangement(lib, N, K, words):
+    """Host model of csrc/score_tc2.cu: the models' words in tensor-memory order against correspondence tiles of
+    80 rows read through the shared-memory descriptor (instruction shape 128 x 80), rows past N contributing 0."""
+    from differentiable_ransac_b200 import synth
+    from oracle import scoring
+
+    matches, _, _ = synth.relative_pose_batch(1, N, seed=78, noise=5e-4)
+    matches = matches[0]
+    g = torch.Generator().manual_seed(N + 1)
+    idx = torch.stack([torch.randperm(N, generator=g)[:5] for _ in range(K)])
+    inl = torch.arange(N - int(0.3 * N), N)
+    idx[: K // 3] = inl[torch.stack([torch.randperm(len(inl), generator=g)[:5] for _ in range(K // 3)])]
+    E = nister.five_point(matches[idx].double())
+    E = E[trace_constraint_residual(E) < 1e-8].float()
+    thr = 0.75 / 800.0
+    want, _ = scoring.msac_score(matches.double(), E.double(), thr)
+    m = np.ascontiguousarray(matches.numpy().astype(np.float32))
+    md = np.ascontiguousarray(E.reshape(-1, 9).numpy().astype(np.float32))
+    out = np.full(md.shape[0], -1.0, dtype=np.float32)
+    assert lib.hc_msac_tc2_scores(vp(m), N, vp(md), md.shape[0], ctypes.c_float(thr), words, vp(out)) == 0
+    rel = (torch.from_numpy(out).double() - want).abs() / want.clamp_min(1.0)
+    assert rel.max() < (1e-4 if words == 2 else 3e-5), rel.max()
+    assert int(out.argmax()) == int(want.argmax())
