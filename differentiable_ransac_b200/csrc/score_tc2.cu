@@ -3,10 +3,10 @@
 // NOT yet run on hardware).
 //
 // Same contraction and the same reference lines as score_tc.cu (scorings/msac_score.py:12-55, ransac.py:114;
-// operands by msac_tc_layout.cuh), with the roles of the two operands swapped.  Why: ncu on score_tc.cu shows the
-// tensor pipe busy 86 % of the time although its arithmetic needs 46 % -- 238 cycles per 128 x 256 x 8 MMA instead
-// of 128.  Both operands come from shared memory there (12 KB per MMA, 72 KB per tile of 128 x 128 pairs), and the
-// model operand -- 48 KB, the larger one -- is read again for every tile of correspondences although it does not
+// operands by msac_tc_layout.cuh), with the roles of the two operands swapped.  Why: in score_tc.cu both operands
+// of every MMA come from shared memory (12 KB per MMA, 72 KB per tile of 128 x 128 pairs; ncu: the tensor core's
+// shared-memory operand path at 33 % of its peak) and the model operand -- 48 KB, the larger one -- is read again
+// for every tile of correspondences although it does not
 // change within a unit.  Here a unit's 128 models are written ONCE into tensor memory (tcgen05.st from the
 // registers of the warps that compute the coefficient words; no shared-memory image of the models exists) and
 // serve as the A operand of every MMA of the unit; only the 15 KB tile of 80 correspondences is read from shared
