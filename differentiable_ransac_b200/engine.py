@@ -332,6 +332,8 @@ class E5TestService:
         self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
         # one slot: whatever a single call uses (ops default); several: SERVICE_SCORER unless the caller says
         self.scorer = scorer if scorer is not None else (SERVICE_SCORER if int(slots) > 1 else None)
+        if scorer is None and self.scorer is not None and self.scorer.startswith("tc") and int(B) > 1024:
+            self.scorer = "block"      # drb_score_msac_tc takes at most 1024 pairs per call (its unit table)
         self.graph = bool(graph)
         # host_io=False: batches are already on the device -- submit(slot, packed=<device tensor>) copies the
         # packed batch into the slot (device to device) and results stay on the device (`dev_out[slot]`)
