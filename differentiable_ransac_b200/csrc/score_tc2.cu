@@ -114,26 +114,7 @@ score_msac_tc2_kernel(const uint32_t* __restrict__ images, const float* __restri
         fence_barrier_init();
         fence_proxy_async();
     }
-    if (warp == kWarpEpi0) {
-        int carry = 0;
-        for (int base = 0; base < B; base += 32) {
-            const int b = base + lane;
-            int v = 0;
-            if (b < B) {
-                const int cnt = count ? min(__ldg(count + b), M) : M;
-                v = (max(cnt, 0) + kModels - 1) / kModels;
-            }
-            int inc = v;
-            DRB_UNROLL
-            for (int o = 1; o < 32; o <<= 1) {
-                const int up = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += up;
-            }
-            if (b < B) prefix[b] = carry + inc - v;
-            carry += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) prefix[B] = carry;
-    }
+    if (warp == kWarpEpi0) unit_prefix(prefix, count, B, M, kModels, lane);
     if (warp == kWarpMma) tmem_alloc(tmem_ptr, kTmemCols);
     tc_fence_before();
     __syncthreads();

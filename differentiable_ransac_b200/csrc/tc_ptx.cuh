@@ -73,6 +73,30 @@ struct Ring {
     }
 };
 
+// One warp: prefix[b] = number of units (tiles of `per_unit` models) of the pairs before b, prefix[B] = all units;
+// count[b] (nullable: M) models per pair.  32 pairs per round.
+__device__ __forceinline__ void unit_prefix(int* prefix, const int32_t* __restrict__ count, int B, int M, int per_unit,
+                                            int lane) {
+    int carry = 0;
+    for (int base = 0; base < B; base += 32) {
+        const int b = base + lane;
+        int v = 0;
+        if (b < B) {
+            const int cnt = count ? min(__ldg(count + b), M) : M;
+            v = (max(cnt, 0) + per_unit - 1) / per_unit;
+        }
+        int inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += up;
+        }
+        if (b < B) prefix[b] = carry + inc - v;
+        carry += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0) prefix[B] = carry;
+}
+
 // unit u -> (pair, model tile): prefix[b] = number of model tiles of the pairs before b
 __device__ __forceinline__ void unit_of(const int* prefix, int B, int u, int& b, int& mt) {
     int lo = 0, hi = B;   // largest b with prefix[b] <= u
