@@ -32,6 +32,38 @@ def _noise_args(noise, seed, offset):
     return dict(noise=noise, seed=int(seed), offset=int(offset))
 
 
+_TC_CHECKED = {}
+
+
+def tc_scorer_agrees(device, scorer="tc_tf32", tol=5e-4):
+    """One-off check (cached per device and scorer) that the tensor-core scorer reproduces the FP32 kernel on a
+    small random problem -- scores within `tol` relative, same or equally good winners.  The pipelined service
+    runs it before it adopts a "tc*" scorer BY DEFAULT and stays on the FP32 block kernel (with a warning) if it
+    fails; an explicitly requested scorer is never second-guessed."""
+    key = (str(device), scorer)
+    if key in _TC_CHECKED:
+        return _TC_CHECKED[key]
+    ok = False
+    try:
+        gen = torch.Generator().manual_seed(1234)
+        B, M, N = 2, 200, 300
+        matches = (torch.rand(B, N, 4, generator=gen) - 0.5).to(device)
+        models = torch.randn(B, M, 3, 3, generator=gen)
+        models = (models / models.flatten(-2).norm(dim=-1)[..., None, None]).to(device)
+        thr = torch.full((B,), 0.02).to(device)
+        s_ref, _ = ops.score_msac(matches, models, thr, kernel="block")
+        s_tc, _ = ops.score_msac(matches, models, thr, kernel=scorer)
+        rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0)).max()
+        ok = bool(torch.isfinite(s_tc).all()) and float(rel) < tol and float(s_ref.max()) > 1.0
+    except Exception as e:          # a scorer that cannot even run is a failed check
+        import warnings
+
+        warnings.warn(f"tensor-core scorer {scorer!r} could not be checked: {e}")
+        ok = False
+    _TC_CHECKED[key] = ok
+    return ok
+
+
 # ---- test mode ---------------------------------------------------------------------------------
 def _draw(logits, K, s, tau, noise, seed, offset, sampler, offset_dev=None):
     """Test-mode sampling: injected noise -> exact Gumbel keys (bit-exact with the reference);
@@ -332,8 +364,15 @@ class E5TestService:
         self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
         # one slot: whatever a single call uses (ops default); several: SERVICE_SCORER unless the caller says
         self.scorer = scorer if scorer is not None else (SERVICE_SCORER if int(slots) > 1 else None)
-        if scorer is None and self.scorer is not None and self.scorer.startswith("tc") and int(B) > 1024:
-            self.scorer = "block"      # drb_score_msac_tc takes at most 1024 pairs per call (its unit table)
+        if scorer is None and self.scorer is not None and self.scorer.startswith("tc"):
+            if int(B) > 1024:
+                self.scorer = "block"      # drb_score_msac_tc takes at most 1024 pairs per call (its unit table)
+            elif not tc_scorer_agrees(device, self.scorer):
+                import warnings
+
+                warnings.warn(f"{self.scorer!r} disagrees with the FP32 kernel on this device: the service scores "
+                              "with the FP32 block kernel instead")
+                self.scorer = "block"
         self.graph = bool(graph)
         # host_io=False: batches are already on the device -- submit(slot, packed=<device tensor>) copies the
         # packed batch into the slot (device to device) and results stay on the device (`dev_out[slot]`)
