@@ -491,7 +491,7 @@ def run_ours(args):
                        "serial_ms_per_step and the roofline pass: L2 flushed by a 256 MB write before each launch; "
                        "e2e re-copies its inputs from the host every step",
                     value_streams=S, value_graph=bool(args.value_graph), serial_ms_per_step=ms_serial,
-                    scorer=msac_name,
+                    scorer=f"{msac_name} ({msac_kernel})",
                     e2e_mode=f"engine.E5TestService(graph={bool(args.e2e_graph)}), {args.e2e_slots} batches in flight "
                              "(one stream each; a CUDA graph per slot when graph=True): packed H2D per step, one packed D2H of (model, id, score, #inliers) "
                              "per step, results read on the host before a slot is reused",

@@ -18,14 +18,17 @@ import os
 from . import ops
 
 # Scorer of the pipelined service (E5TestService with more than one slot):
-#   "tc_tf32"  tensor cores, two TF32 words per operand (csrc/score_tc.cu) -- the default: measured on B200 at cfg2
-#              0.175 ms per pipelined batch against 0.254 ms with "block" (profiles/r1_notes.md); per-model scores
-#              within 1.4e-4 relative of the FP32 kernels (the winner's score: ~1e-6), so the winner can differ from
-#              the FP32 kernels' only between near-ties
+#   "auto"     (default) the most precise tensor-core variant that verifies itself on this device -- "tc_bf16", then
+#              "tc_tf32" -- else "block"; see service_scorer()
+#   "tc_tf32"  tensor cores, two TF32 words per operand (csrc/score_tc.cu): measured on B200 at cfg2 0.175 ms per
+#              pipelined batch against 0.254 ms with "block" (profiles/r1_notes.md); per-model scores within 1.4e-4
+#              relative of the FP32 kernels (the winner's score: ~1e-6), so the winner can differ from the FP32
+#              kernels' only between near-ties
+#   "tc_bf16"  three BF16 words per operand: exact operands, fp32-level scores (5e-6 against fp64 on the host model),
+#              same time
 #   "block"    FP32, one CTA per 32 models; bit-identical to what `ransac_e5_test(scorer="block")` returns
-#   "stream"   FP32 work queue;  "tc_bf16": three BF16 words (fp32-level scores on the host model; validate with
-#              DRB_EXPERIMENTAL=1 pytest tests/test_gpu_score_tc.py before making it the default)
-SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "tc_tf32")
+#   "stream"   FP32 work queue
+SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "auto")
 
 
 def _noise_args(noise, seed, offset):
@@ -36,21 +39,22 @@ _TC_CHECKED = {}
 
 
 def tc_scorer_agrees(device, scorer="tc_tf32", tol=5e-4):
-    """One-off check (cached per device and scorer) that the tensor-core scorer reproduces the FP32 kernel on a
-    small random problem -- scores within `tol` relative, same or equally good winners.  The pipelined service
-    runs it before it adopts a "tc*" scorer BY DEFAULT and stays on the FP32 block kernel (with a warning) if it
-    fails; an explicitly requested scorer is never second-guessed."""
+    """One-off check (cached per device and scorer) that a tensor-core scorer reproduces the FP32 kernel on a
+    problem built to expose a broken operand split: 256 random models x 4000 random correspondences with a tight
+    threshold (1e-3), where losing the second-order partial products of the BF16 split moves scores by 5e-3 and a
+    correct split by < 1e-4 (profiles/r1_notes.md).  Scores within `tol` relative (floor 1.0) of the FP32 block
+    kernel's."""
     key = (str(device), scorer)
     if key in _TC_CHECKED:
         return _TC_CHECKED[key]
     ok = False
     try:
         gen = torch.Generator().manual_seed(1234)
-        B, M, N = 2, 200, 300
+        B, M, N = 2, 256, 4000
         matches = (torch.rand(B, N, 4, generator=gen) - 0.5).to(device)
         models = torch.randn(B, M, 3, 3, generator=gen)
         models = (models / models.flatten(-2).norm(dim=-1)[..., None, None]).to(device)
-        thr = torch.full((B,), 0.02).to(device)
+        thr = torch.full((B,), 1e-3).to(device)
         s_ref, _ = ops.score_msac(matches, models, thr, kernel="block")
         s_tc, _ = ops.score_msac(matches, models, thr, kernel=scorer)
         rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0)).max()
@@ -62,6 +66,28 @@ def tc_scorer_agrees(device, scorer="tc_tf32", tol=5e-4):
         ok = False
     _TC_CHECKED[key] = ok
     return ok
+
+
+def service_scorer(device, B, requested=None):
+    """The scorer a pipelined service uses: `requested` (or SERVICE_SCORER) if it names one; "auto" -> the first of
+    "tc_bf16", "tc_tf32" that agrees with the FP32 kernel on this device (tc_scorer_agrees), else "block".  A
+    tensor-core scorer named by SERVICE_SCORER is checked the same way and replaced by "block" (with a warning) if
+    it fails; one passed explicitly by the caller is taken as is.  drb_score_msac_tc takes at most 1024 pairs."""
+    if requested is not None:
+        return requested
+    name = SERVICE_SCORER
+    if name != "auto" and not name.startswith("tc"):
+        return name
+    if int(B) > 1024:
+        return "block"
+    for cand in (("tc_bf16", "tc_tf32") if name == "auto" else (name,)):
+        if tc_scorer_agrees(device, cand):
+            return cand
+    import warnings
+
+    warnings.warn("no tensor-core scorer agrees with the FP32 kernel on this device: the service scores with the "
+                  "FP32 block kernel")
+    return "block"
 
 
 # ---- test mode ---------------------------------------------------------------------------------
@@ -362,17 +388,8 @@ class E5TestService:
 
     def __init__(self, B, N, K, device, slots=2, seed=0, graph=False, host_io=True, scorer=None):
         self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
-        # one slot: whatever a single call uses (ops default); several: SERVICE_SCORER unless the caller says
-        self.scorer = scorer if scorer is not None else (SERVICE_SCORER if int(slots) > 1 else None)
-        if scorer is None and self.scorer is not None and self.scorer.startswith("tc"):
-            if int(B) > 1024:
-                self.scorer = "block"      # drb_score_msac_tc takes at most 1024 pairs per call (its unit table)
-            elif not tc_scorer_agrees(device, self.scorer):
-                import warnings
-
-                warnings.warn(f"{self.scorer!r} disagrees with the FP32 kernel on this device: the service scores "
-                              "with the FP32 block kernel instead")
-                self.scorer = "block"
+        # one slot: whatever a single call uses (ops default); several: service_scorer() unless the caller says
+        self.scorer = scorer if (scorer is not None or int(slots) <= 1) else service_scorer(device, B)
         self.graph = bool(graph)
         # host_io=False: batches are already on the device -- submit(slot, packed=<device tensor>) copies the
         # packed batch into the slot (device to device) and results stay on the device (`dev_out[slot]`)

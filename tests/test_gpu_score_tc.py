@@ -1,7 +1,7 @@
 """GPU tests of the tensor-core soft-MSAC scorer (drb_score_msac_tc, csrc/score_tc.cu) against the CPU oracle
 (oracle/scoring.py <- scorings/msac_score.py:12-55) and the FP32 kernel (drb_score_msac).
 
-Two tiers.  (1) The TF32 variant ("tc_tf32", the pipelined service's default) ran on a B200 at the end of round 1
+Two tiers.  (1) The TF32 variant ("tc_tf32") ran on a B200 at the end of round 1
 (profiles/r1_score_tc_first_contact.jsonl): its cases here are the ones measured then, with the tolerance the
 3xTF32 split allows.  (2) Everything else -- the BF16 variant beyond one small case, the oracle-level 1e-4 bar at
 the headline size -- has NOT been confirmed on hardware yet and is opt-in: DRB_EXPERIMENTAL=1, each case in a
