@@ -396,3 +396,16 @@ def test_msac_tc2_model_stationary_arrangement(lib, N, K, words):
     rel = (torch.from_numpy(out).double() - want).abs() / want.clamp_min(1.0)
     assert rel.max() < (1e-4 if words == 2 else 3e-5), rel.max()
     assert int(out.argmax()) == int(want.argmax())
+
+
+@pytest.mark.parametrize("words", [2, 3, 3 + 16])
+def test_msac_tc_against_the_reference_golden(lib, golden, words):
+    """The tensor-core operand path (host model of csrc/score_tc.cu) against the scores the REFERENCE's own
+    MSACScore.score produced (tests/golden/msac.npz, generated by importing scorings/msac_score.py): same
+    scores within the path's 1e-4 relative bar, same arg-max."""
+    g = golden("msac")
+    got = _tc_scores(lib, g["matches"], g["models"], float(g["threshold"]), words)
+    want = g["scores"]
+    rel = (got - want).abs() / want.clamp_min(1.0)
+    assert float(rel.max()) < 1e-4, float(rel.max())
+    assert int(got.argmax()) == int(g["best"])
