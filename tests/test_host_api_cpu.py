@@ -67,3 +67,48 @@ def test_no_cpu_fallback():
 
     with pytest.raises(_lib.DrbError):
         ops.sample(torch.zeros(1, 16), 4, 5)
+
+
+def test_service_scorer_selection_logic(monkeypatch):
+    """engine.service_scorer / tc_scorer_agrees with a stand-in for the CUDA scorers: "auto" adopts the first
+    tensor-core variant whose scores agree with the FP32 kernel's, falls back to "block" (with a warning) when none
+    does, never second-guesses an explicit request, and keeps batches of more than 1024 pairs on "block"."""
+    import types
+    import warnings
+
+    import torch
+
+    from differentiable_ransac_b200 import engine
+
+    def reference_scores(matches, models, thr):
+        B, N, _ = matches.shape
+        m = models.reshape(B, -1, 3, 3)
+        one = torch.ones(B, N, 1)
+        x1, x2 = torch.cat([matches[..., :2], one], -1), torch.cat([matches[..., 2:], one], -1)
+        mx = torch.einsum("bmij,bnj->bmni", m, x1)
+        mtx = torch.einsum("bmji,bnj->bmni", m, x2)
+        r = (mx * x2[:, None]).sum(-1)
+        j = (mx[..., :2] ** 2).sum(-1) + (mtx[..., :2] ** 2).sum(-1)
+        t = (1.5 * thr)[:, None, None] ** 2
+        return (1 - (r * r / j) / t).clamp(0, 1).sum(-1)
+
+    def stand_in(bad):
+        def score_msac(matches, models, thr, kernel=None, **kw):
+            s = reference_scores(matches, models, thr)
+            return s * (1.01 if kernel in bad else 1.0 + 2e-5 if kernel != "block" else 1.0), None
+        return types.SimpleNamespace(score_msac=score_msac)
+
+    monkeypatch.setattr(engine, "SERVICE_SCORER", "auto")
+    for bad, want in ((set(), "tc_bf16"), ({"tc_bf16"}, "tc_tf32"), ({"tc_bf16", "tc_tf32"}, "block")):
+        monkeypatch.setattr(engine, "ops", stand_in(bad))
+        monkeypatch.setattr(engine, "_TC_CHECKED", {})
+        with warnings.catch_warnings(record=True) as caught:
+            warnings.simplefilter("always")
+            assert engine.service_scorer("cpu", 32) == want
+        assert bool(caught) == (want == "block")
+    monkeypatch.setattr(engine, "ops", stand_in(set()))
+    monkeypatch.setattr(engine, "_TC_CHECKED", {})
+    assert engine.service_scorer("cpu", 32, "stream") == "stream"          # explicit request
+    assert engine.service_scorer("cpu", 2000) == "block"                   # more pairs than the unit table holds
+    monkeypatch.setattr(engine, "SERVICE_SCORER", "block")
+    assert engine.service_scorer("cpu", 32) == "block"
