@@ -506,7 +506,8 @@ def run_ours(args):
                       note=("FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops" if launches_per_step == 4 else
                             "not HBM bound: the contraction runs on tcgen05 (operands split into TF32 / BF16 words), the "
                             "epilogue is SFU-bound (ncu: XU pipe 67 %); fp32_tflops counts the 37 flop per (model, correspondence) of the FP32 formula "
-                            "as useful work, so it can exceed the FP32 pipe's peak (DESIGN.md section 10)"),
+                            "as useful work, so it can exceed the FP32 pipe's peak (DESIGN.md section 10); kernel_ms covers both "
+                            "launches of the call (operand images of the correspondences, then the scorer)"),
                       fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,
                       fp32_peak_tflops=FP32_PEAK_TFLOPS,
                       fp32_frac=flops_score / (score_ms / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
