@@ -345,9 +345,9 @@ using namespace drb;
 namespace drb {
 namespace tc2 {   // score_tc2.cu: the model-stationary arrangement
 size_t workspace_bytes(int B, int N);
-int dispatch(bool bf16, bool e16, const float* matches, const float* models, const int32_t* count, const int32_t* ids,
-             const float* thr, int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images,
-             cudaStream_t s);
+int dispatch(bool bf16, bool e16, bool pair, const float* matches, const float* models, const int32_t* count,
+             const int32_t* ids, const float* thr, int B, int M, int N, float* scores, unsigned long long* best_packed,
+             uint32_t* images, cudaStream_t s);
 }  // namespace tc2
 }  // namespace drb
 
@@ -390,10 +390,10 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     // of 8; + 64 = the model-stationary arrangement of score_tc2.cu (the last three not yet measured on hardware)
     const int split = words & 15;
     const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0;
-    if ((split != 2 && split != 3) || (words & ~127) || (v2 && pair)) return DRB_ERR_UNSUPPORTED;
+    if ((split != 2 && split != 3) || (words & ~127)) return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
-    if (v2) return tc2::dispatch(split == 3, e16, matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
+    if (v2) return tc2::dispatch(split == 3, e16, pair, matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
 #define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
 #define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16>(DRB_TC_ARGS) : tc::launch<BF, PR, 8>(DRB_TC_ARGS))
     if (pair) return split == 3 ? DRB_TC_PICK(true, true) : DRB_TC_PICK(false, true);

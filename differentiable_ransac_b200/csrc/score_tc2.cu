@@ -80,7 +80,7 @@ msac_tc2_features_kernel(const float* __restrict__ matches, int N, int tiles, ui
 }
 
 // ---- launch 2 -----------------------------------------------------------------------------------------
-template <bool BF16, int EPI>
+template <bool BF16, int EPI, bool PAIR>
 __global__ void __launch_bounds__(threads_of(EPI), 1)
 score_msac_tc2_kernel(const uint32_t* __restrict__ images, const float* __restrict__ models,
                       const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
@@ -258,13 +258,29 @@ score_msac_tc2_kernel(const uint32_t* __restrict__ images, const float* __restri
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
                 rd.advance(2);
-                DRB_UNROLL
-                for (int i = 0; i < kCols / 2; ++i) {
-                    const pk2 R = pk2_make(__uint_as_float(vr[2 * i]), __uint_as_float(vr[2 * i + 1]));
-                    const pk2 IJ = pk2_make(rcp_approx(__uint_as_float(vj[2 * i])), rcp_approx(__uint_as_float(vj[2 * i + 1])));
-                    float u0, u1;
-                    pk2_split(pk2_mul(pk2_mul(R, R), IJ), u0, u1);
-                    acc[i & 3] = pk2_add(acc[i & 3], pk2_make(fma_sat(u0, nci, 1.f), fma_sat(u1, nci, 1.f)));
+                // PAIR: one reciprocal per two neighbouring correspondences, (1/j0, 1/j1) = rcp(j0 j1) (j1, j0).  A row
+                // past N has r = j = 0 and would take its neighbour with it (0 * inf), so when N is odd the last
+                // tile -- the only place where a real and an absent correspondence share a pair -- takes the plain path.
+                const bool paired = PAIR && !((N & 1) && t == tiles - 1);
+                if (paired) {
+                    DRB_UNROLL
+                    for (int i = 0; i < kCols / 2; ++i) {
+                        const float j0 = __uint_as_float(vj[2 * i]), j1 = __uint_as_float(vj[2 * i + 1]);
+                        float q0, q1;
+                        const pk2 R = pk2_make(__uint_as_float(vr[2 * i]), __uint_as_float(vr[2 * i + 1]));
+                        pk2_split(pk2_mul(R, R), q0, q1);
+                        const float tn = rcp_approx(j0 * j1) * nci;
+                        acc[i & 3] = pk2_add(acc[i & 3], pk2_make(fma_sat(q0 * j1, tn, 1.f), fma_sat(q1 * j0, tn, 1.f)));
+                    }
+                } else {
+                    DRB_UNROLL
+                    for (int i = 0; i < kCols / 2; ++i) {
+                        const pk2 R = pk2_make(__uint_as_float(vr[2 * i]), __uint_as_float(vr[2 * i + 1]));
+                        const pk2 IJ = pk2_make(rcp_approx(__uint_as_float(vj[2 * i])), rcp_approx(__uint_as_float(vj[2 * i + 1])));
+                        float u0, u1;
+                        pk2_split(pk2_mul(pk2_mul(R, R), IJ), u0, u1);
+                        acc[i & 3] = pk2_add(acc[i & 3], pk2_make(fma_sat(u0, nci, 1.f), fma_sat(u1, nci, 1.f)));
+                    }
                 }
             }
             float lo, hi;
@@ -310,29 +326,31 @@ static int sm_count() {
 
 size_t workspace_bytes(int B, int N) { return (size_t)B * ((N + kPts - 1) / kPts) * kPtBytes; }
 
-template <bool BF16, int EPI>
+template <bool BF16, int EPI, bool PAIR>
 int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr, int B,
            int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc2_kernel<BF16, EPI>,
+    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc2_kernel<BF16, EPI, PAIR>,
                                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
     if (attr != cudaSuccess) return DRB_ERR_CUDA;
     const int tiles = (N + kPts - 1) / kPts;
     msac_tc2_features_kernel<BF16><<<dim3(tiles, B), 96, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kModels - 1) / kModels);
     const int grid = (int)(max_units < sm_count() ? max_units : sm_count());
-    score_msac_tc2_kernel<BF16, EPI><<<grid, threads_of(EPI), kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N,
+    score_msac_tc2_kernel<BF16, EPI, PAIR><<<grid, threads_of(EPI), kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N,
                                                                               tiles, scores, best_packed);
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
 
 // called by drb_score_msac_tc (score_tc.cu) for words + 64
-int dispatch(bool bf16, bool e16, const float* matches, const float* models, const int32_t* count, const int32_t* ids,
-             const float* thr, int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images,
-             cudaStream_t s) {
-    if (bf16) return e16 ? launch<true, 16>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s)
-                         : launch<true, 8>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
-    return e16 ? launch<false, 16>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s)
-               : launch<false, 8>(matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
+int dispatch(bool bf16, bool e16, bool pair, const float* matches, const float* models, const int32_t* count,
+             const int32_t* ids, const float* thr, int B, int M, int N, float* scores, unsigned long long* best_packed,
+             uint32_t* images, cudaStream_t s) {
+#define DRB_TC2_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
+#define DRB_TC2_PICK(BF, E) (pair ? launch<BF, E, true>(DRB_TC2_ARGS) : launch<BF, E, false>(DRB_TC2_ARGS))
+    if (bf16) return e16 ? DRB_TC2_PICK(true, 16) : DRB_TC2_PICK(true, 8);
+    return e16 ? DRB_TC2_PICK(false, 16) : DRB_TC2_PICK(false, 8);
+#undef DRB_TC2_PICK
+#undef DRB_TC2_ARGS
 }
 
 }  // namespace tc2

@@ -165,8 +165,8 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
  * touching its neighbour); words + 32: 16 epilogue warps per CTA instead of 8 (more warps to hide the latency of
  * the tensor-memory loads and the SFU); words + 64: the model-stationary arrangement of score_tc2.cu (a unit's
  * 128 models live in tensor memory as the A operand, only tiles of 80 correspondences pass through shared memory:
- * a third of the shared-memory operand traffic, one accumulator register per thread; combines with + 32, not with
- * + 16) -- none of the three measured on hardware yet.  B <= 1024; matches 16-byte aligned.  Needs a
+ * a third of the shared-memory operand traffic, one accumulator register per thread; with + 16 it pairs
+ * neighbouring correspondences instead of neighbouring models) -- none of the three measured on hardware yet.  B <= 1024; matches 16-byte aligned.  Needs a
  * 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents irrelevant on entry:
  * the call writes the operand images of the correspondences there first).                         */
 size_t drb_score_msac_tc_workspace_bytes(int B, int N);

@@ -33,7 +33,7 @@ print(json.dumps(dict(check="tc vs block", max_rel=float(rel.max()), same_best=i
       flush=True)
 
 for kern in ("block", "stream", "tc_tf32", "tc_bf16", "tc_tf32p", "tc_bf16p", "tc_tf32_e16", "tc_tf32p_e16", "tc_bf16p_e16",
-             "tc2_tf32", "tc2_tf32_e16", "tc2_bf16") * 2:
+             "tc2_tf32", "tc2_tf32_e16", "tc2_bf16", "tc2_tf32p", "tc2_tf32p_e16") * 2:
     for _ in range(3):
         ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=False, kernel=kern)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]

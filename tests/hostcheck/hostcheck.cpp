@@ -401,7 +401,9 @@ int hc_msac_tc2_scores(const float* matches, int N, const float* models, int M, 
                 for (int k = 0; k < kK; ++k) smem[p_addr / 4 + image_index(row, k)] = row48[k];
             }
             const uint64_t bdesc = smem_desc(p_addr);
-            for (int lane = 0; lane < 128; ++lane)
+            const bool paired = (words & 16) && !((N & 1) && t == tiles - 1);   // as the kernel decides
+            for (int lane = 0; lane < 128; ++lane) {
+                float rr[80], jj[80];
                 for (int c = 0; c < kPts; ++c) {
                     float r = 0.f, j = 0.f;
                     for (int s = 0; s < kKSteps; ++s) {
@@ -412,10 +414,24 @@ int hc_msac_tc2_scores(const float* matches, int N, const float* models, int M, 
                             j += a_elem(tm_j, lane, 8 * s, kk) * p;
                         }
                     }
-                    float v = ((r * r) * (1.f / j)) * nci + 1.f;
-                    v = (v != v) ? 0.f : (v < 0.f ? 0.f : (v > 1.f ? 1.f : v));   // FFMA.SAT (NaN -> 0: rows past N)
-                    sum[lane] += v;
+                    rr[c] = r;
+                    jj[c] = j;
                 }
+                for (int c = 0; c < kPts; c += 2) {
+                    float v0, v1;
+                    if (paired) {
+                        const float tn = (1.f / (jj[c] * jj[c + 1])) * nci;
+                        v0 = ((rr[c] * rr[c]) * jj[c + 1]) * tn + 1.f;
+                        v1 = ((rr[c + 1] * rr[c + 1]) * jj[c]) * tn + 1.f;
+                    } else {
+                        v0 = ((rr[c] * rr[c]) * (1.f / jj[c])) * nci + 1.f;
+                        v1 = ((rr[c + 1] * rr[c + 1]) * (1.f / jj[c + 1])) * nci + 1.f;
+                    }
+                    v0 = (v0 != v0) ? 0.f : (v0 < 0.f ? 0.f : (v0 > 1.f ? 1.f : v0));   // FFMA.SAT (NaN -> 0: rows past N)
+                    v1 = (v1 != v1) ? 0.f : (v1 < 0.f ? 0.f : (v1 > 1.f ? 1.f : v1));
+                    sum[lane] += v0 + v1;
+                }
+            }
         }
         for (int i = 0; i < 128 && m0 + i < M; ++i) scores[m0 + i] = sum[i];
     }

@@ -146,7 +146,7 @@ CASES = [
     (40, 200, 500, None),
 ]
 KERNELS = ["tc_bf16", "tc_tf32", "tc_bf16p", "tc_tf32p", "tc_tf32_e16", "tc_bf16p_e16", "tc2_tf32", "tc2_bf16",
-           "tc2_tf32_e16"]
+           "tc2_tf32_e16", "tc2_tf32p", "tc2_bf16p_e16"]
 
 
 @pytest.mark.parametrize("kernel", KERNELS)

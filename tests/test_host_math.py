@@ -371,8 +371,8 @@ def test_msac_tc_bf16_split_is_exact(lib):
         assert lib.hc_tc_bf16_sum(ctypes.c_float(float(x))) == float(x)
 
 
-@pytest.mark.parametrize("words", [2, 3])
-@pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (80, 20)])
+@pytest.mark.parametrize("words", [2, 3, 2 + 16])
+@pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (80, 20), (90, 20)])
 def test_msac_tc2_model_stationary_arrangement(lib, N, K, words):
     """Host model of csrc/score_tc2.cu: the models' words in tensor-memory order against correspondence tiles of
     80 rows read through the shared-memory descriptor (instruction shape 128 x 80), rows past N contributing 0."""
@@ -394,7 +394,7 @@ def test_msac_tc2_model_stationary_arrangement(lib, N, K, words):
     out = np.full(md.shape[0], -1.0, dtype=np.float32)
     assert lib.hc_msac_tc2_scores(vp(m), N, vp(md), md.shape[0], ctypes.c_float(thr), words, vp(out)) == 0
     rel = (torch.from_numpy(out).double() - want).abs() / want.clamp_min(1.0)
-    assert rel.max() < (1e-4 if words == 2 else 3e-5), rel.max()
+    assert rel.max() < (1e-4 if words & 15 == 2 else 3e-5), rel.max()
     assert int(out.argmax()) == int(want.argmax())
 
 
