@@ -156,19 +156,20 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
 /* The same contract with the contraction on the tensor cores (score_tc.cu; 0.122 ms
  * against 0.215 ms at the headline shape).  r = x2' M x1 and the Sampson denominator are two polynomials
  * in the correspondence's coordinates, i.e. inner products of 15 monomials with per-model coefficients; a
- * (128 correspondences x 128 models) tile is one 128 x 256 x 48 tcgen05 MMA (3xTF32 split operands, fp32
- * accumulation in tensor memory) and the CUDA cores keep r^2 / j -> clamp -> sum.  words = 2: operands split
- * into two TF32 words, three partial products (22-bit operands: scores within ~1.4e-4 relative of
- * drb_score_msac); words = 3: three BF16 words, six partial products (exact operands: fp32-level scores) for
- * the same MMA time; words + 16: one reciprocal per PAIR of neighbouring models, rcp(j0 j1) (j1, j0), which halves
- * the work of the pipe that bounds the kernel (a model with a non-finite coefficient then scores 0 without
- * touching its neighbour); words + 32: 16 epilogue warps per CTA instead of 8 (more warps to hide the latency of
- * the tensor-memory loads and the SFU); words + 64: the model-stationary arrangement of score_tc2.cu (a unit's
- * 128 models live in tensor memory as the A operand, only tiles of 80 correspondences pass through shared memory:
- * a third of the shared-memory operand traffic, one accumulator register per thread; with + 16 it pairs
- * neighbouring correspondences instead of neighbouring models) -- none of the three measured on hardware yet.  B <= 1024; matches 16-byte aligned.  Needs a
- * 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents irrelevant on entry:
- * the call writes the operand images of the correspondences there first).                         */
+ * (128 correspondences x 128 models) tile is one 128 x 256 x 48 tcgen05 MMA (split operands, fp32
+ * accumulation in tensor memory) and the CUDA cores keep r^2 / j -> clamp -> sum.  `words` selects the variant:
+ *    2   operands split into two TF32 words, three partial products (22-bit operands: scores within
+ *        ~1.4e-4 relative of drb_score_msac) -- measured on B200
+ *    3   three BF16 words, six partial products (exact operands: fp32-level scores), same MMA time
+ *  + 16  one reciprocal per PAIR of neighbouring models, rcp(j0 j1) (j1, j0): half the work of the pipe that
+ *        bounds the kernel; a model with a non-finite coefficient still scores 0 without touching its neighbour
+ *  + 32  16 epilogue warps per CTA instead of 8
+ *  + 64  the model-stationary arrangement of score_tc2.cu: a unit's 128 models live in tensor memory as the A
+ *        operand, only tiles of 80 correspondences pass through shared memory (a third of the operand traffic,
+ *        one accumulator register per thread); with + 16 it pairs neighbouring correspondences
+ * (+ 16 / + 32 / + 64 are built and host-checked, not yet measured on hardware.)  B <= 1024; matches 16-byte
+ * aligned.  Needs a 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents
+ * irrelevant on entry: the call writes the operand images of the correspondences there first).           */
 size_t drb_score_msac_tc_workspace_bytes(int B, int N);
 int drb_score_msac_tc(const float* matches, const float* models, const int32_t* count, const int32_t* ids,
                       const float* thr, int B, int M, int N, int words,
