@@ -17,7 +17,8 @@ noise = synth.gumbel_noise((B, K, N), seed=3)
 m, E, lg, thr, noise = m.to(DEV), E.to(DEV), lg.to(DEV), thr.to(DEV), noise.to(DEV)
 for kw in (dict(), dict(noise=noise), dict(sampler="gumbel")):
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, **kw)
-for scorer in ("block", "stream"):       # both MSAC kernels; the queue kernel with a block cut into several pieces
+TC = os.environ.get("DRB_SANITIZE_TC", "tc_tf32,tc_bf16").split(",")   # add the unmeasured variants by hand: tc_tf32p, tc2_tf32, ...
+for scorer in ["block", "stream"] + [t for t in TC if t]:   # every MSAC kernel; the queue kernel with a block cut into pieces
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, scorer=scorer)
 svc = engine.E5TestService(B, N, K, DEV, slots=2, seed=1, graph=False, host_io=False)
 for _ in range(3):
