@@ -108,11 +108,14 @@ def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     ninl [B], idx [B,K,5], models [B,K,10,3,3], nsol [B,K] (, scores [B,K*10] in compact order,
     cids)).
 
-    scorer: "stream" (default; persistent work-queue kernel: lowest latency for one call, and it keeps every SM
+    scorer: "auto" (the tensor-core scorer the pipelined service would pick on this device),
+    "stream" (default; persistent work-queue kernel: lowest latency for one call, and it keeps every SM
     busy when there are few models) or "block" (one CTA per 32 models: its CTAs retire one by one, which lets
     the kernels of an independent call on another stream move in -- what pipelined callers want, see
     E5TestService)."""
     B = matches.shape[0]
+    if scorer == "auto":        # what the pipelined service would pick on this device (tensor cores when they verify)
+        scorer = service_scorer(matches.device, B, None if SERVICE_SCORER == "auto" else SERVICE_SCORER)
     idx = _draw(logits, K, 5, tau, noise, seed, offset, sampler, offset_dev)
     best0, cc0 = ops.zeroed_counters(B, matches.device)
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True, ccount=cc0)
