@@ -1,18 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the hypothesize-and-score hot path (BASELINE.json metric: hypotheses/sec,
-5PC-E, 2k correspondences x 1k hypotheses, 32 pairs per GPU).
+"""Benchmark of the hypothesize-and-score hot path (BASELINE.json metric: hypotheses/sec).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config cfg2|cfg1|cfg3|cfg4|cfg5]
 
-One "step" = one pass of the hot path over one batch of synthetic pairs: Gumbel top-5 sampling
-(in-kernel Philox, fresh offset every step) -> Nister 5-point on every sample -> Sampson/MSAC
-score of every model against every correspondence -> arg-max + winner mask.  Prints ONE JSON
-line (rank 0).  `value` has the inputs resident in HBM; `e2e` goes through the public API with
-pinned-host inputs and a device->host read of the result inside the timed region.
+Default `--config cfg2` is the headline: 5PC-E (Nister), 32 pairs x 1000 hypotheses x 2000 correspondences per
+GPU, forward only.  One "step" = one pass of the hot path over one batch of synthetic pairs.  Prints ONE JSON line
+(rank 0).  `value` has the inputs resident in HBM; `e2e` goes through the reference-facing plugin
+(`model_cl.RANSACLayer`) with pinned-HOST tensors in and host results out, copies inside the timed region.
 
---impl reference times the reference's own algorithm on the host cores: the CPU oracle
-(`oracle/`, a line-cited restatement of the reference's PyTorch path, pinned to the reference
-by tests/golden) -- /root/reference does not exist on the GPU box.
+    cfg1  Essential 5PC Stewenius, 1 pair x 100 hyps x 2000 corrs          (the reference's own CPU-runnable case)
+    cfg2  Essential 5PC Nister, 32 x 1000 x 2000, fwd only                 (headline)
+    cfg3  Fundamental 8PC, 64 x 2000 x 2000, fwd + bwd training step (epipolar loss)
+    cfg4  Rigid 3-point, 16 x 1000 x 50 000, fwd + bwd of the mean residual
+    cfg5  Essential 5PC training, 32 pairs per GPU x 1000 x 2000 fwd + bwd, + the NCCL all-reduce of a
+          CLNet-sized (2.49 MB) gradient buffer at --gpus > 1
+
+--impl reference times the UNMODIFIED reference (oracle/_ref, copied by oracle/make_ref.py in the build container;
+/root/reference does not exist on the GPU box) on the host cores through its own public entry
+(`model_cl.RANSACLayer.forward`), falling back to the CPU oracle port when oracle/_ref is absent.
 """
 from __future__ import annotations
 
@@ -23,6 +28,7 @@ import subprocess
 import sys
 import threading
 import time
+import types
 
 import torch
 
@@ -35,9 +41,24 @@ WORKLOAD = dict(B=32, K=1000, N=2000, sample_size=5, slots=10, threshold_px=0.75
 ALGO_BYTES_PER_HYP = 442.0
 WORKLOAD_NAME = ("cfg2: Essential 5PC (Nister), 32 pairs x 1000 hyps x 2000 corrs per GPU, fwd only, "
                  "test-mode semantics (sample -> solve -> MSAC -> arg-max + winner mask)")
+CONFIGS = {
+    "cfg1": dict(kind="e5", mode="test", B=1, K=100, N=2000,
+                 name="cfg1: Essential 5PC Stewenius, 1 pair x 100 hyps x 2000 corrs, loop body (sample -> solve -> MSAC)"),
+    "cfg2": dict(kind="e5", mode="test", B=32, K=1000, N=2000, name=WORKLOAD_NAME),
+    "cfg3": dict(kind="f8", mode="train", B=64, K=2000, N=2000,
+                 name="cfg3: Fundamental 8PC, 64 pairs x 2000 hyps x 2000 corrs per GPU, fwd + bwd training step "
+                      "(loss.py epipolar MatchLoss on the GT inliers, gradient to the sampling weights)"),
+    "cfg4": dict(kind="rigid", mode="train", B=16, K=1000, N=50000,
+                 name="cfg4: Rigid 3-point SVD (3DMatch shape), 16 x 1000 hyps x 50 000 corrs per GPU, train-mode "
+                      "forward + backward of the mean squared residual"),
+    "cfg5": dict(kind="e5", mode="train", B=32, K=1000, N=2000,
+                 name="cfg5: Essential 5PC training, 32 pairs per GPU x 1000 hyps x 2000 corrs (256 pairs over 8 GPUs), "
+                      "fwd + bwd (closest-to-GT slot, MatchLoss), NCCL all-reduce of a CLNet-sized gradient buffer"),
+}
+CLNET_PARAMS = 622_616          # the weight network's parameter count = the all-reduced gradient (2.49 MB)
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12   # non-tensor FP32 FMA peak of a B200 at its 1965 MHz boost: 74.4
+XU_PEAK_GOPS = 148 * 16 * 1.965                     # MUFU results per ns: 16 lanes per SM per clock
 REF_BUDGET_S = 150.0      # the reference arm sizes its per-step sample so that the whole run stays below this
-ALGO_FLOP_PER_HYP = 0.82e6
 
 
 def load_peaks():
@@ -52,9 +73,11 @@ def load_peaks():
 def tensor_side(n_models, n_points, kernel_ms, scorer):
     """tcgen05 work of one launch of the tensor-core scorer: every (128 correspondences x 128 models) tile is six
     128 x 256 x 8 (TF32) or x 16 (BF16) MMAs, padded tiles included.  Peak: the driver-measured dense BF16 rate
-    (MEASURED_PEAKS.json; TF32 runs at half of it).  Extra keys beside the mandated HBM roofline; never raises."""
+    (MEASURED_PEAKS.json; TF32 runs at half of it).  Also the SFU side: one MUFU.RCP per (model, correspondence), or
+    one per two in the pair-reciprocal variants, against 16 results per SM per clock.  Never raises."""
     try:
         bf16 = "bf16" in scorer or scorer == "tc"
+        pair = scorer.replace("_e16", "").endswith("p")
         tiles = -(-n_points // 128) * -(-n_models // 128)            # lower bound: per-pair tails add a little
         flop = tiles * 6 * 2.0 * 128 * 256 * (16 if bf16 else 8)
         try:
@@ -66,21 +89,28 @@ def tensor_side(n_models, n_points, kernel_ms, scorer):
         if not bf16:
             peak, src = peak / 2, src + " / 2 for TF32"
         t = flop / (kernel_ms / 1e3) / 1e12
+        rcp = tiles * 128 * 128 * (0.5 if pair else 1.0)
+        xu = rcp / (kernel_ms * 1e6)                                  # results per ns
         return dict(tensor_tflops=t, tensor_peak_tflops=peak, tensor_frac=t / peak, tensor_peak_source=src,
                     tensor_note="flops issued on tcgen05, the 3 (TF32) or 6 (BF16) partial products of the split "
-                                "operands included")
+                                "operands included",
+                    xu_gops=xu, xu_peak_gops=XU_PEAK_GOPS, xu_frac=xu / XU_PEAK_GOPS,
+                    xu_note="MUFU.RCP results per ns against 148 SMs x 16 lanes x 1.965 GHz")
     except Exception as e:                                         # reporting only
         return dict(tensor_note=f"unavailable: {e}")
 
 
 def load_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture."""
-    try:
-        with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-            t = json.load(f)[kernel]
-        return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
-    except Exception:
-        return None
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
+    (profiles/r2_traffic.json, else round 1's)."""
+    for name in ("r2_traffic.json", "r1_traffic.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", name)) as f:
+                t = json.load(f)[kernel]
+            return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
+        except Exception:
+            continue
+    return None
 
 
 class ClockSampler:
@@ -143,12 +173,47 @@ def make_inputs(B, N, seed):
     return matches, logits, thr, E_gt
 
 
+def _inlier_pack(matches, inl):
+    B = matches.shape[0]
+    npts = inl.sum(1).int()
+    P = int(npts.max())
+    pts = torch.zeros(B, P, 4)
+    for b in range(B):
+        pts[b, : int(npts[b])] = matches[b][inl[b]]
+    return pts, npts
+
+
+def make_train_inputs(cfg, B, seed):
+    """Synthetic batch of a training config: dict of CPU tensors."""
+    from differentiable_ransac_b200 import synth
+
+    kind, N = cfg["kind"], cfg["N"]
+    if kind == "e5":
+        matches, gt, inl = synth.relative_pose_batch(B, N, seed=seed, noise=2e-4)
+        pts, npts = _inlier_pack(matches, inl)
+        return dict(matches=matches, logits=synth.logits_regime(B, N, "L0", seed=seed + 4), gt=gt, pts=pts, npts=npts)
+    if kind == "f8":
+        pairs = [synth.pixel_pair(N, 0.5, seed=seed + b) for b in range(B)]
+        matches = torch.stack([p[0] / 640.0 for p in pairs])
+        pts, npts = _inlier_pack(matches, torch.stack([p[3] for p in pairs]))
+        return dict(matches=matches, logits=synth.logits_regime(B, N, "L1", seed=seed + 1), gt=None, pts=pts, npts=npts,
+                    F=torch.stack([p[1] for p in pairs]), pixels=torch.stack([p[0] for p in pairs]))
+    pts3 = [synth.rigid_pair(N, 0.7, seed=seed + b) for b in range(B)]
+    return dict(matches=torch.stack([p[0] for p in pts3]), logits=synth.logits_regime(B, N, "L1", seed=seed + 2), gt=None,
+                pts=None, npts=None, pose=torch.stack([p[1] for p in pts3]))
+
+
 # ---------------------------------------------------------------------------------------------------
-def pick_cpu_threads(N):
-    """torch's default (= all host cores) is pathological for this path on a many-core box: the
-    per-sample 10x10 eigvals loop (nister.py:355-370) and the tiny batched LAPACK calls spend their
-    time in thread wake-ups.  Give the CPU side its BEST case: time a short run at several thread
-    counts and keep the fastest."""
+# the CPU side: the unmodified reference (oracle/_ref) when present, else the oracle port
+def _harness():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_harness
+
+    return ref_harness if ref_harness.reference_dir() is not None else None
+
+
+def pick_cpu_threads_port(N):
+    """Best thread count for the oracle PORT (used only when oracle/_ref is absent)."""
     from differentiable_ransac_b200 import synth
     from oracle import driver
 
@@ -170,36 +235,139 @@ def pick_cpu_threads(N):
     return best[0], cores
 
 
-def cpu_reference_throughput(max_seconds=12.0, max_pairs=8, K=None, N=None):
-    """The reference's algorithm on the host cores (oracle port): serial over pairs exactly as
-    model_cl.py:488 is, one chunk of K hypotheses per pair (ransac_batch_size = K)."""
-    from differentiable_ransac_b200 import synth
-    from oracle import driver
+def _cpu_step_fn(cfg_name, Ks, pair=0, seed=1234):
+    """-> (callable running ONE pair x Ks hypotheses of the config's workload on the host cores, kind, entry)."""
+    cfg = CONFIGS[cfg_name]
+    rh = _harness()
+    N = cfg["N"]
+    if cfg["mode"] == "test":
+        matches, logits, thr, _ = make_inputs(pair + 1, N, seed=seed)
+        m, w, th = matches[pair], logits[pair], float(thr[pair])
+        if rh is not None:
+            if cfg_name == "cfg1":
+                return (lambda: rh.stewenius_loop_body(m, w, Ks, th)), "reference", \
+                    "ransac.py:55-144 loop body with EssentialMatrixEstimator (Stewenius), unmodified reference"
+            K1, K2, im1, im2 = rh.intrinsics()
+            layer = rh.make_layer(Ks)
 
-    K = K or WORKLOAD["K"]
-    N = N or WORKLOAD["N"]
-    threads, cores = pick_cpu_threads(N)
-    matches, logits, thr, _ = make_inputs(max_pairs, N, seed=1234)
-    done, t_total = 0, 0.0
-    # warm-up on a small chunk (LAPACK / thread pool initialisation)
-    driver.test_loop(matches[0], logits[0], [synth.gumbel_noise((16, N), seed=1)], float(thr[0]))
-    for b in range(max_pairs):
-        G = synth.gumbel_noise((K, N), seed=100 + b)
+            def run():
+                with torch.no_grad():
+                    layer.forward(m, w, K1, K2, im1, im2)
+            return run, "reference", "model_cl.RANSACLayer.forward, unmodified reference"
+        from differentiable_ransac_b200 import synth
+        from oracle import driver
+
+        solver = "stewenius" if cfg_name == "cfg1" else "nister"
+        return (lambda: driver.test_loop(m, w, [synth.gumbel_noise((Ks, N), seed=100)], th, solver=solver)), "port", \
+            "oracle/driver.test_loop (sample + 5-point + MSAC + arg-max)"
+    data = make_train_inputs(cfg, pair + 1, seed)
+    if rh is None:
+        raise RuntimeError("the training configs need oracle/_ref (python oracle/make_ref.py in the build container)")
+    kind = cfg["kind"]
+    if kind == "f8":
+        pix = data["pixels"][pair]
+        pts = pix.clone()
+        c = torch.tensor([320.0, 240.0])
+        pts[:, 0:2] = (pix[:, 0:2] - c) / 640.0          # datasets.py:74-79: (pixels - centre) / max(im)
+        pts[:, 2:4] = (pix[:, 2:4] - c) / 640.0
+        gt = data["F"][pair]
+    else:
+        pts = data["matches"][pair]
+        gt = data["gt"][pair] if kind == "e5" else data["pose"][pair]
+    w = data["logits"][pair]
+    return (lambda: rh.train_step(kind, Ks, pts, w, gt)), "reference", \
+        {"e5": "RANSACLayer(train).forward + MatchLoss + backward", "f8": "RANSACLayer(-fmat 1 -sam 3, train).forward + "
+         "MatchLoss + backward", "rigid": "RANSACLayer3D(train).forward + loss.backward"}[kind] + ", unmodified reference"
+
+
+def _cpu_threads(cfg_name):
+    rh = _harness()
+    N = min(CONFIGS[cfg_name]["N"], 2000)
+    if rh is not None:
+        matches, logits, _, _ = make_inputs(1, N, seed=4321)
+        return rh.pick_threads(matches, logits)
+    return pick_cpu_threads_port(N)
+
+
+def cpu_reference_throughput(cfg_name="cfg2", max_seconds=12.0):
+    """The reference on the host cores, a BOUNDED sample of the config's workload: pairs are processed one after the
+    other exactly as model_cl.py:488 does, one chunk of K hypotheses per pair (fewer when one pair would not fit
+    the time budget: the reference's loop is linear in the hypotheses)."""
+    cfg = CONFIGS[cfg_name]
+    threads, cores = _cpu_threads(cfg_name)
+    K, N = cfg["K"], cfg["N"]
+    probe_K = max(8, min(K, 32))
+    fn, kind, entry = _cpu_step_fn(cfg_name, probe_K)
+    fn()                                                     # warm-up (imports, LAPACK, thread pool)
+    t0 = time.perf_counter()
+    fn()
+    per_hyp = (time.perf_counter() - t0) / probe_K
+    Ks = int(max(8, min(K, max_seconds / max(per_hyp, 1e-9))))
+    done, total, pair = 0, 0.0, 0
+    while total < max_seconds and pair < 8:
+        fn, kind, entry = _cpu_step_fn(cfg_name, Ks, pair=pair)
         t0 = time.perf_counter()
-        driver.test_loop(matches[b], logits[b], [G], float(thr[b]))
-        t_total += time.perf_counter() - t0
-        done += 1
-        if t_total > max_seconds:
-            break
-    return dict(value=done * K / t_total, unit="hypotheses/s", cores=threads, kind="port",
-                sample=f"{done} pair(s) x {K} hyps x {N} corrs, oracle/driver.test_loop (sample+5pt+MSAC), "
-                       f"{t_total:.2f} s, torch {torch.__version__} CPU, {threads} threads (fastest of a sweep; "
-                       f"host has {cores} cores)")
+        fn()
+        total += time.perf_counter() - t0
+        done += Ks
+        pair += 1
+    out = dict(value=done / total, unit="hypotheses/s", cores=threads, kind=kind,
+               sample=f"{pair} pair(s) x {Ks} hyps x {N} corrs of {cfg_name}, {entry}, {total:.2f} s, torch "
+                      f"{torch.__version__} CPU, {threads} threads (fastest of a sweep; host has {cores} cores)")
+    rh = _harness()
+    if rh is not None:
+        out["reference"] = rh.provenance()
+    return out
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cfg = CONFIGS[args.config]
+    K, N = cfg["K"], cfg["N"]
+    cores, host_cores = _cpu_threads(args.config)
+    # Bounded sample: a step is 1 pair x Ks hypotheses x N correspondences of the workload (the reference is
+    # serial over pairs, model_cl.py:488, and linear in the hypotheses: a Python loop over the samples).  Ks is
+    # the workload's K unless --steps is so large that the run would pass REF_BUDGET_S; then it shrinks.
+    probe_K = max(8, min(K, 32))
+    fn, kind, entry = _cpu_step_fn(args.config, probe_K)
+    fn()
+    t0 = time.perf_counter()
+    fn()
+    per_hyp = (time.perf_counter() - t0) / probe_K
+    total = max(1, args.warmup + args.steps)
+    Ks = int(min(K, max(min(K, 16), REF_BUDGET_S / (total * per_hyp))))
+    fn, kind, entry = _cpu_step_fn(args.config, Ks)
+    times = []
+    for it in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        fn()
+        dt = time.perf_counter() - t0
+        if it >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * sum(times) / len(times)
+    value = Ks / (ms / 1e3)
+    sample = (f"each step = 1 pair x {Ks} hyps x {N} corrs of the workload on the host cores ({entry}), {cores} "
+              f"threads (fastest of a sweep; host has {host_cores} cores)")
+    rh = _harness()
+    line = dict(impl="reference", metric="hypotheses_per_sec", value=value, unit="hypotheses/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=cfg["name"], pairs_per_gpu=cfg["B"], hypotheses_per_pair=K,
+                            correspondences=N, sample=sample),
+                cpu_baseline=dict(value=value, unit="hypotheses/s", cores=cores, kind=kind,
+                                  sample=f"{args.steps} step(s); " + sample),
+                e2e=dict(value=value, unit="hypotheses/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    if rh is not None:
+        line["cpu_baseline"]["reference"] = rh.provenance()
+    return line
 
 
 def auc_parity(dev, pairs=12, N=1000, K=192, scorer=None):
     """AUC@5/10/20 of the poses recovered from the winning E, CUDA path vs the CPU oracle of the reference,
-    same synthetic pairs and the same injected Gumbel noise (bounded sample: ~5 s of CPU work)."""
+    same synthetic pairs and the same injected Gumbel noise (bounded sample: ~5 s of CPU work).  Every pair whose
+    winning hypothesis differs from the oracle's is classified: a tie (scores within 1e-4 relative) or worse."""
     from differentiable_ransac_b200 import engine, synth
     from oracle import driver, pose_eval
 
@@ -211,70 +379,34 @@ def auc_parity(dev, pairs=12, N=1000, K=192, scorer=None):
     noise = synth.gumbel_noise((pairs, K, N), seed=13)
     ours = engine.ransac_e5_test(matches.to(dev), logits.to(dev), K, torch.full((pairs,), thr, device=dev),
                                  noise=noise.to(dev), want_scores=True, scorer=scorer)
-    e_ours, e_ref, same = [], [], 0
+    e_ours, e_ref, same, ties, worse, worst = [], [], 0, 0, 0, 0.0
     for b in range(pairs):
         _, _, _, R, t = data[b]
-        ref = driver.test_loop(matches[b], logits[b], [noise[b]], thr)
-        same += int(int(ours["best_hyp"][b]) == ref["best_idx"] // 10)
+        ref = driver.test_loop(matches[b].double(), logits[b].double(), [noise[b].double()], thr)   # fp64 oracle
+        rel = abs(float(ours["best_score"][b]) - float(ref["best_score"])) / float(ref["best_score"])
+        if int(ours["best_hyp"][b]) == ref["best_idx"] // 10:
+            same += 1
+        elif rel <= 1e-4:
+            ties += 1
+        else:
+            worse += 1
+        worst = max(worst, rel)
         e_ours.append(max(pose_eval.pose_error_deg(ours["best_model"][b].cpu().numpy(), matches[b].numpy(), R, t,
                                                    ours["mask"][b].cpu().numpy())))
-        e_ref.append(max(pose_eval.pose_error_deg(ref["best_model"].numpy(), matches[b].numpy(), R, t,
+        e_ref.append(max(pose_eval.pose_error_deg(ref["best_model"].float().numpy(), matches[b].numpy(), R, t,
                                                   ref["best_mask"].numpy())))
     a, r = pose_eval.auc(e_ours), pose_eval.auc(e_ref)
-    # the same evaluation without leaving the device (drb_recover_pose: decomposition, DLT cheirality vote over all
-    # correspondences as test.py:73-76 does, angular errors), one launch for all pairs
     from differentiable_ransac_b200 import cv_utils
     R_gt = torch.stack([d[3] for d in data]).float().to(dev)
     t_gt = torch.stack([d[4] for d in data]).float().to(dev)
     err = cv_utils.pose_errors(ours["best_model"], matches.to(dev), R_gt, t_gt)[:, 0]
     a_dev = pose_eval.auc(err.max(dim=-1).values.cpu().tolist())
     return dict(auc5_10_20_ours=a, auc5_10_20_cpu_reference=r, auc5_10_20_ours_device_pose=a_dev,
-                same_best_hypothesis=f"{same}/{pairs}", scorer=scorer or "default (FP32 work queue)",
-                sample=f"{pairs} synthetic pairs x {K} hyps x {N} corrs, identical injected Gumbel noise, "
-                       "pose from cv2.recoverPose, AUC as cv_utils.py:528-546")
-
-
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from differentiable_ransac_b200 import synth
-    from oracle import driver
-
-    K, N = WORKLOAD["K"], WORKLOAD["N"]
-    cores, host_cores = pick_cpu_threads(N)
-    pairs_per_step = 1
-    matches, logits, thr, _ = make_inputs(pairs_per_step, N, seed=1234)
-    # Bounded sample: a step is 1 pair x Ks hypotheses x N correspondences of the workload (the reference is
-    # serial over pairs, model_cl.py:488, and linear in the hypotheses: a Python loop over the samples).  Ks is
-    # the workload's 1000 unless --steps is so large that the run would pass REF_BUDGET_S; then it shrinks.
-    t0 = time.perf_counter()
-    driver.test_loop(matches[0], logits[0], [synth.gumbel_noise((100, N), seed=99)], float(thr[0]))
-    per_hyp = (time.perf_counter() - t0) / 100
-    total = max(1, args.warmup + args.steps)
-    Ks = int(min(K, max(50, REF_BUDGET_S / (total * per_hyp))))
-    times = []
-    for it in range(args.warmup + args.steps):
-        G = synth.gumbel_noise((Ks, N), seed=100 + it)
-        t0 = time.perf_counter()
-        driver.test_loop(matches[0], logits[0], [G], float(thr[0]))
-        dt = time.perf_counter() - t0
-        if it >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
-    value = pairs_per_step * Ks / (ms / 1e3)
-    sample = (f"each step = {pairs_per_step} pair x {Ks} hyps x {N} corrs of the workload on the host cores "
-              f"(oracle/driver.test_loop: sample + 5-point + MSAC + arg-max), {cores} threads (fastest of a sweep; "
-              f"host has {host_cores} cores)")
-    line = dict(impl="reference", metric="hypotheses_per_sec", value=value, unit="hypotheses/s", n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=ms, higher_is_better=True, scaling="weak",
-                vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=WORKLOAD_NAME, pairs_per_gpu=WORKLOAD["B"], hypotheses_per_pair=K,
-                            correspondences=N, sample=sample),
-                cpu_baseline=dict(value=value, unit="hypotheses/s", cores=cores, kind="port",
-                                  sample=f"{args.steps} step(s); " + sample),
-                e2e=dict(value=value, unit="hypotheses/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    return line
+                same_best_hypothesis=f"{same}/{pairs}", ties_within_1e_4=ties, worse_than_1e_4=worse,
+                worst_rel_score_gap=worst, scorer=scorer or "default (FP32 work queue)",
+                sample=f"{pairs} synthetic pairs x {K} hyps x {N} corrs, identical injected Gumbel noise, fp64 CPU oracle "
+                       "of the reference loop, pose from cv2.recoverPose, AUC as cv_utils.py:528-546; the full-size "
+                       "(32 x 1000 x 2000) index parity of the timed pipeline is tests/test_gpu_pipeline_parity.py")
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -284,11 +416,12 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-slots", type=int, default=int(os.environ.get("DRB_E2E_SLOTS", "3")),
-                    help="batches in flight in the end-to-end service (engine.E5TestService)")
+                    help="batches in flight in the end-to-end plugin calls (RANSACLayer.submit / collect)")
     ap.add_argument("--e2e-graph", type=int, default=int(os.environ.get("DRB_E2E_GRAPH", "1")),
-                    help="1: each service slot replays one CUDA graph (copy-in, kernels, copy-out) per batch")
+                    help="1: each service slot replays one CUDA graph (kernels, copy-out) per batch")
     ap.add_argument("--value-graph", type=int, default=int(os.environ.get("DRB_VALUE_GRAPH", "1")),
                     help="1: the device-resident steps replay one CUDA graph per stream")
     ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "3")),
@@ -300,7 +433,12 @@ def main():
     real_stdout = os.dup(1)
     os.dup2(2, 1)
     try:
-        line = run_reference_arm(args) if args.impl == "reference" else run_ours(args)
+        if args.impl == "reference":
+            line = run_reference_arm(args)
+        elif CONFIGS[args.config]["mode"] == "train":
+            line = run_train(args)
+        else:
+            line = run_ours(args)
     finally:
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
@@ -309,8 +447,7 @@ def main():
         print(json.dumps(line), flush=True)
 
 
-def run_ours(args):
-
+def _setup_dist():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -323,10 +460,42 @@ def run_ours(args):
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=dev)
+    return rank, world, local_rank, dev, dist
 
+
+def _barrier(dist):
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def _max_over_ranks(ms, dev, dist):
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def _time_stage(fn, reps=5):
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    fn()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b_.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b_) / reps
+
+
+def run_ours(args):
+    rank, world, local_rank, dev, dist = _setup_dist()
     from differentiable_ransac_b200 import engine, ops
+    from differentiable_ransac_b200.model_cl import RANSACLayer
 
-    B, K, N = WORKLOAD["B"], WORKLOAD["K"], WORKLOAD["N"]
+    cfg = CONFIGS[args.config]
+    B, K, N = cfg["B"], cfg["K"], cfg["N"]
     warmup = max(args.warmup, 3)
     matches_h, logits_h, thr_h, E_gt = make_inputs(B, N, seed=1234 + 1000 * rank)   # pairs shard over ranks
     matches_h, logits_h, thr_h = matches_h.pin_memory(), logits_h.pin_memory(), thr_h.pin_memory()
@@ -334,7 +503,9 @@ def run_ours(args):
     # L2 policy for `value`: every step copies its (packed) inputs from one of NB places in HBM, 168 MB in all
     # (> the 126 MB L2), so a step never finds its inputs cached by an earlier one; the roofline pass below
     # (one kernel timed alone) flushes L2 with a 256 MB write instead.
-    NB = 128
+    n_in = B * N * 5 + B
+    NB = max(4, -(-168 * 1024 * 1024 // (n_in * 4)))
+    NB = min(NB, 4096)
     packed_all = torch.cat((matches.flatten(), logits.flatten(), thr)).unsqueeze(0).repeat(NB, 1)   # [NB, n_in]
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)     # > 126 MB L2
     S = max(1, args.value_streams)
@@ -344,40 +515,27 @@ def run_ours(args):
     def run_steps(n, first):
         """n independent steps (fresh Philox offset each) through engine.E5TestService(host_io=False): issued
         round-robin over S streams (one CUDA graph per stream when --value-graph 1), so the latency-bound
-        5-point kernel of one step overlaps the FMA-bound scoring kernel of the previous one.  Every step
-        first copies ITS inputs, device to device, from one of NB distinct places in HBM."""
-        fork = torch.cuda.Event()
-        fork.record(main_stream)
-        dsvc.after(fork)
+        5-point kernel of one step overlaps the scoring kernel of the previous one.  Every step first copies ITS
+        inputs, device to device, from one of NB distinct places in HBM."""
         for i in range(n):
             dsvc.submit(packed=packed_all[(first + i) % NB])
         dsvc.join(main_stream)
         return dsvc.dev_out[(n - 1) % S]
 
-    def barrier():
-        torch.cuda.synchronize()
-        if dist is not None:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     # ---- device-resident throughput ("value") -------------------------------------------------------
-    out = run_steps(warmup, 0)
-    barrier()
+    run_steps(warmup, 0)
+    _barrier(dist)
     clocks = ClockSampler(local_rank)
     if rank == 0:
         clocks.start()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    _barrier(dist)
     t_begin.record(main_stream)
-    out = run_steps(args.steps, warmup)
+    run_steps(args.steps, warmup)
     t_end.record(main_stream)
-    barrier()
-    ms_local = t_begin.elapsed_time(t_end)
+    _barrier(dist)
+    ms_total = _max_over_ranks(t_begin.elapsed_time(t_end), dev, dist)
     clock_info = clocks.stop() if rank == 0 else None
-    t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = world * B * K * args.steps / (ms_total / 1e3)
 
@@ -386,45 +544,63 @@ def run_ours(args):
     for i in range(args.steps):
         flush.fill_(float(i))
         ev[i][0].record()
-        out = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i,
-                                    scorer=dsvc.scorer if str(dsvc.scorer).startswith("tc") else None)
+        engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=10_000 + i,
+                              scorer=dsvc.scorer if str(dsvc.scorer).startswith("tc") else None)
         ev[i][1].record()
-    barrier()
+    _barrier(dist)
     ms_serial = sorted(a.elapsed_time(b) for a, b in ev)[args.steps // 2]      # median
 
-    # ---- end to end through the public API with host buffers ("e2e") ------------------------------------
-    # engine.E5TestService: every step copies ITS inputs from pinned host memory (one packed buffer: matches |
-    # logits | thr) and reads ITS results back (one packed buffer: model | id | score | #inliers) before the
-    # slot is reused.  `--e2e-slots` batches are in flight at once, each on its own compute stream, copies on
-    # a copy stream: steady-state service throughput.  Inputs come from the host every step, so no L2 flush
-    # is inserted here (and it could not be excluded from the timed region once copies and compute overlap).
-    svc = engine.E5TestService(B, N, K, dev, slots=args.e2e_slots, seed=42 + rank, graph=bool(args.e2e_graph))
-    for s_ in range(svc.slots):
-        svc.stage(s_, matches_h, logits_h, thr_h)      # synthetic: the same pairs staged in every slot
-    h2d, d2h = svc.h2d_bytes, svc.d2h_bytes
+    # ---- end to end through the reference-facing plugin with host buffers ("e2e") ------------------------
+    # model_cl.RANSACLayer configured for the hot path proper (test mode, every hypothesis scored: opt.adaptive =
+    # False, opt.final_refit = False, one chunk of K hypotheses): `submit(points, weights, K1, K2)` takes the
+    # batch's pinned HOST tensors, `collect()` returns list_B[E], the winners' inlier masks [B,N] and scores on
+    # the host.  `--e2e-slots` batches are in flight, so the copies of one batch overlap the kernels of another;
+    # every step's H2D (matches, weights, thresholds) and D2H (models, ids, scores, #inliers, masks) are inside the
+    # timed region.  Inputs come from the host every step, so no L2 flush is inserted here.
+    opt = types.SimpleNamespace(device=dev, fmat=0, sampler=2, precision=1, tr=0, threshold=WORKLOAD["threshold_px"],
+                                ransac_batch_size=K, weighted=0, adaptive=False, final_refit=False, seed=42 + rank)
+    layer = RANSACLayer(opt)
+    layer.estimator.max_iterations = K
+    Kmat = torch.tensor([[WORKLOAD["focal"], 0.0, 320.0], [0.0, WORKLOAD["focal"], 240.0], [0.0, 0.0, 1.0]])
+    K1_h = Kmat.expand(B, 3, 3).contiguous()
+    slots = max(1, args.e2e_slots)
 
     def run_e2e(n_steps):
-        pending = []
+        pending, last = [], None
         for _ in range(n_steps):
-            if len(pending) == svc.slots:
-                svc.result(pending.pop(0))              # the caller reads the oldest batch's results (host sync)
-            pending.append(svc.submit())
+            if len(pending) == slots:
+                last = layer.collect(pending.pop(0))     # the caller reads the oldest batch's results (host sync)
+            pending.append(layer.submit(matches_h, logits_h, K1_h, K1_h, slots=slots, graph=bool(args.e2e_graph)))
         for s_ in pending:
-            svc.result(s_)
+            last = layer.collect(s_)
+        return last
 
     run_e2e(warmup)
-    barrier()
+    svc = layer._svc
+    h2d, d2h = svc.h2d_bytes, svc.d2h_bytes
+    _barrier(dist)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_host0 = time.perf_counter()
     e0.record(main_stream)
     svc.after(e0)
-    run_e2e(args.steps)
+    Es, masks, scores = run_e2e(args.steps)
     svc.join(main_stream)
     e1.record(main_stream)
-    barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    e2e_value = world * B * K * args.steps / (float(t2.item()) / 1e3)
+    torch.cuda.synchronize()
+    t_host = (time.perf_counter() - t_host0) * 1e3
+    _barrier(dist)
+    e2e_ms = _max_over_ranks(max(e0.elapsed_time(e1), t_host), dev, dist)
+    e2e_value = world * B * K * args.steps / (e2e_ms / 1e3)
+    # e2e_check: the plugin call returns what a direct engine call returns for the same Philox position
+    chk = RANSACLayer(types.SimpleNamespace(**{**vars(opt)}))
+    chk.estimator.max_iterations = K
+    Es0, masks0, scores0 = chk.collect(chk.submit(matches_h, logits_h, K1_h, K1_h, slots=1, graph=False))
+    direct = engine.ransac_e5_test(matches, logits, K, thr, seed=42 + rank, offset=0, scorer=chk._svc.scorer)
+    torch.cuda.synchronize()
+    e2e_check = dict(models_equal=bool(torch.equal(torch.stack(Es0), direct["best_model"].cpu())),
+                     masks_equal=bool(torch.equal(masks0, direct["mask"].cpu())),
+                     scores_equal=bool(torch.equal(scores0, direct["best_score"].cpu())),
+                     inliers_in_last_batch=int(masks.sum()))
 
     if rank != 0:
         if dist is not None:
@@ -432,7 +608,7 @@ def run_ours(args):
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel (score_msac_kernel), timed live with CUDA events -------------------
+    # ---- roofline of the dominant kernel (the MSAC scorer), timed live with CUDA events -------------------
     idx = ops.sample_sets(logits, K, 5, seed=7, offset=0)
     models, nsol, cm, cid, cc = ops.solve_e5(matches, idx, compact=True)
     n_valid = int(cc.sum().item())
@@ -440,7 +616,8 @@ def run_ours(args):
     msac_kernel = dsvc.scorer or ops._MSAC_KERNEL     # the kernel the timed steps above ran
     msac_name = {"block": "score_msac_kernel", "stream": "score_msac_stream_kernel"}.get(msac_kernel,
                                                                                            "score_msac_tc_kernel")
-    launches_per_step = 5 if msac_name == "score_msac_tc_kernel" else 4   # tc: operand images + scorer
+    is_tc = msac_name == "score_msac_tc_kernel"
+    launches_per_step = 5 if is_tc else 4   # tc: operand images + scorer
     for _ in range(3):
         ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=True, kernel=msac_kernel)
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
@@ -451,73 +628,265 @@ def run_ours(args):
         b_.record()
     torch.cuda.synchronize()
     score_ms = sum(a.elapsed_time(b_) for a, b_ in evs) / reps          # includes the 8-byte/pair memset of `best`
-    # stage shares of one step (events around each stage)
     shares = {}
     for name, fn in (("sample_sets", lambda: ops.sample_sets(logits, K, 5, seed=7, offset=1)),
-                     ("sample_gumbel_race", lambda: ops.sample(logits, K, 5, 1.0, seed=7, offset=1)),
                      ("solve_e5", lambda: ops.solve_e5(matches, idx, compact=True)),
                      ("score_msac", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid, want_scores=False,
                                                            kernel=msac_kernel)),
                      ("score_msac_stream", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
                                                                   want_scores=False, kernel="stream")),
-                     ("score_msac_block", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
-                                                                 want_scores=False, kernel="block")),
-                     ("score_msac_tc", lambda: ops.score_msac(matches, cm, thr, count=cc, ids=cid,
-                                                              want_scores=False, kernel="tc")),
                      ):
-        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        fn()
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(5):
-            fn()
-        b_.record()
-        torch.cuda.synchronize()
-        shares[name + "_ms"] = a.elapsed_time(b_) / 5
+        shares[name + "_ms"] = _time_stage(fn)
     peak, peak_src = load_peaks()
     score_bytes = B * N * 16 + n_valid * (36 + 4 + 4) + B * 8
     achieved = score_bytes / (score_ms / 1e3) / 1e9
-    flops_score = n_valid * N * 37.0
     line = dict(
         metric="hypotheses_per_sec", value=value, unit="hypotheses/s", n_gpus=world, steps=args.steps,
         warmup=warmup, ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None,
         dtype="f32", data="synthetic",
-        config=dict(workload=WORKLOAD_NAME,
+        config=dict(workload=cfg["name"],
                     pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N,
                     noise="in-kernel Philox4x32-10; sets drawn without replacement from softmax(logits) "
                           "(= Gumbel top-5 in law, drb_sample_sets)",
-                    l2="`value`: every step copies its inputs (device to device, inside the timed region) from one "
-                       "of 128 distinct places in HBM, 168 MB in all (> L2); "
+                    l2=f"`value`: every step copies its inputs (device to device, inside the timed region) from one "
+                       f"of {NB} distinct places in HBM, {NB * n_in * 4 >> 20} MB in all (> L2); "
                        "serial_ms_per_step and the roofline pass: L2 flushed by a 256 MB write before each launch; "
                        "e2e re-copies its inputs from the host every step",
                     value_streams=S, value_graph=bool(args.value_graph), serial_ms_per_step=ms_serial,
                     scorer=f"{msac_name} ({msac_kernel})",
-                    e2e_mode=f"engine.E5TestService(graph={bool(args.e2e_graph)}), {args.e2e_slots} batches in flight "
-                             "(one stream each; a CUDA graph per slot when graph=True): packed H2D per step, one packed D2H of (model, id, score, #inliers) "
-                             "per step, results read on the host before a slot is reused",
+                    e2e_mode=f"model_cl.RANSACLayer.submit / collect (the reference-facing plugin; test mode, adaptive "
+                             f"exit and final refit off = the hot path proper), {slots} batches in flight (one stream "
+                             f"each; graph={bool(args.e2e_graph)}): H2D of the caller's pinned matches / weights / "
+                             "thresholds, D2H of (model, id, score, #inliers) + the winner's inlier mask [B,N] per step, "
+                             "results read on the host before a slot is reused; timed as max(device events, host clock)",
+                    e2e_check=e2e_check,
                     parallelism=f"pairs sharded over {world} GPU(s)"),
         clocks=clock_info,
         e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h),
         gpu_launches=launches_per_step * args.steps,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                      traffic=load_traffic(msac_name),
+                      traffic=load_traffic(msac_name if not is_tc else f"score_msac_tc_kernel<{msac_kernel}>"),
                       kernel=msac_name, kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,
-                      note=("FP32-issue bound, not HBM bound (SURVEY H8): see fp32_tflops" if launches_per_step == 4 else
-                            "not HBM bound: the contraction runs on tcgen05 (operands split into TF32 / BF16 words), the "
-                            "epilogue is SFU-bound (ncu: XU pipe 67 %); fp32_tflops counts the 37 flop per (model, correspondence) of the FP32 formula "
-                            "as useful work, so it can exceed the FP32 pipe's peak (DESIGN.md section 10); kernel_ms covers both "
-                            "launches of the call (operand images of the correspondences, then the scorer)"),
-                      fp32_tflops=flops_score / (score_ms / 1e3) / 1e12,
-                      fp32_peak_tflops=FP32_PEAK_TFLOPS,
-                      fp32_frac=flops_score / (score_ms / 1e3) / 1e12 / FP32_PEAK_TFLOPS,
+                      note=("FP32-issue bound, not HBM bound (SURVEY H8)" if not is_tc else
+                            "not HBM bound (SURVEY H8: ~1 900 flop per algorithmic byte): the contraction runs on tcgen05 "
+                            "(operands split into BF16 / TF32 words), the epilogue on the SFU and FMA pipes; the "
+                            "informative fractions are tensor_frac and xu_frac; kernel_ms covers both launches of the "
+                            "call (operand images of the correspondences, then the scorer)"),
                       step_algorithmic_gbs=ALGO_BYTES_PER_HYP * B * K / (ms_per_step / 1e3) / 1e9, **shares),
     )
-    if launches_per_step == 5:
+    if is_tc:
         line["roofline"].update(tensor_side(n_valid, N, score_ms, str(msac_kernel)))
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is reported at N = 1 only
-        line["cpu_baseline"] = cpu_reference_throughput()
+        line["cpu_baseline"] = cpu_reference_throughput(args.config)
         line["accuracy"] = auc_parity(dev, scorer=dsvc.scorer)      # through the scorer the timed steps used
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return line
+
+
+# ---------------------------------------------------------------------------------------------------
+def _train_stage_table(cfg, data, dev):
+    """Per-kernel times of one training step (CUDA events, each stage alone) and the algorithmic bytes of each:
+    -> (stages dict name -> (ms, bytes), dominant name)."""
+    from differentiable_ransac_b200 import ops
+
+    kind, B, K, N = cfg["kind"], cfg["B"], cfg["K"], cfg["N"]
+    s = {"e5": 5, "f8": 8, "rigid": 3}[kind]
+    D = 6 if kind == "rigid" else 4
+    m, lg = data["matches"].to(dev), data["logits"].to(dev)
+    idx, lse, sel_key, _ = ops.sample(lg, K, s, 1.0, None, 3, 0, want_lse=True)
+    st = {}
+    st["sample"] = (_time_stage(lambda: ops.sample(lg, K, s, 1.0, None, 3, 0, want_lse=True)),
+                    B * N * 4 + B * K * (4 * s + 4 + 4 * s))
+    if kind == "e5":
+        gt = data["gt"].to(dev)
+        models, nsol = ops.solve_e5(m, idx)
+        sel, used = ops.select_closest(models, nsol, gt)
+        valid = sel >= 0
+        st["solve_e5"] = (_time_stage(lambda: ops.solve_e5(m, idx)), B * K * (s * 16 + 360 + 4))
+        st["select_closest"] = (_time_stage(lambda: ops.select_closest(models, nsol, gt)), B * K * (360 + 4 + 36 + 4))
+    elif kind == "f8":
+        used, valid = ops.solve_f8(m, idx)
+        valid = valid.bool()
+        st["solve_f8"] = (_time_stage(lambda: ops.solve_f8(m, idx)), B * K * (s * 16 + 36 + 1))
+    else:
+        used, valid = ops.solve_rigid3(m, idx, True)
+        valid = valid.bool()
+        used = torch.where(valid[..., None, None], used, torch.zeros_like(used))
+        st["solve_rigid3"] = (_time_stage(lambda: ops.solve_rigid3(m, idx, True)), B * K * (s * 24 + 64 + 1))
+    g_row = torch.full((B, K), 1.0 / (B * K), device=dev)
+    if kind == "rigid":
+        st["rigid_residual_fwd"] = (_time_stage(lambda: ops.rigid_residual_forward(m, used, want_ninl=False)),
+                                    B * N * 24 + B * K * (64 + 4))
+        st["rigid_residual_bwd"] = (_time_stage(lambda: ops.rigid_residual_backward(m, used, g_row)),
+                                    B * N * 24 + B * K * (64 + 4 + 64))
+        g_used = ops.rigid_residual_backward(m, used, g_row)
+        st["solve_rigid3_bwd"] = (_time_stage(lambda: ops.solve_rigid3_backward(m, idx, g_used.reshape(B, K, 16), True)),
+                                  B * K * (s * 24 + 64 + s * 24))
+        g_pts = ops.solve_rigid3_backward(m, idx, g_used.reshape(B, K, 16), True)
+    else:
+        pts, npts = data["pts"].to(dev), data["npts"].to(dev)
+        P = pts.shape[1]
+        st["episym_fwd"] = (_time_stage(lambda: ops.episym_forward(pts, used, npts, valid)), B * P * 16 + B * K * (36 + 4))
+        st["episym_bwd"] = (_time_stage(lambda: ops.episym_backward(pts, used, g_row, npts, valid)),
+                            B * P * 16 + B * K * (36 + 4 + 36))
+        g_used = ops.episym_backward(pts, used, g_row, npts, valid)
+        if kind == "e5":
+            st["solve_e5_bwd"] = (_time_stage(lambda: ops.solve_e5_backward(m, idx, models, sel, g_used.reshape(B, K, 9))),
+                                  B * K * (s * 16 + 36 + 36 + s * 16))
+            g_pts = ops.solve_e5_backward(m, idx, models, sel, g_used.reshape(B, K, 9))
+        else:
+            st["solve_f8_bwd"] = (_time_stage(lambda: ops.solve_f8_backward(m, idx, g_used.reshape(B, K, 9), used)),
+                                  B * K * (s * 16 + 36 + 36 + s * 16))
+            g_pts = ops.solve_f8_backward(m, idx, g_used.reshape(B, K, 9), used)
+    st["gather_bwd"] = (_time_stage(lambda: ops.gather_backward(m, idx, g_pts, want_grad_matches=False)),
+                        B * K * s * (4 * D + 4 + 4))
+    g_sel, _ = ops.gather_backward(m, idx, g_pts, want_grad_matches=False)
+    st["sample_bwd"] = (_time_stage(lambda: ops.sample_backward(lg, idx, lse, sel_key, g_sel, 1.0, None, 3, 0)),
+                        B * N * 8 + B * K * (4 + 12 * s))
+    dominant = max(st, key=lambda k_: st[k_][0])
+    return st, dominant
+
+
+def run_train(args):
+    """cfg3 / cfg4 / cfg5: one step = forward + loss + backward for one batch through engine.TrainStep (the fused,
+    CUDA-graph form of the autograd path; tests/test_gpu_train_step.py pins the two to each other)."""
+    rank, world, local_rank, dev, dist = _setup_dist()
+    from differentiable_ransac_b200 import engine
+
+    cfg = CONFIGS[args.config]
+    kind, B, K, N = cfg["kind"], cfg["B"], cfg["K"], cfg["N"]
+    warmup = max(args.warmup, 3)
+    data = make_train_inputs(cfg, B, seed=300 + 1000 * rank)
+    P = None if data["pts"] is None else data["pts"].shape[1]
+    step = engine.TrainStep(kind, B, N, K, dev, P=P, seed=5 + rank, graph=True)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in data.items()}
+    devd = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in data.items()}
+    in_bytes = sum(devd[k].numel() * devd[k].element_size() for k in ("matches", "logits"))
+    # L2 policy: the step's inputs rotate over NB distinct copies in HBM, > 126 MB in all
+    NB = max(2, min(256, -(-160 * 1024 * 1024 // in_bytes)))
+    rot_m = devd["matches"].unsqueeze(0).repeat(NB, *([1] * devd["matches"].dim()))
+    rot_l = devd["logits"].unsqueeze(0).repeat(NB, 1, 1)
+    step.load(devd["matches"], devd["logits"], devd.get("gt"), devd["pts"], devd["npts"])
+    # cfg5 at --gpus > 1: the data-parallel all-reduce of the weight network's gradients (SURVEY 8e: d loss /
+    # d logits is consumed locally by CLNet's backward; only the resulting 622 616 parameter gradients are shared).
+    # CLNet is outside this path, so the buffer is a stand-in of its size; the collective runs on its own stream
+    # behind the step's backward and the NEXT step waits for it (it needs the updated weights), i.e. it is on the
+    # critical path exactly as in train.py -- not hidden behind the next step.
+    do_ar = args.config == "cfg5" and dist is not None
+    grads = torch.zeros(CLNET_PARAMS, device=dev)
+    comm = torch.cuda.Stream(device=dev)
+    main_stream = torch.cuda.current_stream()
+
+    def one_step(i, rotate=True):
+        if rotate:
+            step.matches.copy_(rot_m[i % NB], non_blocking=True)
+            step.logits.copy_(rot_l[i % NB], non_blocking=True)
+        loss, gl = step.run()
+        if do_ar:
+            comm.wait_stream(main_stream)
+            with torch.cuda.stream(comm):
+                dist.all_reduce(grads)
+            main_stream.wait_stream(comm)
+        return loss
+
+    for i in range(warmup):
+        one_step(i)
+    _barrier(dist)
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(dist)
+    t0.record()
+    for i in range(args.steps):
+        one_step(warmup + i)
+    t1.record()
+    _barrier(dist)
+    ms_total = _max_over_ranks(t0.elapsed_time(t1), dev, dist)
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_per_step = ms_total / args.steps
+    value = world * B * K * args.steps / (ms_total / 1e3)
+
+    ar_ms = None
+    if do_ar:                                         # the collective alone, device-timed, max over ranks
+        for _ in range(5):
+            dist.all_reduce(grads)
+        _barrier(dist)
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for _ in range(50):
+            dist.all_reduce(grads)
+        a1.record()
+        torch.cuda.synchronize()
+        ar_ms = _max_over_ranks(a0.elapsed_time(a1) / 50, dev, dist)
+
+    # ---- e2e: pinned host batch in, loss on the host, every step ------------------------------------
+    loss_h = torch.empty(1).pin_memory()
+
+    def e2e_step():
+        step.load(host["matches"], host["logits"], host.get("gt"), host["pts"], host["npts"])
+        loss = one_step(0, rotate=False)
+        loss_h.copy_(loss, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the training loop reads the loss (train.py:175)
+        return float(loss_h)
+
+    for _ in range(warmup):
+        e2e_step()
+    _barrier(dist)
+    th0 = time.perf_counter()
+    for _ in range(args.steps):
+        last_loss = e2e_step()
+    torch.cuda.synchronize()
+    e2e_ms = _max_over_ranks((time.perf_counter() - th0) * 1e3, dev, dist)
+    e2e_value = world * B * K * args.steps / (e2e_ms / 1e3)
+    h2d = sum(host[k].numel() * host[k].element_size() for k in ("matches", "logits", "gt", "pts", "npts")
+              if torch.is_tensor(host.get(k)))
+
+    if rank != 0:
+        if dist is not None:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    stages, dominant = _train_stage_table(cfg, data, dev)
+    peak, peak_src = load_peaks()
+    dom_ms, dom_bytes = stages[dominant]
+    achieved = dom_bytes / (dom_ms / 1e3) / 1e9
+    D = 6 if kind == "rigid" else 4
+    step_bytes = B * N * (4 * D + 4) + B * K * (64 if kind == "rigid" else 36) + B * N * 4     # SURVEY 8d
+    line = dict(
+        metric="hypotheses_per_sec", value=value, unit="hypotheses/s", n_gpus=world, steps=args.steps, warmup=warmup,
+        ms_per_step=ms_per_step, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+        config=dict(workload=cfg["name"], pairs_per_gpu=B, hypotheses_per_pair=K, correspondences=N,
+                    step="engine.TrainStep: sample (Gumbel top-s, in-kernel Philox, device-side stream position) -> minimal "
+                         "solver -> loss -> IFT adjoint of the solver -> gather backward -> straight-through sampler "
+                         "backward; ONE CUDA graph replay per step; gradient: d loss / d logits [B,N]",
+                    l2=f"the step's inputs rotate over {NB} distinct copies in HBM ({NB * in_bytes >> 20} MB > L2), copied "
+                       "device to device inside the timed region",
+                    allreduce=(None if not do_ar else
+                               dict(bytes=CLNET_PARAMS * 4, ms_alone=ar_ms, share_of_step=ar_ms / ms_per_step,
+                                    placement="own stream, behind the step's backward; the next step waits for it "
+                                              "(critical path, as in data-parallel train.py)")),
+                    e2e_mode="every step: H2D of the pinned host batch into the step's static buffers, graph replay, D2H of "
+                             "the loss, host synchronisation (a training loop is sequential: no batches in flight); timed "
+                             "on the host clock",
+                    last_loss=last_loss, parallelism=f"pairs sharded over {world} GPU(s)"),
+        clocks=clock_info,
+        e2e=dict(value=e2e_value, unit="hypotheses/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4),
+        gpu_launches=len(stages) * args.steps,
+        roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak, traffic=None,
+                      kernel=dominant, kernel_ms=dom_ms, algorithmic_bytes=dom_bytes, peak_source=peak_src,
+                      stages_ms={k_: v[0] for k_, v in stages.items()},
+                      step_algorithmic_bytes_per_hyp=step_bytes / (B * K),
+                      step_algorithmic_gbs=step_bytes / (ms_per_step / 1e3) / 1e9,
+                      note="latency / FP32-issue bound like cfg2 (SURVEY H8); the mandated HBM fraction of the dominant "
+                           "kernel, each kernel timed alone with CUDA events"),
+    )
+    if not args.no_cpu_baseline and world == 1:
+        line["cpu_baseline"] = cpu_reference_throughput(args.config)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

@@ -17,9 +17,9 @@ _SIGNATURES = {
     "drb_status_string": ([c_int], c_char_p),
     "drb_last_error": ([], c_int),
     "drb_device_sm_count": ([], c_int),
-    "drb_sample": ([P, P, c_uint64, c_uint64, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P], c_int),
+    "drb_sample": ([P, P, c_uint64, c_uint64, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P], c_int),
     "drb_sample_sets": ([P, c_uint64, c_uint64, P, c_int, c_int, c_int, c_int, P, P], c_int),
-    "drb_sample_backward": ([P, P, c_uint64, c_uint64, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P],
+    "drb_sample_backward": ([P, P, c_uint64, c_uint64, P, c_float, c_int, c_int, c_int, c_int, P, P, P, P, P, P, P],
                             c_int),
     "drb_solve_e5": ([P, P, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
     "drb_solve_e5_backward": ([P, P, c_int, c_int, c_int, P, P, P, P, P], c_int),

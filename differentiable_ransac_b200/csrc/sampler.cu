@@ -11,6 +11,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"
+#include "device_cfg.cuh"
 #include "drb_common.cuh"
 #include "philox.cuh"
 
@@ -111,8 +112,9 @@ constexpr int kRaceMaxN = 8192;
 
 template <int S>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
-sample_race_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
-                   int32_t* __restrict__ idx_out) {
+sample_race_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ offset_dev, int K,
+                   int N, int32_t* __restrict__ idx_out) {
+    if (offset_dev) offset += *offset_dev;  // stream position kept on the device (CUDA-graph replay draws fresh noise)
     __shared__ __align__(16) float winv[kRaceMaxN];
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
@@ -260,16 +262,49 @@ sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
             }
         }
     }
-    // degenerate weights (all the mass on fewer than S items): complete with the lowest unused indices
-    for (int n = 0; count < S && n < N; ++n) {
-        bool dup = false;
+    // Peaked weights (almost all the mass on fewer than S items): 64 rejected draws.  The remaining members are
+    // then drawn EXACTLY -- Gumbel-max over the items not chosen yet, keys logit + G on fresh Philox words, the
+    // `S - count` largest win -- which is the same Plackett-Luce law continued, and resolves weights that the fp32
+    // prefix sums cannot (a weight of 1e-10 beside a total of 1).  O(N) for this thread; rare by construction.
+    if (count < S) {
+        const int need = S - count;
+        float bk[S];
+        int bi[S];
         DRB_UNROLL
-        for (int j = 0; j < S; ++j) dup = dup || (j < count && chosen[j] == n);
-        if (!dup) {
+        for (int j = 0; j < S; ++j) { bk[j] = -INFINITY; bi[j] = -1; }
+        for (int n4 = 0; n4 < N; n4 += 4) {
+            const Philox4 r = philox4x32_10((uint32_t)(16 + (n4 >> 2)), (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0, k1);
+            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
             DRB_UNROLL
-            for (int j = 0; j < S; ++j)
-                if (j == count) chosen[j] = n;
-            ++count;
+            for (int t = 0; t < 4; ++t) {
+                const int n = n4 + t;
+                if (n >= N) break;
+                bool dup = false;
+                DRB_UNROLL
+                for (int j = 0; j < S; ++j) dup = dup || (j < count && chosen[j] == n);
+                if (dup) continue;
+                const float u = ((float)(rr[t] >> 8) + 0.5f) * 5.9604644775390625e-08f;
+                float key = __ldg(lg + n) - __logf(-__logf(u));
+                int id = n;
+                // insertion into the descending list of the `need` best (ties: lower index first, like top-k)
+                DRB_UNROLL
+                for (int j = 0; j < S; ++j) {
+                    if (j < need && (key > bk[j] || (key == bk[j] && bi[j] < 0))) {
+                        const float tk = bk[j]; const int ti = bi[j];
+                        bk[j] = key; bi[j] = id;
+                        key = tk; id = ti;
+                    }
+                }
+            }
+        }
+        DRB_UNROLL
+        for (int q = 0; q < S; ++q) {
+            if (q < need && bi[q] >= 0) {
+                DRB_UNROLL
+                for (int j = 0; j < S; ++j)
+                    if (j == count) chosen[j] = bi[q];
+                ++count;
+            }
         }
     }
     // ascending order, like the reference's boolean-mask gather (ransac.py:65)
@@ -362,8 +397,9 @@ __device__ __forceinline__ void train_sweep(const float* __restrict__ wtab, cons
 
 template <int S, int kTrainWarps>
 __global__ void __launch_bounds__(kTrainWarps * 32)
-sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, int K, int N,
-                    int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out) {
+sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t offset, const unsigned long long* __restrict__ offset_dev, int K,
+                    int N, int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out) {
+    if (offset_dev) offset += *offset_dev;  // stream position kept on the device (CUDA-graph replay draws fresh noise)
     constexpr int kTrainChunk = train_chunk(kTrainWarps);
     __shared__ __align__(16) float wtab[kTrainChunk];     // exp(l - lmax)
     __shared__ __align__(16) float winv[kTrainChunk];     // exp(lmax - l)
@@ -496,8 +532,10 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
 template <int S>
 __global__ void __launch_bounds__(kSamplerWarps * 32)
 sample_kernel(const float* __restrict__ logits, const float* __restrict__ noise, uint64_t seed, uint64_t offset,
-              float tau, int B, int K, int N, int32_t* __restrict__ idx_out, float* __restrict__ lse_out,
-              float* __restrict__ sel_key_out, float* __restrict__ noise_out) {
+              const unsigned long long* __restrict__ offset_dev, float tau, int B, int K, int N,
+              int32_t* __restrict__ idx_out, float* __restrict__ lse_out, float* __restrict__ sel_key_out,
+              float* __restrict__ noise_out) {
+    if (offset_dev) offset += *offset_dev;  // stream position kept on the device (CUDA-graph replay draws fresh noise)
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
     const long long row = (long long)blockIdx.x * kSamplerWarps + warp;  // b * K + k
@@ -608,9 +646,10 @@ constexpr int kBwdThreads = 128;
 
 __global__ void __launch_bounds__(kBwdThreads)
 sample_bwd_dense_kernel(const float* __restrict__ logits, const float* __restrict__ noise, uint64_t seed,
-                        uint64_t offset, float tau, int B, int K, int N, int k_per_block,
-                        const float* __restrict__ lse, const float* __restrict__ ck,
+                        uint64_t offset, const unsigned long long* __restrict__ offset_dev, float tau, int B, int K, int N,
+                        int k_per_block, const float* __restrict__ lse, const float* __restrict__ ck,
                         float* __restrict__ grad_logits) {
+    if (offset_dev) offset += *offset_dev;  // stream position kept on the device (CUDA-graph replay draws fresh noise)
     const int b = blockIdx.z;
     const int n0 = (blockIdx.x * kBwdThreads + threadIdx.x) * 4;
     const int k_begin = blockIdx.y * k_per_block;
@@ -664,9 +703,10 @@ using namespace drb;
 
 static int check_launch() { return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA; }
 
-extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau, int B,
-                          int K, int N, int s, int32_t* idx, float* lse, float* sel_key, float* noise_out,
-                          void* stream) {
+extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t offset,
+                          const uint64_t* offset_dev, float tau, int B, int K, int N, int s, int32_t* idx, float* lse,
+                          float* sel_key, float* noise_out, void* stream) {
+    const unsigned long long* od = reinterpret_cast<const unsigned long long*>(offset_dev);
     if (!logits || !idx) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || N <= 0 || s <= 0 || s > N || !(tau > 0.f)) return DRB_ERR_BAD_SHAPE;
     cudaStream_t st = (cudaStream_t)stream;
@@ -681,9 +721,9 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
 #define DRB_LAUNCH_TRAIN(S_)                                                                                      \
     case S_:                                                                                                      \
         if (one_chunk)                                                                                            \
-            sample_train_kernel<S_, 8><<<tgrid, 256, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key);     \
+            sample_train_kernel<S_, 8><<<tgrid, 256, 0, st>>>(logits, seed, offset, od, K, N, idx, lse, sel_key); \
         else                                                                                                      \
-            sample_train_kernel<S_, 16><<<tgrid, 512, 0, st>>>(logits, seed, offset, K, N, idx, lse, sel_key);    \
+            sample_train_kernel<S_, 16><<<tgrid, 512, 0, st>>>(logits, seed, offset, od, K, N, idx, lse, sel_key); \
         break;
         switch (s) {
             DRB_LAUNCH_TRAIN(3)
@@ -701,7 +741,7 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
         const dim3 rgrid((K + kSamplerWarps - 1) / kSamplerWarps, B);
 #define DRB_LAUNCH_RACE(S_)                                                                   \
     case S_:                                                                                  \
-        sample_race_kernel<S_><<<rgrid, block, 0, st>>>(logits, seed, offset, K, N, idx);     \
+        sample_race_kernel<S_><<<rgrid, block, 0, st>>>(logits, seed, offset, od, K, N, idx); \
         break;
         switch (s) {
             DRB_LAUNCH_RACE(3)
@@ -716,8 +756,8 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
     }
 #define DRB_LAUNCH_SAMPLE(S_)                                                                                   \
     case S_:                                                                                                    \
-        sample_kernel<S_><<<grid, block, 0, st>>>(logits, noise, seed, offset, tau, B, K, N, idx, lse, sel_key, \
-                                                  noise_out);                                                   \
+        sample_kernel<S_><<<grid, block, 0, st>>>(logits, noise, seed, offset, od, tau, B, K, N, idx, lse,      \
+                                                  sel_key, noise_out);                                          \
         break;
     switch (s) {
         DRB_LAUNCH_SAMPLE(3)
@@ -740,13 +780,8 @@ extern "C" int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offs
     const dim3 grid((K + kSetThreads - 1) / kSetThreads, B);
 #define DRB_LAUNCH_SETS(S_)                                                                                       \
     case S_: {                                                                                                    \
-        static bool configured = false;                                                                           \
-        if (!configured) {                                                                                        \
-            if (cudaFuncSetAttribute(sample_sets_kernel<S_>, cudaFuncAttributeMaxDynamicSharedMemorySize,         \
-                                     200 * 1024) != cudaSuccess)                                                  \
-                return DRB_ERR_CUDA;                                                                              \
-            configured = true;                                                                                    \
-        }                                                                                                         \
+        static std::atomic<unsigned long long> configured{0};                                                     \
+        if (!ensure_dynamic_smem(sample_sets_kernel<S_>, 200 * 1024, configured)) return DRB_ERR_CUDA;            \
         sample_sets_kernel<S_><<<grid, kSetThreads, smem, (cudaStream_t)stream>>>(                                \
             logits, seed, offset, reinterpret_cast<const unsigned long long*>(offset_dev), K, N, idx);            \
         break;                                                                                                    \
@@ -763,8 +798,9 @@ extern "C" int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offs
     return check_launch();
 }
 
-extern "C" int drb_sample_backward(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau,
-                                   int B, int K, int N, int s, const int32_t* idx, const float* lse,
+extern "C" int drb_sample_backward(const float* logits, const float* noise, uint64_t seed, uint64_t offset,
+                                   const uint64_t* offset_dev, float tau, int B, int K, int N, int s,
+                                   const int32_t* idx, const float* lse,
                                    const float* sel_key, const float* g_sel, float* scratch, float* grad_logits,
                                    void* stream) {
     if (!logits || !idx || !lse || !sel_key || !g_sel || !scratch || !grad_logits) return DRB_ERR_NULL_POINTER;
@@ -782,7 +818,8 @@ extern "C" int drb_sample_backward(const float* logits, const float* noise, uint
     const int k_per_block = (K + k_split - 1) / k_split;
     k_split = (K + k_per_block - 1) / k_per_block;
     dim3 grid(n_blocks, k_split, B);
-    sample_bwd_dense_kernel<<<grid, kBwdThreads, 0, st>>>(logits, noise, seed, offset, tau, B, K, N, k_per_block, lse,
-                                                          ck, grad_logits);
+    sample_bwd_dense_kernel<<<grid, kBwdThreads, 0, st>>>(logits, noise, seed, offset,
+                                                          reinterpret_cast<const unsigned long long*>(offset_dev), tau,
+                                                          B, K, N, k_per_block, lse, ck, grad_logits);
     return check_launch();
 }

@@ -19,6 +19,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"
+#include "device_cfg.cuh"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
 #include "msac_records.cuh"
@@ -200,15 +201,17 @@ score_msac_stream_kernel(const float* __restrict__ matches, const float* __restr
 }
 
 static int ss_grid() {
-    static const int grid = []() {
-        int dev = 0, sms = 148, per_sm = 16;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_msac_stream_kernel, kSsLanes, 0) != cudaSuccess ||
-            per_sm < 1)
-            per_sm = 16;
-        return sms * per_sm;
-    }();
+    // CTAs per SM of this kernel x SMs of the CURRENT device, cached per device
+    static std::atomic<int> cache[kMaxDevices];
+    const int dev = current_device();
+    int grid = cache[dev].load(std::memory_order_relaxed);
+    if (grid > 0) return grid;
+    int per_sm = 16;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, score_msac_stream_kernel, kSsLanes, 0) != cudaSuccess ||
+        per_sm < 1)
+        per_sm = 16;
+    grid = sm_count_current_device() * per_sm;
+    cache[dev].store(grid, std::memory_order_relaxed);
     return grid;
 }
 

@@ -35,6 +35,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"
+#include "device_cfg.cuh"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
 #include "msac_tc_layout.cuh"
@@ -327,15 +328,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
     }
 }
 
-static int tc_sm_count() {
-    static const int sms = []() {
-        int dev = 0, n = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n > 0 ? n : 148;
-    }();
-    return sms;
-}
+static int tc_sm_count() { return sm_count_current_device(); }
 
 }  // namespace tc
 }  // namespace drb
@@ -363,9 +356,8 @@ namespace tc {
 template <bool BF16, bool PAIR, int EPI>
 static int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr,
                   int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc_kernel<BF16, PAIR, EPI>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (attr != cudaSuccess) return DRB_ERR_CUDA;
+    static std::atomic<unsigned long long> configured{0};
+    if (!ensure_dynamic_smem(score_msac_tc_kernel<BF16, PAIR, EPI>, kSmemBytes, configured)) return DRB_ERR_CUDA;
     const int tiles = (N + kTileM - 1) / kTileM;
     msac_tc_features_kernel<BF16><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kTileModels - 1) / kTileModels);

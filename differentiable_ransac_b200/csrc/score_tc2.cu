@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"
+#include "device_cfg.cuh"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
 #include "msac_tc_layout.cuh"
@@ -314,24 +315,15 @@ score_msac_tc2_kernel(const uint32_t* __restrict__ images, const float* __restri
     }
 }
 
-static int sm_count() {
-    static const int sms = []() {
-        int dev = 0, n = 148;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        return n > 0 ? n : 148;
-    }();
-    return sms;
-}
+static int sm_count() { return sm_count_current_device(); }
 
 size_t workspace_bytes(int B, int N) { return (size_t)B * ((N + kPts - 1) / kPts) * kPtBytes; }
 
 template <bool BF16, int EPI, bool PAIR>
 int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr, int B,
            int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(score_msac_tc2_kernel<BF16, EPI, PAIR>,
-                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes);
-    if (attr != cudaSuccess) return DRB_ERR_CUDA;
+    static std::atomic<unsigned long long> configured{0};
+    if (!ensure_dynamic_smem(score_msac_tc2_kernel<BF16, EPI, PAIR>, kSmemBytes, configured)) return DRB_ERR_CUDA;
     const int tiles = (N + kPts - 1) / kPts;
     msac_tc2_features_kernel<BF16><<<dim3(tiles, B), 96, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kModels - 1) / kModels);

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"
+#include "device_cfg.cuh"
 #include "drb_common.cuh"
 #include "e5_math.cuh"
 #include "e5_backward.cuh"
@@ -306,13 +307,8 @@ extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int
     if (!matches || !models || !nsol) return DRB_ERR_NULL_POINTER;
     if (cmodels && (!cids || !ccount)) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
-    static bool configured = false;
-    if (!configured) {
-        if (cudaFuncSetAttribute(solve_e5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kE5SmemBytes) !=
-            cudaSuccess)
-            return DRB_ERR_CUDA;
-        configured = true;
-    }
+    static std::atomic<unsigned long long> configured{0};
+    if (!ensure_dynamic_smem(solve_e5_kernel, kE5SmemBytes, configured)) return DRB_ERR_CUDA;
     const long long rows = (long long)B * K;
     solve_e5_kernel<<<(unsigned)((rows + kE5Threads - 1) / kE5Threads), kE5Threads, kE5SmemBytes,
                       (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol, cmodels, cids, ccount);

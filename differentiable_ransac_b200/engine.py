@@ -18,14 +18,17 @@ import os
 from . import ops
 
 # Scorer of the pipelined service (E5TestService with more than one slot):
-#   "auto"     (default) the most precise tensor-core variant that verifies itself on this device -- "tc_bf16", then
-#              "tc_tf32" -- else "block"; see service_scorer()
+#   "auto"     (default) the fastest exact-operand tensor-core variant that verifies itself on this device --
+#              "tc_bf16p" (0.105 ms at cfg2), then "tc_bf16" (0.122), then "tc_tf32" -- else "block"; see
+#              service_scorer().  Every variant is pinned to the fp64 oracle at 1e-4 (BF16) / 5e-4 (TF32) by
+#              tests/test_gpu_score_tc.py (profiles/r2_tc_oracle_parity.log)
 #   "tc_tf32"  tensor cores, two TF32 words per operand (csrc/score_tc.cu): measured on B200 at cfg2 0.175 ms per
 #              pipelined batch against 0.254 ms with "block" (profiles/r1_notes.md); per-model scores within 1.4e-4
 #              relative of the FP32 kernels (the winner's score: ~1e-6), so the winner can differ from the FP32
 #              kernels' only between near-ties
 #   "tc_bf16"  three BF16 words per operand: exact operands, fp32-level scores (5e-6 against fp64 on the host model),
 #              same time
+#   "tc_bf16p" the same with ONE reciprocal per pair of neighbouring models (halves the SFU work)
 #   "block"    FP32, one CTA per 32 models; bit-identical to what `ransac_e5_test(scorer="block")` returns
 #   "stream"   FP32 work queue
 SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "auto")
@@ -70,7 +73,7 @@ def tc_scorer_agrees(device, scorer="tc_tf32", tol=5e-4):
 
 def service_scorer(device, B, requested=None):
     """The scorer a pipelined service uses: `requested` (or SERVICE_SCORER) if it names one; "auto" -> the first of
-    "tc_bf16", "tc_tf32" that agrees with the FP32 kernel on this device (tc_scorer_agrees), else "block".  A
+    "tc_bf16p", "tc_bf16", "tc_tf32" that agrees with the FP32 kernel on this device (tc_scorer_agrees), else "block".  A
     tensor-core scorer named by SERVICE_SCORER is checked the same way and replaced by "block" (with a warning) if
     it fails; one passed explicitly by the caller is taken as is.  drb_score_msac_tc takes at most 1024 pairs."""
     if requested is not None:
@@ -80,7 +83,7 @@ def service_scorer(device, B, requested=None):
         return name
     if int(B) > 1024:
         return "block"
-    for cand in (("tc_bf16", "tc_tf32") if name == "auto" else (name,)):
+    for cand in (("tc_bf16p", "tc_bf16", "tc_tf32") if name == "auto" else (name,)):
         if tc_scorer_agrees(device, cand):
             return cand
     import warnings
@@ -165,12 +168,15 @@ def ransac_f7_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
 
 # ---- the chunked loop with adaptive exit, no host sync -----------------------
 def ransac_test_adaptive(matches, logits, rbs, max_iterations, thr, sample_size=5, confidence=0.999, eps=1e-5,
-                         tau=1.0, noise=None, seed=0, offset=0, sampler="sets"):
+                         tau=1.0, noise=None, seed=0, offset=0, sampler="sets", adaptive_exponent=None):
     """What `RANSAC.__call__` returns in test mode with lo = 0 (ransac.py:55-144) for B pairs at once: all
     C = ceil(max_iterations / rbs) chunks go through sample -> solve -> score in one pass, then
     `drb_adaptive_select` replays the loop's bookkeeping (per-chunk arg-max, strict improvement, adaptive
     iteration budget from the winner's inlier count) on the device.  `noise` (optional) is [B, C*rbs, N], chunk c
-    = rows [c*rbs, (c+1)*rbs).  -> dict(best_model, best_id, best_score, mask, ninl, iterations [B], ...)."""
+    = rows [c*rbs, (c+1)*rbs).  -> dict(best_model, best_id, best_score, mask, ninl, iterations [B], ...).
+    `sample_size` picks the solver (the SAMPLER's draw size); `adaptive_exponent` is the exponent of the iteration
+    budget, the ESTIMATOR's `sample_size` in the reference (ransac.py:207,214) -- 7 for the fundamental-matrix
+    estimator even with 8-point samples; defaults to `sample_size`."""
     B = matches.shape[0]
     C = -(-int(max_iterations) // int(rbs))
     K = C * int(rbs)
@@ -199,7 +205,8 @@ def ransac_test_adaptive(matches, logits, rbs, max_iterations, thr, sample_size=
         raise NotImplementedError("test mode supports the 5-, 7- and 8-point samplers")
     dense = models.reshape(B, -1, 9)
     best, its, chunk_best, chunk_ninl = ops.adaptive_select(matches, dense, scores, thr, int(rbs) * slots, rbs,
-                                                            max_iterations, sample_size, confidence, eps, cc, cid)
+                                                            max_iterations, int(adaptive_exponent or sample_size),
+                                                            confidence, eps, cc, cid)
     best_id, best_score, best_model, mask, ninl = ops.best_finalize(matches, dense, best, thr)
     out = dict(best_model=best_model, best_id=best_id, best_score=best_score, mask=mask.view(torch.bool), ninl=ninl,
                iterations=its, idx=idx, models=models, chunk_ninl=chunk_ninl)
@@ -376,6 +383,123 @@ def match_loss(models, valid, pts, npts=None):
     return (row * v).sum(1) / (v.sum(1).clamp_min(1.0) * n.clamp_min(1.0))
 
 
+# ---- one training step without autograd bookkeeping, optionally ONE CUDA graph ------------------------
+class TrainStep:
+    """Forward + loss + backward of the hot path for one batch as a fixed sequence of C-ABI launches on static
+    buffers -- what `train.py:150-175` does through autograd (`HypothesizeE5/F8/Rigid` -> `match_loss` /
+    `RigidResidual` -> `.backward()`), minus the ~25 small torch ops, the graph building and the per-step
+    allocations that made the cfg5 step host-bound (0.6-0.7 ms in round 1 for ~0.3 ms of kernels).
+
+        kind "e5":    sample 5 -> Nister five-point -> slot closest to the GT model -> min(episym, 1) over the
+                      GT-inlier correspondences (loss.py:138-151), mean over valid hypotheses and pairs
+        kind "f8":    sample 8 -> normalised eight-point -> the same loss
+        kind "rigid": sample 3 -> rigid 3-point -> sum of squared residuals over all points
+                      (rigid...solver.py:76-89), mean over valid hypotheses, points and pairs
+
+    `run(...)` copies the batch into the static buffers and replays; afterwards `loss` [1], `loss_pairs` [B],
+    `grad_logits` [B,N] (= d loss / d logits, what CLNet's backward consumes, train.py:171) and, when asked,
+    `grad_matches` hold the step's results.  The Philox stream position lives on the device and advances inside
+    the graph: every replay draws fresh Gumbel noise, and the backward regenerates exactly the forward's.
+    Equal to the autograd path launch for launch (tests/test_gpu_train_step.py)."""
+
+    def __init__(self, kind, B, N, K, device, P=None, seed=0, tau=1.0, graph=True, want_grad_matches=False,
+                 sign_invariant=True, flag=True):
+        if kind not in ("e5", "f8", "rigid"):
+            raise ValueError(kind)
+        self.kind, self.B, self.N, self.K, self.tau = kind, int(B), int(N), int(K), float(tau)
+        self.seed, self.graph_mode = int(seed), bool(graph)
+        self.want_gm, self.sign_invariant, self.flag = bool(want_grad_matches), bool(sign_invariant), bool(flag)
+        self.device = torch.device(device)
+        D = 6 if kind == "rigid" else 4
+        z = dict(dtype=torch.float32, device=self.device)
+        self.matches = torch.zeros(B, N, D, **z)
+        self.logits = torch.zeros(B, N, **z)
+        if kind != "rigid":
+            self.P = int(P if P is not None else N)
+            self.pts = torch.zeros(B, self.P, 4, **z)          # GT-inlier correspondences, zero-padded
+            self.npts = torch.zeros(B, dtype=torch.int32, device=self.device)
+        if kind == "e5":
+            self.gt = torch.zeros(B, 3, 3, **z)
+        self.counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+        self.stream = torch.cuda.Stream(device=self.device)
+        self.g = None
+        self.loss = self.loss_pairs = self.grad_logits = self.grad_matches = None
+
+    def _body(self):
+        B, K, N = self.B, self.K, self.N
+        s = {"e5": 5, "f8": 8, "rigid": 3}[self.kind]
+        m, lg, ctr = self.matches, self.logits, self.counter
+        idx, lse, sel_key, _ = ops.sample(lg, K, s, self.tau, None, self.seed, 0, want_lse=True, offset_dev=ctr)
+        if self.kind == "e5":
+            models, nsol = ops.solve_e5(m, idx)
+            sel, used = ops.select_closest(models, nsol, self.gt, self.sign_invariant)
+            valid = sel >= 0
+        elif self.kind == "f8":
+            used, valid = ops.solve_f8(m, idx)
+            valid = valid.bool()
+        else:
+            used, valid = ops.solve_rigid3(m, idx, self.flag)
+            valid = valid.bool()
+        v = valid.to(torch.float32)
+        if self.kind == "rigid":
+            row, _ = ops.rigid_residual_forward(m, used, want_ninl=False)
+            row = torch.where(valid, row, torch.zeros_like(row))          # invalid models carry NaN
+            denom = v.sum(1).clamp_min(1.0) * float(N)
+        else:
+            row = ops.episym_forward(self.pts, used, self.npts, valid)
+            denom = v.sum(1).clamp_min(1.0) * self.npts.to(torch.float32).clamp_min(1.0)
+        loss_pairs = (row * v).sum(1) / denom
+        g_row = v / (denom[:, None] * float(B))                            # d mean_b(loss_b) / d row
+        if self.kind == "rigid":
+            g_used = ops.rigid_residual_backward(m, torch.where(valid[..., None, None], used, torch.zeros_like(used)),
+                                                 g_row)
+            g_pts = ops.solve_rigid3_backward(m, idx, g_used.reshape(B, K, 16), self.flag)
+        else:
+            g_used = ops.episym_backward(self.pts, used, g_row, self.npts, valid)
+            if self.kind == "e5":
+                g_pts = ops.solve_e5_backward(m, idx, models, sel, g_used.reshape(B, K, 9))
+            else:
+                g_pts = ops.solve_f8_backward(m, idx, g_used.reshape(B, K, 9), used)
+        g_sel, gm = ops.gather_backward(m, idx, g_pts, want_grad_matches=self.want_gm)
+        gl = ops.sample_backward(lg, idx, lse, sel_key, g_sel, self.tau, None, self.seed, 0, offset_dev=ctr)
+        ctr.add_(1)
+        return loss_pairs.mean().reshape(1), loss_pairs, gl, gm
+
+    def _capture(self):
+        st = self.stream
+        st.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(st):
+            self._body()                                   # eager warm-up (lazy attributes, allocator pools)
+        st.synchronize()
+        self.counter.zero_()
+        self.g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.g, stream=st):
+            self.loss, self.loss_pairs, self.grad_logits, self.grad_matches = self._body()
+
+    def load(self, matches, logits, gt=None, pts=None, npts=None):
+        """Copy a batch (device or pinned-host tensors) into the static buffers, on the current stream."""
+        self.matches.copy_(matches, non_blocking=True)
+        self.logits.copy_(logits, non_blocking=True)
+        if gt is not None:
+            self.gt.copy_(gt, non_blocking=True)
+        if pts is not None:
+            self.pts.copy_(pts, non_blocking=True)
+            self.npts.copy_(npts, non_blocking=True)
+
+    def run(self, matches=None, logits=None, gt=None, pts=None, npts=None):
+        """One step on the current stream; returns (loss [1], grad_logits [B,N]) -- static tensors, overwritten by
+        the next `run`."""
+        if matches is not None:
+            self.load(matches, logits, gt, pts, npts)
+        if self.graph_mode:
+            if self.g is None:
+                self._capture()
+            self.g.replay()
+        else:
+            self.loss, self.loss_pairs, self.grad_logits, self.grad_matches = self._body()
+        return self.loss, self.grad_logits
+
+
 # ---- host-buffer service: test-mode batches from pinned host memory, pipelined over streams -----------
 class E5TestService:
     """Steady-state test-mode service for batches that live in HOST memory (the reference's
@@ -389,7 +513,7 @@ class E5TestService:
     the FMA-bound scoring kernel of batch i leaves idle (measured on B200, cfg2: 0.309 -> 0.256 ms per batch
     with two slots, profiles/r1_notes.md)."""
 
-    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False, host_io=True, scorer=None):
+    def __init__(self, B, N, K, device, slots=2, seed=0, graph=False, host_io=True, scorer=None, want_mask=False):
         self.B, self.N, self.K, self.seed = int(B), int(N), int(K), int(seed)
         # one slot: whatever a single call uses (ops default); several: service_scorer() unless the caller says
         self.scorer = scorer if (scorer is not None or int(slots) <= 1) else service_scorer(device, B)
@@ -397,6 +521,9 @@ class E5TestService:
         # host_io=False: batches are already on the device -- submit(slot, packed=<device tensor>) copies the
         # packed batch into the slot (device to device) and results stay on the device (`dev_out[slot]`)
         self.host_io = bool(host_io)
+        # want_mask: the winner's inlier mask [B,N] (what `RANSAC.__call__` returns as best_mask, ransac.py:200)
+        # is part of every batch's results: a second, B*N-byte copy beside the packed floats
+        self.want_mask = bool(want_mask)
         self.device = torch.device(device)
         self.slots = int(slots)
         self.n_in = B * N * 4 + B * N + B
@@ -405,6 +532,9 @@ class E5TestService:
         self.host_out = [torch.empty(self.n_out, dtype=torch.float32).pin_memory() for _ in range(self.slots)]
         self.dev_in = [torch.empty(self.n_in, dtype=torch.float32, device=self.device) for _ in range(self.slots)]
         self.dev_out = [torch.empty(self.n_out, dtype=torch.float32, device=self.device) for _ in range(self.slots)]
+        if self.want_mask:
+            self.host_mask = [torch.empty(B, N, dtype=torch.uint8).pin_memory() for _ in range(self.slots)]
+            self.dev_mask = [torch.empty(B, N, dtype=torch.uint8, device=self.device) for _ in range(self.slots)]
         self.copy_stream = torch.cuda.Stream(device=self.device)
         self.compute = [torch.cuda.Stream(device=self.device) for _ in range(self.slots)]
         self.copied = [torch.cuda.Event() for _ in range(self.slots)]
@@ -413,7 +543,7 @@ class E5TestService:
         self.busy = [False] * self.slots
         self.step = 0
         self.h2d_bytes = self.n_in * 4
-        self.d2h_bytes = self.n_out * 4
+        self.d2h_bytes = self.n_out * 4 + (B * N if self.want_mask else 0)
         # graph mode: one CUDA graph per slot (copy-in, four kernels, copy-out), replayed by submit(); the Philox
         # stream position of the slot's next batch lives on the device and is advanced inside the graph, so
         # batch i draws with offset i exactly as in eager mode when the slots are used round-robin
@@ -428,6 +558,12 @@ class E5TestService:
                            scorer=self.scorer)
         return o, torch.cat((o["best_model"].flatten(), o["best_id"].float(), o["best_score"], o["ninl"].float()))
 
+    def _copy_out(self, slot, o, packed):
+        """Results of the slot's batch -> its output buffers (pinned host memory when host_io)."""
+        (self.host_out if self.host_io else self.dev_out)[slot].copy_(packed, non_blocking=True)
+        if self.want_mask:
+            (self.host_mask if self.host_io else self.dev_mask)[slot].copy_(o["mask"].view(torch.uint8), non_blocking=True)
+
     def _capture(self, slot):
         ks = self.compute[slot]
         ks.wait_stream(torch.cuda.current_stream())
@@ -436,41 +572,59 @@ class E5TestService:
         ks.synchronize()
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, stream=ks):
-            if self.host_io:
-                self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
-            _, packed = self._body(slot, 0, self.counters[slot])
+            # the host->device copy stays OUTSIDE the graph (its source may be the caller's own pinned tensors)
+            o, packed = self._body(slot, 0, self.counters[slot])
             self.counters[slot].add_(self.slots)
-            (self.host_out if self.host_io else self.dev_out)[slot].copy_(packed, non_blocking=True)
+            self._copy_out(slot, o, packed)
         self.graphs[slot] = g
 
     def stage(self, slot, matches, logits, thr):
         """Pack one batch of host tensors into the slot's pinned staging buffer (a host-side memcpy; callers
-        that produce their batches directly in `host_in[slot]` skip this)."""
+        whose tensors are pinned already hand them to `submit(host=...)` instead and skip this)."""
         B, N = self.B, self.N
         buf = self.host_in[slot]
         buf[: B * N * 4].copy_(matches.reshape(-1))
         buf[B * N * 4: B * N * 5].copy_(logits.reshape(-1))
         buf[B * N * 5:].copy_(thr.reshape(-1))
 
-    def submit(self, slot=None, packed=None):
-        """Enqueue the batch staged in `host_in[slot]` (host_io) or given as one packed device tensor
-        (matches | logits | thr, `n_in` floats; host_io=False); returns the slot."""
+    def _h2d(self, slot, host):
+        """Enqueue the slot's host->device copy on the current stream: from the staging buffer, or straight from the
+        caller's (matches [B,N,4], logits [B,N], thr [B]) host tensors."""
+        B, N = self.B, self.N
+        buf = self.dev_in[slot]
+        if host is None:
+            buf.copy_(self.host_in[slot], non_blocking=True)
+            return
+        m, lg, thr = host
+        buf[: B * N * 4].view(B, N, 4).copy_(m, non_blocking=True)
+        buf[B * N * 4: B * N * 5].view(B, N).copy_(lg, non_blocking=True)
+        buf[B * N * 5:].copy_(thr, non_blocking=True)
+
+    def submit(self, slot=None, packed=None, host=None):
+        """Enqueue one batch; returns the slot.  host_io: the batch staged in `host_in[slot]`, or `host` =
+        (matches, logits, thr) host tensors copied directly (pinned: asynchronously).  host_io=False: `packed`, one
+        device tensor (matches | logits | thr, `n_in` floats)."""
         if slot is None:
             slot = self.step % self.slots
         if self.busy[slot] and self.host_io:
             self.done[slot].synchronize()          # the slot's previous results must have been collected
-        B, N = self.B, self.N
         cs, ks = self.copy_stream, self.compute[slot]
         if not self.host_io:
             if self.graph and self.graphs[slot] is None:
                 self._capture(slot)
-            with torch.cuda.stream(ks):            # in order on the slot's stream: no events needed
+            # `packed` was produced on the caller's current stream: the slot's stream waits for it, and the
+            # allocator must not hand its block to anyone while the copy is pending.  The same wait orders this
+            # batch behind whatever the caller enqueued on its stream to read the slot's previous results
+            # (`dev_out[slot]`); a consumer on any OTHER stream must `join()` before the slot comes round again.
+            ks.wait_stream(torch.cuda.current_stream(self.device))
+            packed.record_stream(ks)
+            with torch.cuda.stream(ks):
                 self.dev_in[slot].copy_(packed, non_blocking=True)
                 if self.graph:
                     self.graphs[slot].replay()
                 else:
-                    _, out = self._body(slot, self.step, None)
-                    self.dev_out[slot].copy_(out, non_blocking=True)
+                    o, out = self._body(slot, self.step, None)
+                    self._copy_out(slot, o, out)
                 self.done[slot].record(ks)
             self.busy[slot] = True
             self.step += 1
@@ -478,7 +632,8 @@ class E5TestService:
         if self.graph:
             if self.graphs[slot] is None:
                 self._capture(slot)
-            with torch.cuda.stream(ks):
+            with torch.cuda.stream(ks):            # in order on the slot's stream: copy-in, graph (kernels + copy-out)
+                self._h2d(slot, host)
                 self.graphs[slot].replay()
                 self.done[slot].record(ks)
             self.busy[slot] = True
@@ -486,13 +641,13 @@ class E5TestService:
             return slot
         cs.wait_event(self.consumed[slot])         # the previous batch of this slot has read its inputs
         with torch.cuda.stream(cs):
-            self.dev_in[slot].copy_(self.host_in[slot], non_blocking=True)
+            self._h2d(slot, host)
             self.copied[slot].record(cs)
         ks.wait_event(self.copied[slot])
         with torch.cuda.stream(ks):
-            _, packed = self._body(slot, self.step, None)
+            o, packed = self._body(slot, self.step, None)
             self.consumed[slot].record(ks)
-            self.host_out[slot].copy_(packed, non_blocking=True)
+            self._copy_out(slot, o, packed)
             self.done[slot].record(ks)
         self.busy[slot] = True
         self.step += 1
@@ -505,8 +660,11 @@ class E5TestService:
         self.busy[slot] = False
         B = self.B
         out = (self.host_out if self.host_io else self.dev_out)[slot]
-        return dict(best_model=out[: 9 * B].view(B, 3, 3), best_id=out[9 * B: 10 * B].to(torch.int32),
-                    best_score=out[10 * B: 11 * B], ninl=out[11 * B: 12 * B].to(torch.int32))
+        res = dict(best_model=out[: 9 * B].view(B, 3, 3), best_id=out[9 * B: 10 * B].to(torch.int32),
+                   best_score=out[10 * B: 11 * B], ninl=out[11 * B: 12 * B].to(torch.int32))
+        if self.want_mask:
+            res["mask"] = (self.host_mask if self.host_io else self.dev_mask)[slot].view(torch.bool)
+        return res
 
     def drain(self):
         for s in range(self.slots):

@@ -54,7 +54,7 @@ class RANSACLayer(nn.Module):
         self.estimator = RANSAC(solver, sampler, MSACScore(opt.device), max_iterations=max_iters, fmat=opt.fmat,
                                 train=opt.tr, ransac_batch_size=opt.ransac_batch_size, sampler_id=opt.sampler,
                                 weighted=opt.weighted, threshold=opt.threshold,
-                                adaptive=getattr(opt, "adaptive", True))
+                                adaptive=getattr(opt, "adaptive", True), final_refit=getattr(opt, "final_refit", True))
 
     def _points(self, points, im_size1, im_size2):
         pts = points.clone()
@@ -75,10 +75,25 @@ class RANSACLayer(nn.Module):
             Es = Es[~torch.isnan(Es).flatten(1).any(1)]
         return Es, dt
 
+    def thresholds(self, K1, K2, B, device):
+        """ransac.py:49-53 for B pairs at once: threshold / ((K1[0,0] + K1[1,1] + K1[0,0] + K2[1,1]) / 4), computed
+        where K1 / K2 live (no device->host sync when they are on the GPU, as test.py:31 puts them)."""
+        drv = self.estimator
+        if drv.fmat:
+            return torch.full((B,), float(drv.threshold), dtype=torch.float32, device=device)
+        K1, K2 = torch.as_tensor(K1), torch.as_tensor(K2)
+        mult = (K1[..., 0, 0] + K1[..., 1, 1] + K1[..., 0, 0] + K2[..., 1, 1]) / 4
+        return (float(drv.threshold) / mult).to(dtype=torch.float32).expand(B).to(device)
+
     def forward_batched(self, points, weights, K1, K2, im_size1=None, im_size2=None, ground_truth=None, K=None):
         """points [B,N,4], weights [B,N], K1/K2 [B,3,3] -> list_B[Es_b] (train: [K_b,3,3]; test: [3,3]),
-        with ONE launch per stage for the whole batch."""
+        with ONE launch per stage for the whole batch.  HOST tensors in test mode go through the pipelined
+        service (`submit` / `collect`); the winners' inlier masks and scores of the last call are kept in
+        `self.last_masks` / `self.last_scores`."""
         B = points.shape[0]
+        if not self.opt.tr and points.device.type == "cpu" and self._service_ok():
+            Es, self.last_masks, self.last_scores = self.collect(self.submit(points, weights, K1, K2, K=K))
+            return Es
         pts = points
         if self.opt.fmat:
             pts = torch.stack([self._points(points[b], im_size1[b], im_size2[b]) for b in range(B)])
@@ -92,10 +107,49 @@ class RANSACLayer(nn.Module):
                 models, valid = engine.HypothesizeE5.apply(pts, weights, ground_truth.float(), Kt, smp.tau, None,
                                                            smp.seed, smp._next_offset(), True)
             return [models[b][valid[b]] for b in range(B)]
-        thr = torch.tensor([normalized_threshold(drv.threshold, K1[b], K2[b], drv.fmat) for b in range(B)],
-                           device=points.device)
-        out = drv.batched_test(pts, weights, thr, K)
-        return [out["best_model"][b] for b in range(B)]
+        out = drv.batched_test(pts, weights, self.thresholds(K1, K2, B, points.device), K)
+        self.last_masks, self.last_scores = out["mask"], out["best_score"]
+        return list(out["best_model"].unbind(0))
+
+    # -- pipelined entry for batches that live in HOST memory (what a DataLoader hands to model_cl.py:488-510) ----
+    def _service_ok(self):
+        """The pipelined service runs the hot path proper -- sample -> five-point -> MSAC -> arg-max + winner mask,
+        every hypothesis scored -- i.e. test mode, essential matrix, no adaptive exit / LO / final refit
+        (`opt.adaptive = False`, `opt.final_refit = False`: SURVEY 8d's cfg2 semantics)."""
+        drv = self.estimator
+        return (not self.opt.tr and not drv.fmat and drv.sampler.num_samples == 5 and not drv.adaptive
+                and not drv.final_refit and not drv.lo and torch.cuda.is_available())
+
+    def submit(self, points, weights, K1, K2, K=None, slots=3, graph=True):
+        """Enqueue one batch of HOST tensors (points [B,N,4], weights [B,N], K1/K2 [B,3,3] or [3,3]) and return a
+        ticket; nothing blocks unless `slots` batches are already in flight.  Pinned tensors are copied
+        asynchronously straight from where they are.  `collect(ticket)` returns the batch's results."""
+        if not self._service_ok():
+            raise NotImplementedError("submit/collect serve test-mode essential-matrix layers with opt.adaptive = "
+                                      "False and opt.final_refit = False; use forward_batched otherwise")
+        drv = self.estimator
+        B, N, _ = points.shape
+        Kh = int(K or drv._chunks() * drv.ransac_batch_size)
+        key = (B, N, Kh, int(slots), bool(graph))
+        if getattr(self, "_svc_key", None) != key:
+            dev = torch.device("cuda", torch.cuda.current_device())
+            self._svc = engine.E5TestService(B, N, Kh, dev, slots=slots, seed=drv.sampler.seed, graph=graph,
+                                             want_mask=True)
+            self._svc_key = key
+            self._thr_pinned = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(int(slots))]
+        svc = self._svc
+        slot = svc.step % svc.slots
+        if svc.busy[slot]:
+            svc.done[slot].synchronize()           # its results were not collected: they are overwritten
+        thr = self._thr_pinned[slot]
+        thr.copy_(self.thresholds(K1, K2, B, "cpu"))
+        return svc.submit(slot, host=(points, weights, thr))
+
+    def collect(self, ticket):
+        """-> (list_B[E_b [3,3]], masks [B,N] bool, scores [B]) of the batch `submit` returned `ticket` for: views
+        of the slot's pinned host buffers, valid until the slot is submitted again (`slots` submits later)."""
+        r = self._svc.result(ticket)
+        return list(r["best_model"].unbind(0)), r["mask"], r["best_score"]
 
 
 class RANSACLayer3D(nn.Module):

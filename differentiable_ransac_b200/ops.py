@@ -60,9 +60,16 @@ def _i32(t: torch.Tensor) -> torch.Tensor:
 
 
 # ---- sampler -----------------------------------------------------------------------------------
-def sample(logits, K, s, tau=1.0, noise=None, seed=0, offset=0, want_lse=False, want_noise=False):
+def _offset_dev(offset_dev, device):
+    if offset_dev is not None and (offset_dev.dtype != torch.int64 or offset_dev.device != device):
+        raise _lib.DrbError("offset_dev must be an int64 tensor on the device of `logits`")
+    return offset_dev
+
+
+def sample(logits, K, s, tau=1.0, noise=None, seed=0, offset=0, want_lse=False, want_noise=False, offset_dev=None):
     """logits [B,N] -> idx [B,K,s] int32 (ascending per row), lse [B,K] | None,
-    sel_key [B,K,s] | None, noise_out [B,K,N] | None."""
+    sel_key [B,K,s] | None, noise_out [B,K,N] | None.
+    offset_dev: optional int64 [1] CUDA tensor added to `offset` on the device (CUDA-graph replay)."""
     logits = _f32(logits)
     B, N = logits.shape
     dev = logits.device
@@ -74,8 +81,8 @@ def sample(logits, K, s, tau=1.0, noise=None, seed=0, offset=0, want_lse=False, 
     sel_key = torch.empty(B, K, s, dtype=torch.float32, device=dev) if want_lse else None
     noise_out = torch.empty(B, K, N, dtype=torch.float32, device=dev) if want_noise else None
     lib = _lib.load()
-    check(lib.drb_sample(_p(logits), _p(noise), seed, offset, float(tau), B, K, N, s, _p(idx), _p(lse), _p(sel_key),
-                         _p(noise_out), _stream()), "drb_sample")
+    check(lib.drb_sample(_p(logits), _p(noise), seed, offset, _p(_offset_dev(offset_dev, dev)), float(tau), B, K, N, s,
+                         _p(idx), _p(lse), _p(sel_key), _p(noise_out), _stream()), "drb_sample")
     return idx, lse, sel_key, noise_out
 
 
@@ -87,8 +94,7 @@ def sample_sets(logits, K, s, seed=0, offset=0, offset_dev=None):
     B, N = logits.shape
     idx = torch.empty(B, K, s, dtype=torch.int32, device=logits.device)
     lib = _lib.load()
-    if offset_dev is not None and (offset_dev.dtype != torch.int64 or offset_dev.device != logits.device):
-        raise _lib.DrbError("offset_dev must be an int64 tensor on the device of `logits`")
+    _offset_dev(offset_dev, logits.device)
     rc = lib.drb_sample_sets(_p(logits), seed, offset, _p(offset_dev), B, K, N, s, _p(idx), _stream())
     if rc == -3 and s in (3, 5, 7, 8) and offset_dev is None:
         return sample(logits, K, s, 1.0, None, seed, offset)[0]
@@ -96,7 +102,7 @@ def sample_sets(logits, K, s, seed=0, offset=0, offset_dev=None):
     return idx
 
 
-def sample_backward(logits, idx, lse, sel_key, g_sel, tau=1.0, noise=None, seed=0, offset=0):
+def sample_backward(logits, idx, lse, sel_key, g_sel, tau=1.0, noise=None, seed=0, offset=0, offset_dev=None):
     logits = _f32(logits)
     B, N = logits.shape
     _, K, s = idx.shape
@@ -105,7 +111,8 @@ def sample_backward(logits, idx, lse, sel_key, g_sel, tau=1.0, noise=None, seed=
     grad = torch.zeros(B, N, dtype=torch.float32, device=logits.device)
     scratch = torch.empty(B, K, dtype=torch.float32, device=logits.device)
     lib = _lib.load()
-    check(lib.drb_sample_backward(_p(logits), _p(noise), seed, offset, float(tau), B, K, N, s, _p(idx), _p(lse),
+    check(lib.drb_sample_backward(_p(logits), _p(noise), seed, offset, _p(_offset_dev(offset_dev, logits.device)),
+                                  float(tau), B, K, N, s, _p(idx), _p(lse),
                                   _p(sel_key), _p(g_sel), _p(scratch), _p(grad), _stream()), "drb_sample_backward")
     return grad
 

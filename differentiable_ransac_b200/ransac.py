@@ -22,6 +22,15 @@ def normalized_threshold(threshold, K1, K2, fmat):
     return float(threshold) / float((K1[0, 0] + K1[1, 1] + K1[0, 0] + K2[1, 1]) / 4)
 
 
+def threshold_tensor(threshold, K1, K2, fmat, device):
+    """The same value as a [1] fp32 tensor on `device`, computed where K1 / K2 live: no device->host sync when
+    they are CUDA tensors (test.py:31 moves them to the GPU)."""
+    if fmat or not torch.is_tensor(K1):
+        return torch.tensor([normalized_threshold(threshold, K1, K2, fmat)], dtype=torch.float32, device=device)
+    mult = (K1[0, 0] + K1[1, 1] + K1[0, 0] + K2[1, 1]) / 4
+    return (float(threshold) / mult).reshape(1).to(device=device, dtype=torch.float32)
+
+
 class RANSAC(object):
     def __init__(self, estimator, sampler, scoring, fmat=False, train=False, ransac_batch_size=64, sampler_id=0,
                  weighted=0, threshold=1e-3, confidence=0.999, max_iterations=5000, lo=0, lo_iters=64, eps=1e-5,
@@ -58,11 +67,97 @@ class RANSAC(object):
         return max(0.0, math.log10(1.0 - confidence) / math.log10(1 - inlier_ratio ** self.estimator.sample_size + self.eps))
 
     # -- the driver ------------------------------------------------------------------------------
+    def plugins_are_native(self):
+        """True when sampler, estimator and scoring are exactly this package's classes: then `__call__` runs the
+        fused CUDA path for them.  Anything else -- a user's estimator or scoring, or a subclass that overrides a
+        method -- is HONOURED: the chunked loop is run through the objects' own `sample` / `estimate_model` /
+        `score` calls, as the reference does (ransac.py:63-76, 111)."""
+        from .estimators.essential_matrix_estimator_nister import EssentialMatrixEstimatorNister
+        from .estimators.essential_matrix_estimator_stewenius import EssentialMatrixEstimator
+        from .estimators.fundamental_matrix_estimator import FundamentalMatrixEstimatorNew
+        from .samplers.gumbel_sampler import GumbelSoftmaxSampler
+        from .scorings.msac_score import MSACScore
+
+        return (type(self.estimator) in (EssentialMatrixEstimatorNister, EssentialMatrixEstimator,
+                                         FundamentalMatrixEstimatorNew)
+                and type(self.sampler) is GumbelSoftmaxSampler and type(self.scoring) is MSACScore)
+
+    def _plugin_call(self, matches, logits, K1, K2, gt_model):
+        """The reference's loop (ransac.py:55-200) driven through the plugin objects' own methods, for plugins that
+        are not this package's classes.  One chunk per trip: `sampler.sample(logits)` -> dense straight-through
+        one-hot [K,N]; gather; `estimator.estimate_model(minimal[K,s,D] (, weights))`; then either the train-mode
+        selection (closest slot to `gt_model`, NaN rows dropped) or `scoring.score(matches, models, thr)`, arg-max,
+        strict improvement and the adaptive iteration budget.  No local optimisation here (it refits through this
+        package's kernels, which a foreign estimator does not use): lo != 0 raises."""
+        if self.lo:
+            raise NotImplementedError("local optimisation runs on this package's solvers; with a plugin estimator / "
+                                      "scoring use lo=0")
+        thr = normalized_threshold(self.threshold, K1, K2, self.fmat)
+        rbs, N, D = self.ransac_batch_size, matches.shape[0], matches.shape[-1]
+        iterations, budget = 0, self.max_iterations
+        best_score, best_mask, best_model, soft = 0, [], [], None
+        collected = {}
+        while iterations < budget:
+            ret, soft = self.sampler.sample(logits)
+            picked = ret != 0
+            minimal = (matches.unsqueeze(0) * ret.unsqueeze(-1))[picked].view(rbs, -1, D)
+            if minimal.shape[1] == 0:
+                continue
+            if self.weighted:
+                est = self.estimator.estimate_model(minimal, soft[picked].view(rbs, -1))
+            else:
+                est = self.estimator.estimate_model(minimal)
+            if self.train:
+                if est is None or est.shape[0] == 0:
+                    continue
+                if self.sampler.num_samples == 8:
+                    chosen = est
+                else:
+                    slots = 4 if self.fmat else 10
+                    grouped = est.view(-1, slots, 3, 3)
+                    pick = (grouped - gt_model).flatten(2).norm(dim=-1).argmin(dim=-1)
+                    chosen = grouped[torch.arange(grouped.shape[0], device=est.device), pick]
+                collected[iterations] = chosen[~torch.isnan(chosen).flatten(1).any(1)]
+            else:
+                scores, masks = self.scoring.score(matches, est, thr)
+                i = torch.argmax(scores)
+                if iterations == 0 or scores[i] > best_score:
+                    best_score, best_mask, best_model = scores[i], masks[i], est[i]
+                    if self.adaptive:
+                        budget = min(self.max_iterations,
+                                     self.adaptive_iteration_number(int(best_mask.sum()), N, self.confidence))
+            iterations += rbs
+        if self.train:
+            return collected, best_mask, best_score, iterations
+        if self.final_refit:                      # ransac.py:148-185, the same calls on the plugin estimator
+            inl = best_mask.nonzero(as_tuple=True)
+            if self.fmat:
+                args = (soft[0, inl[0]],) if self.weighted else ()
+                est = self.estimator.estimate_model(matches[inl].unsqueeze(0), *args)
+            else:
+                est = self.estimator.estimate_model(matches.unsqueeze(0).double(), K1=K1.detach().cpu().numpy(),
+                                                    K2=K2.detach().cpu().numpy(),
+                                                    inlier_indices=inl[0].cpu().numpy().astype("uint64"),
+                                                    best_model=best_model.detach().cpu().numpy().T,
+                                                    unnormalzied_threshold=0.75, best_score=best_score)
+            if est is None or est.shape[0] == 0:
+                best_model = torch.eye(3, device=matches.device, dtype=matches.dtype)
+            else:
+                est = est.to(matches.dtype)
+                scores, _ = self.scoring.score(matches, est, thr)
+                if scores.max() > best_score:
+                    best_model, best_score = est[torch.argmax(scores)], scores.max()
+        if not getattr(self.scoring, "provides_inliers", True):
+            best_model, best_mask = self.scoring.get_inliers(matches, best_model.unsqueeze(0), self.estimator,
+                                                             threshold=thr)
+        return best_model, best_mask, best_score, iterations
+
     def __call__(self, matches, logits, K1, K2, gt_model):
-        threshold = normalized_threshold(self.threshold, K1, K2, self.fmat)
+        if not self.plugins_are_native():
+            return self._plugin_call(matches, logits, K1, K2, gt_model)
         if self.train:
             return self._train(matches, logits, gt_model)
-        return self._test(matches, logits, threshold)
+        return self._test(matches, logits, threshold_tensor(self.threshold, K1, K2, self.fmat, matches.device))
 
     def _train(self, matches, logits, gt_model):
         """ransac.py:78-108: every chunk's chosen models, NaN-free, keyed by the iteration count."""
@@ -100,7 +195,7 @@ class RANSAC(object):
         if self.adaptive:
             return engine.ransac_test_adaptive(m, lg, rbs, self.max_iterations, thr, self.sample_size,
                                                self.confidence, self.eps, self.sampler.tau, noise, self.sampler.seed,
-                                               off)
+                                               off, adaptive_exponent=self.estimator.sample_size)
         out = self._run()(m, lg, K, thr, self.sampler.tau, noise, self.sampler.seed, off)
         out["iterations"] = torch.full((m.shape[0],), K, dtype=torch.int32, device=m.device)
         return out
@@ -126,9 +221,7 @@ class RANSAC(object):
         best["iterations"] = torch.full((1,), iterations, dtype=torch.int32, device=m.device)
         return best
 
-    def _test(self, matches, logits, threshold):
-        dev = matches.device
-        thr = torch.tensor([threshold], device=dev, dtype=torch.float32)
+    def _test(self, matches, logits, thr):
         m, lg = matches[None].float(), logits[None].float()
         noise = self.sampler.injected_noise
         if noise is not None:
@@ -148,10 +241,11 @@ class RANSAC(object):
 
     # -- B pairs at once (replaces the python loop of model_cl.py:488-510) ---------------------------
     def batched_test(self, matches, logits, thresholds, K=None):
-        """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict with, per pair, exactly what
-        `__call__` returns for it (winner, inlier mask, score, `iterations` [B]): the chunked loop with its
-        adaptive exit replayed on the device, then the optional LO pass and the final refit for all pairs at
-        once.  `K` overrides max_iterations for this call."""
+        """matches [B,N,4], logits [B,N], thresholds [B] -> engine result dict (winner, inlier mask, score,
+        `iterations` [B]) for all pairs at once: the chunked loop with its adaptive exit replayed on the device,
+        then the final refit.  With lo = 0 this is, per pair, exactly what `__call__` returns.  With lo in (1, 2)
+        it is NOT: `__call__` optimises after every improvement inside the loop (ransac.py:122-132, sequential per
+        pair), here local optimisation runs ONCE on the loop's winner.  `K` overrides max_iterations."""
         keep = self.max_iterations
         if K:
             self.max_iterations = int(K)
@@ -187,7 +281,10 @@ class RANSAC3D(RANSAC):
         out_m, out_r, out_mean = {}, {}, {}
         for c in range(chunks):
             sl = slice(c * rbs, (c + 1) * rbs)
-            out_m[c * rbs] = models[0, sl][ok[0, sl]]
-            out_r[c * rbs] = res[sl]
-            out_mean[c * rbs] = res[sl].sum() / (rbs * N)
+            keep = ok[0, sl]
+            # the reference drops NaN models inside estimate_model, before squared_residual
+            # (rigid...solver.py:60-74): residuals and their mean cover the valid models only
+            out_m[c * rbs] = models[0, sl][keep]
+            out_r[c * rbs] = res[sl][keep]
+            out_mean[c * rbs] = res[sl][keep].sum() / (keep.sum().clamp_min(1) * N)
         return out_m, out_r, out_mean, 0, K

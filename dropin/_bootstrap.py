@@ -8,9 +8,20 @@ import types
 
 import numpy as np
 
-REF = os.environ.get("DRB_REFERENCE_DIR", "/root/reference")
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
+
+
+def _reference_dir():
+    """$DRB_REFERENCE_DIR, else a checkout at /root/reference, else the byte-for-byte copy oracle/make_ref.py puts
+    in oracle/_ref (what exists on the GPU box)."""
+    for cand in (os.environ.get("DRB_REFERENCE_DIR"), "/root/reference", os.path.join(ROOT, "oracle", "_ref")):
+        if cand and os.path.isfile(os.path.join(cand, "model_cl.py")):
+            return cand
+    return "/root/reference"
+
+
+REF = _reference_dir()
 
 
 def setup():

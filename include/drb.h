@@ -57,9 +57,12 @@ int drb_device_sm_count(void);
  * (parity mode), otherwise generated in-kernel with Philox4x32-10 keyed by (seed, offset).
  * Optional outputs (nullable): lse[B,K] = logsumexp_n keys (needed by the backward),
  * sel_key[B,K,s] = keys of the selected points (same order as idx), noise_out[B,K,N] = the
- * Gumbel noise actually used (lets a test replay a Philox run through the oracle).        */
-int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau,
-               int B, int K, int N, int s,
+ * Gumbel noise actually used (lets a test replay a Philox run through the oracle).
+ * offset_dev (nullable): one uint64 in device memory ADDED to `offset` when the kernel runs, so a captured
+ * CUDA graph of a training step draws fresh noise on every replay (the caller advances it on the stream;
+ * drb_sample_backward must be given the same pointer before it is advanced).                */
+int drb_sample(const float* logits, const float* noise, uint64_t seed, uint64_t offset,
+               const uint64_t* offset_dev, float tau, int B, int K, int N, int s,
                int32_t* idx, float* lse, float* sel_key, float* noise_out, void* stream);
 
 /* Test-mode set sampler: when only the K minimal sets are wanted (no log-sum-exp, no noise dump,
@@ -79,7 +82,8 @@ int drb_sample_sets(const float* logits, uint64_t seed, uint64_t offset, const u
  *   (1/tau) * sum_k y[k,n] (g[k,n] - sum_m y[k,m] g[k,m]),  y = softmax_n(keys).
  * The noise is re-read (`noise` non-null) or regenerated from (seed, offset); the K x N
  * soft one-hot is never stored.  `scratch` is B*K floats of caller-owned workspace.          */
-int drb_sample_backward(const float* logits, const float* noise, uint64_t seed, uint64_t offset, float tau,
+int drb_sample_backward(const float* logits, const float* noise, uint64_t seed, uint64_t offset,
+                        const uint64_t* offset_dev /* nullable, as in drb_sample */, float tau,
                         int B, int K, int N, int s,
                         const int32_t* idx, const float* lse, const float* sel_key, const float* g_sel,
                         float* scratch /* [B,K] */, float* grad_logits, void* stream);

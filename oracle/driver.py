@@ -124,10 +124,15 @@ def local_optimization(matches, best_score, best_mask, best_model, threshold, fm
 
 
 def full_test_driver(matches, logits, noises, K1, K2, threshold, fmat=False, sample_size=5, tau=1.0,
-                     confidence=0.999, lo=0, lo_iters=64, weighted=False):
+                     confidence=0.999, lo=0, lo_iters=64, weighted=False, estimator_sample_size=None):
     """`RANSAC.__call__` in test mode, ransac.py:41-200: chunked loop with adaptive exit, optional LO on every
     improvement, final refit (8-point on the inliers / 5-point on all points in fp64), MSAC re-score, keep
-    the refit only if it scores higher.  -> (best_model, best_mask, best_score, iterations)."""
+    the refit only if it scores higher.  -> (best_model, best_mask, best_score, iterations).
+    The exponent of the adaptive budget is the ESTIMATOR's sample size (ransac.py:207,214 read
+    `self.estimator.sample_size`): 5 for the five-point, 7 for FundamentalMatrixEstimatorNew
+    (fundamental_matrix_estimator.py:163) even when the sampler draws 8 points (`-fmat 1 -sam 3`)."""
+    if estimator_sample_size is None:
+        estimator_sample_size = 7 if fmat else 5
     rbs = noises[0].shape[0]
     max_iterations = rbs * len(noises)
     thr = normalized_threshold(threshold, K1, K2, fmat)
@@ -147,7 +152,7 @@ def full_test_driver(matches, logits, noises, K1, K2, threshold, fmat=False, sam
                 best_score, best_mask, best_model = local_optimization(matches, best_score, best_mask, best_model,
                                                                        thr, fmat, lo, lo_iters)
             max_iters = min(max_iterations, adaptive_iteration_number(int(best_mask.sum()), N, confidence,
-                                                                      sample_size, max_iterations))
+                                                                      estimator_sample_size, max_iterations))
         iterations += rbs
         ci += 1
     if fmat:

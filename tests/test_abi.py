@@ -49,11 +49,11 @@ def test_null_and_shape_errors_do_not_need_a_gpu(lib_path):
     from differentiable_ransac_b200 import _lib
 
     lib = _lib.load()
-    assert lib.drb_sample(None, None, 0, 0, 1.0, 1, 1, 8, 5, None, None, None, None, None) == -1
+    assert lib.drb_sample(None, None, 0, 0, None, 1.0, 1, 1, 8, 5, None, None, None, None, None) == -1
     buf = ctypes.create_string_buffer(64)
     p = ctypes.cast(buf, ctypes.c_void_p)
-    assert lib.drb_sample(p, None, 0, 0, 1.0, 1, 1, 4, 5, p, None, None, None, None) == -2      # s > N
-    assert lib.drb_sample(p, None, 0, 0, 1.0, 1, 1, 8, 6, p, None, None, None, None) == -3      # s unsupported
+    assert lib.drb_sample(p, None, 0, 0, None, 1.0, 1, 1, 4, 5, p, None, None, None, None) == -2      # s > N
+    assert lib.drb_sample(p, None, 0, 0, None, 1.0, 1, 1, 8, 6, p, None, None, None, None) == -3      # s unsupported
     assert lib.drb_solve_e5(None, None, 1, 1, 1, None, None, None, None, None, None) == -1
 
 

@@ -23,11 +23,26 @@ def test_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["metric"] == "hypotheses_per_sec" and d["unit"] == "hypotheses/s"
     assert d["higher_is_better"] is True and d["steps"] == 1 and d["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    have_ref = os.path.exists(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json"))
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port") and d["cpu_baseline"]["cores"] >= 1
+    if have_ref:        # the unmodified reference, hashed against its manifest
+        assert d["cpu_baseline"]["reference"]["verified"] == "sha256 of every file equals MANIFEST.json"
     sys.path.insert(0, ROOT)
     import bench
 
     assert d["config"]["workload"] == bench.WORKLOAD_NAME
+
+
+def test_reference_arm_of_the_other_configs():
+    """cfg1 (Stewenius loop body) and a training config through the reference's own entry points."""
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "MANIFEST.json")):
+        return
+    for cfg in ("cfg1", "cfg3"):
+        p = _run("--impl", "reference", "--steps", "1", "--warmup", "0", "--config", cfg)
+        assert p.returncode == 0, p.stderr[-2000:]
+        d = json.loads([l for l in p.stdout.splitlines() if l.strip()][0])
+        assert d["impl"] == "reference" and d["value"] > 0 and d["config"]["workload"].startswith(cfg)
+        assert d["cpu_baseline"]["kind"] == "reference"
 
 
 def test_reference_arm_other_ranks_print_nothing():

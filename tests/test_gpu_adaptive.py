@@ -67,6 +67,36 @@ def test_replay_equals_the_loop_pair_by_pair(sample_size):
     assert len(seen) > 1 and min(seen) < C * rbs          # the pairs really stop at different trip counts
 
 
+def test_adaptive_exponent_is_the_estimators_sample_size():
+    """`-fmat 1 -sam 3`: the sampler draws 8 points but the iteration budget uses `estimator.sample_size` = 7
+    (ransac.py:207,214; fundamental_matrix_estimator.py:163).  The replay with exponent 7 equals the loop run with
+    exponent 7, and differs from exponent 8 where the two budgets fall into different chunks."""
+    from differentiable_ransac_b200 import engine, synth
+    from differentiable_ransac_b200.model_cl import RANSACLayer
+    B, N, rbs, max_it = 4, 1000, 32, 640
+    ratios = (0.62, 0.55, 0.5, 0.7)
+    pairs = [synth.pixel_pair(N, ratios[b], seed=650 + b) for b in range(B)]
+    m = torch.stack([p[0] for p in pairs]).to(DEV)
+    thr = torch.full((B,), 0.75, device=DEV)
+    lg = synth.logits_regime(B, N, "L1", seed=4).to(DEV)
+    noise = synth.gumbel_noise((B, max_it, N), seed=78).to(DEV)
+    out7 = engine.ransac_test_adaptive(m, lg, rbs, max_it, thr, 8, noise=noise, adaptive_exponent=7)
+    out8 = engine.ransac_test_adaptive(m, lg, rbs, max_it, thr, 8, noise=noise)
+    for b in range(B):
+        _, its7 = _reference_loop(engine.ransac_f8_test, m[b:b + 1], lg[b:b + 1], thr[b:b + 1], noise[b:b + 1], rbs,
+                                  max_it, 7)
+        assert int(out7["iterations"][b]) == its7
+    assert (out7["iterations"] <= out8["iterations"]).all() and (out7["iterations"] < out8["iterations"]).any()
+    # and the driver passes the estimator's size, whatever the sampler draws
+    opt = types.SimpleNamespace(device=DEV, fmat=1, sampler=3, precision=1, tr=0, threshold=0.75,
+                                ransac_batch_size=rbs, weighted=0)
+    drv = RANSACLayer(opt).estimator
+    drv.max_iterations = max_it
+    assert drv.sampler.num_samples == 8 and drv.estimator.sample_size == 7
+    got = drv._loop(m, lg, thr, noise)
+    assert torch.equal(got["iterations"], out7["iterations"])
+
+
 def test_seven_point_and_philox_paths_run_and_stop_early():
     from differentiable_ransac_b200 import engine, synth
     B, N = 4, 1500

@@ -1,11 +1,12 @@
 """GPU tests of the tensor-core soft-MSAC scorer (drb_score_msac_tc, csrc/score_tc.cu) against the CPU oracle
 (oracle/scoring.py <- scorings/msac_score.py:12-55) and the FP32 kernel (drb_score_msac).
 
-Two tiers.  (1) The TF32 variant ("tc_tf32") ran on a B200 at the end of round 1
-(profiles/r1_score_tc_first_contact.jsonl): its cases here are the ones measured then, with the tolerance the
-3xTF32 split allows.  (2) Everything else -- the BF16 variant beyond one small case, the oracle-level 1e-4 bar at
-the headline size -- has NOT been confirmed on hardware yet and is opt-in: DRB_EXPERIMENTAL=1, each case in a
-CHILD process under a timeout (a wrong mbarrier phase in a warp-specialised kernel is a hang, not an exception).
+Two tiers.  (1) The TF32 variant against the FP32 kernel, cases and margins as first measured on a B200
+(profiles/r1_score_tc_first_contact.jsonl).  (2) EVERY variant against the fp64 CPU oracle -- 1e-4 relative for the
+BF16 splits (exact operands), 5e-4 for the TF32 splits (22-bit operands) -- on eight shapes up to 32 pairs x 1100
+models x 2000 correspondences; all eleven variants passed on the B200 at the start of round 2
+(profiles/r2_tc_oracle_parity.log), so the tier runs by default.  Each variant runs in a CHILD process under a
+timeout (a wrong mbarrier phase in a warp-specialised kernel is a hang, not an exception).
 The kernel's host model is tested on the CPU in test_host_math.py::test_msac_tc_*."""
 import os
 import subprocess
@@ -85,11 +86,7 @@ def test_tc_tf32_headline_shape():
     assert float(((best_tc - best_ref).abs() / best_ref).max()) < 5e-5       # the winners' scores
 
 
-# ---- tier 2: not yet confirmed on hardware (opt-in) --------------------------------------------------------------
-@pytest.fixture()
-def _opt_in():
-    if os.environ.get("DRB_EXPERIMENTAL", "0") != "1":
-        pytest.skip("not yet confirmed on hardware: set DRB_EXPERIMENTAL=1")
+# ---- tier 2: every variant against the fp64 oracle --------------------------------------------------------------
 
 
 CHILD = r"""
@@ -150,7 +147,7 @@ KERNELS = ["tc_bf16", "tc_tf32", "tc_bf16p", "tc_tf32p", "tc_tf32_e16", "tc_bf16
 
 
 @pytest.mark.parametrize("kernel", KERNELS)
-def test_tc_kernel_matches_oracle(kernel, _opt_in):
+def test_tc_kernel_matches_oracle(kernel):
     """One child process per variant (all cases in it, progress flushed): a hang costs that variant's remaining
     cases, not the session."""
     r = subprocess.run([sys.executable, "-c", CHILD.format(root=ROOT, cases=CASES, kernel=kernel)], capture_output=True,
