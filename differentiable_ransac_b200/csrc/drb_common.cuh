@@ -31,6 +31,24 @@ namespace drb {
 template <class T> DRB_HD T t_abs(T x) { return x < T(0) ? -x : x; }
 template <class T> DRB_HD T t_max(T a, T b) { return a > b ? a : b; }
 template <class T> DRB_HD T t_min(T a, T b) { return a < b ? a : b; }
+// float / double: one instruction each on the device (|x| is an operand modifier, max is FMNMX); they differ from
+// the generic forms only when an argument is NaN (fmax returns the other argument)
+DRB_HD float t_abs(float x) { return fabsf(x); }
+DRB_HD double t_abs(double x) { return fabs(x); }
+DRB_HD float t_max(float a, float b) { return fmaxf(a, b); }
+DRB_HD double t_max(double a, double b) { return fmax(a, b); }
+// 1 / x where one ulp does not matter (scale factors, pivots of an elimination whose result is polished, Newton
+// steps): MUFU.RCP on the device instead of the ~10-instruction IEEE division; exact elsewhere
+template <class T> DRB_HD T t_rcp(T x) { return T(1) / x; }
+DRB_HD float t_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+#else
+    return 1.0f / x;
+#endif
+}
 DRB_HD float t_sqrt(float x) { return sqrtf(x); }
 DRB_HD double t_sqrt(double x) { return sqrt(x); }
 DRB_HD float t_rsqrt(float x) {

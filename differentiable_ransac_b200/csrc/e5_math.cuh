@@ -32,17 +32,15 @@ DRB_HD void epipolar_row(T x1, T y1, T x2, T y2, T* r) {
     r[6] = x1;      r[7] = y1;      r[8] = T(1);
 }
 
-// Orthonormal basis of the null space of the R x 9 matrix whose rows are given
-// (R in {5, 7, 8}) by Householder QR of its transpose.  Writes 9 - R vectors.
+// Householder QR of A^T (9 x R, column k = row k of A), in place: the reflector vectors stay in the lower
+// trapezoid of W, their scales in beta.  R in {5, 7, 8}.
 template <class T, int R>
-DRB_HD void null_space_rows(const T (*rows)[9], T (*null)[9]) {
-    T W[9][R];  // A^T, column k = row k of A
+DRB_HD void householder_factor(const T (*rows)[9], T (*W)[R], T* beta) {
     DRB_UNROLL
     for (int k = 0; k < R; ++k) {
         DRB_UNROLL
         for (int i = 0; i < 9; ++i) W[i][k] = rows[k][i];
     }
-    T beta[R];
     DRB_UNROLL
     for (int k = 0; k < R; ++k) {
         T nrm2 = T(0);
@@ -65,24 +63,34 @@ DRB_HD void null_space_rows(const T (*rows)[9], T (*null)[9]) {
             for (int i = k; i < 9; ++i) W[i][j] -= dot * W[i][k];
         }
     }
-    // null vector m = Q e_{R+m} = H_0 H_1 ... H_{R-1} e_{R+m}
+}
+
+// Null vector m (0 <= m < 9 - R) of the factored matrix: Q e_{R+m} = H_0 H_1 ... H_{R-1} e_{R+m}.  `m` may be a
+// run-time value (the lanes of a cooperative group take one vector each): it only selects the unit vector.
+template <class T, int R>
+DRB_HD void householder_null_vector(const T (*W)[R], const T* beta, int m, T* q) {
     DRB_UNROLL
-    for (int mI = 0; mI < 9 - R; ++mI) {
-        T q[9];
+    for (int i = 0; i < 9; ++i) q[i] = (i == R + m) ? T(1) : T(0);
+    DRB_UNROLL
+    for (int k = R - 1; k >= 0; --k) {
+        T dot = T(0);
         DRB_UNROLL
-        for (int i = 0; i < 9; ++i) q[i] = (i == R + mI) ? T(1) : T(0);
+        for (int i = k; i < 9; ++i) dot += W[i][k] * q[i];
+        dot *= beta[k];
         DRB_UNROLL
-        for (int k = R - 1; k >= 0; --k) {
-            T dot = T(0);
-            DRB_UNROLL
-            for (int i = k; i < 9; ++i) dot += W[i][k] * q[i];
-            dot *= beta[k];
-            DRB_UNROLL
-            for (int i = k; i < 9; ++i) q[i] -= dot * W[i][k];
-        }
-        DRB_UNROLL
-        for (int i = 0; i < 9; ++i) null[mI][i] = q[i];
+        for (int i = k; i < 9; ++i) q[i] -= dot * W[i][k];
     }
+}
+
+// Orthonormal basis of the null space of the R x 9 matrix whose rows are given
+// (R in {5, 7, 8}) by Householder QR of its transpose.  Writes 9 - R vectors.
+template <class T, int R>
+DRB_HD void null_space_rows(const T (*rows)[9], T (*null)[9]) {
+    T W[9][R];
+    T beta[R];
+    householder_factor<T, R>(rows, W, beta);
+    DRB_UNROLL
+    for (int mI = 0; mI < 9 - R; ++mI) householder_null_vector<T, R>(W, beta, mI, null[mI]);
 }
 
 // Fill the 10 x 20 constraint matrix (rows 0..8: E E^T E - 1/2 tr(E E^T) E,
@@ -179,7 +187,7 @@ DRB_HD bool e5_eliminate(Mat& M) {
         }
         if (!(best > tol)) ok = false;
         T prow[20];
-        const T ip = T(1) / M(piv, p);
+        const T ip = t_rcp(M(piv, p));
         DRB_UNROLL
         for (int c = 0; c < 20; ++c) {
             const T a = M(piv, c);
@@ -268,7 +276,7 @@ DRB_HD void e5_polish(const T (*N)[9], T& x, T& y, T& z, int iters) {
         const T det = a * c00 + b * c01 + c * c02;
         if (!(t_abs(det) > T(0))) return;
         const T c11 = a * f - c * c, c12 = b * c - a * e, c22 = a * d - b * b;
-        const T id = T(1) / det;
+        const T id = t_rcp(det);
         const T dx = -(c00 * Jtr[0] + c01 * Jtr[1] + c02 * Jtr[2]) * id;
         const T dy = -(c01 * Jtr[0] + c11 * Jtr[1] + c12 * Jtr[2]) * id;
         const T dz = -(c02 * Jtr[0] + c12 * Jtr[1] + c22 * Jtr[2]) * id;
@@ -377,14 +385,17 @@ DRB_HD bool e5_model_from_root(const E5Sample<T>& S, T z, int polish_iters, T* E
     const T d12 = vx[1] * vy[2] - vx[2] * vy[1];
     T x, y;
     if (t_abs(d01) >= t_abs(d02) && t_abs(d01) >= t_abs(d12)) {
-        x = (vq[1] * vy[0] - vq[0] * vy[1]) / d01;
-        y = (vq[0] * vx[1] - vq[1] * vx[0]) / d01;
+        const T id = t_rcp(d01);
+        x = (vq[1] * vy[0] - vq[0] * vy[1]) * id;
+        y = (vq[0] * vx[1] - vq[1] * vx[0]) * id;
     } else if (t_abs(d02) >= t_abs(d12)) {
-        x = (vq[2] * vy[0] - vq[0] * vy[2]) / d02;
-        y = (vq[0] * vx[2] - vq[2] * vx[0]) / d02;
+        const T id = t_rcp(d02);
+        x = (vq[2] * vy[0] - vq[0] * vy[2]) * id;
+        y = (vq[0] * vx[2] - vq[2] * vx[0]) * id;
     } else {
-        x = (vq[2] * vy[1] - vq[1] * vy[2]) / d12;
-        y = (vq[1] * vx[2] - vq[2] * vx[1]) / d12;
+        const T id = t_rcp(d12);
+        x = (vq[2] * vy[1] - vq[1] * vy[2]) * id;
+        y = (vq[1] * vx[2] - vq[2] * vx[1]) * id;
     }
     if (!(x == x) || !(y == y) || t_abs(x) > T(1e18) || t_abs(y) > T(1e18)) return false;
     e5_polish<T>(S.N, x, y, z, polish_iters);

@@ -46,7 +46,7 @@ DRB_HD T refine_bracket(const T* p, T lo, T hi) {
         } else {
             hi = z;
         }
-        T zn = z - f / df;
+        T zn = z - f * t_rcp(df);
         if (!(zn > lo && zn < hi)) zn = T(0.5) * (lo + hi);
         const T dz = t_abs(zn - z);
         z = zn;
@@ -68,7 +68,7 @@ struct SturmChain10 {
         T sc = T(0);
         DRB_UNROLL
         for (int i = 0; i <= 10; ++i) sc = t_max(sc, t_abs(coef[i]));
-        const T inv = sc > T(0) ? T(1) / sc : T(1);
+        const T inv = sc > T(0) ? t_rcp(sc) : T(1);
         DRB_UNROLL
         for (int i = 0; i <= 10; ++i) {
             p[i] = coef[i] * inv;
@@ -81,7 +81,7 @@ struct SturmChain10 {
             T s1 = T(0);
             DRB_UNROLL
             for (int i = 0; i < 10; ++i) s1 = t_max(s1, t_abs(v[i]));
-            const T i1 = s1 > T(0) ? T(1) / s1 : T(1);
+            const T i1 = s1 > T(0) ? t_rcp(s1) : T(1);
             DRB_UNROLL
             for (int i = 0; i < 10; ++i) v[i] *= i1;
         }
@@ -91,7 +91,7 @@ struct SturmChain10 {
             const int d = 10 - i;  // deg v = d, deg u = d + 1
             T lead = v[d];
             if (t_abs(lead) < tiny) lead = lead < T(0) ? -tiny : tiny;
-            const T il = T(1) / lead;
+            const T il = t_rcp(lead);
             const T ai = u[d + 1] * il;
             const T bi = (u[d] - ai * v[d - 1]) * il;
             T r[11];
@@ -104,7 +104,7 @@ struct SturmChain10 {
                 mx = t_max(mx, t_abs(r[j]));
             }
             if (!(mx > tiny)) mx = T(1);
-            const T im = T(1) / mx;
+            const T im = t_rcp(mx);
             a[i] = ai;
             b[i] = bi;
             m[i] = mx;
@@ -174,36 +174,47 @@ struct SturmChain10 {
         return nb;
     }
 
-    // Phase 1 only: brackets (blo[r], bhi[r]], each holding one real root (or a cluster).
-    DRB_HD int brackets_unit(T* blo, T* bhi, int max_out) const {
-        // roots per cell, 4 bits each (a cell holds at most 10); rolled loops keep the code small --
-        // this routine is instruction-cache bound when unrolled
+    // Grid pass over cells [cell0, cell0 + ncells) of the kGrid-cell grid on (-1, 1]: roots per cell, 4 bits each
+    // (a cell holds at most 10); `c_left` receives the Sturm count at the left edge of cell0.  Returns the packed
+    // word.  Rolled loops keep the code small -- this routine is instruction-cache bound when unrolled.
+    DRB_HD unsigned long long grid_cells(int cell0, int ncells, int& c_left) const {
         unsigned long long cells = 0ull;
-        const int c_first = count(T(-1));
-        {
-            int prev = c_first;
+        c_left = count(T(-1) + T(2 * cell0) / T(kGrid));
+        int prev = c_left;
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-            for (int i = 1; i <= kGrid; ++i) {
-                const int cur = count(T(-1) + T(2 * i) / T(kGrid));
-                int n = prev - cur;
-                n = n < 0 ? 0 : (n > 15 ? 15 : n);
-                cells |= (unsigned long long)n << (4 * (i - 1));
-                prev = cur;
-            }
+        for (int i = 1; i <= ncells; ++i) {
+            const int cur = count(T(-1) + T(2 * (cell0 + i)) / T(kGrid));
+            int n = prev - cur;
+            n = n < 0 ? 0 : (n > 15 ? 15 : n);
+            cells |= (unsigned long long)n << (4 * (i - 1));
+            prev = cur;
         }
+        return cells;
+    }
+
+    // Roots in the cells of a packed word.
+    DRB_HD static int cells_total(unsigned long long cells, int ncells) {
+        int n = 0;
+        for (int i = 0; i < ncells; ++i) n += (int)((cells >> (4 * i)) & 15ull);
+        return n;
+    }
+
+    // Emit pass: `out(lo, hi)` for every root of the cells of `cells` (at most `max_out` calls): a cell holding
+    // one root is its own bracket, a cell holding several is split by Sturm bisection (uncommon).
+    template <class Out>
+    DRB_HD int emit_brackets(int cell0, int ncells, unsigned long long cells, int c_left, int max_out, Out& out) const {
         int nb = 0;
-        int c_left = c_first;  // Sturm count at the left edge of the current cell
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1
 #endif
-        for (int i = 0; i < kGrid; ++i) {
+        for (int i = 0; i < ncells; ++i) {
             const int n = (int)((cells >> (4 * i)) & 15ull);
             if (n == 0) continue;
-            const T clo_x = T(-1) + T(2 * i) / T(kGrid), chi_x = T(-1) + T(2 * i + 2) / T(kGrid);
+            const T clo_x = T(-1) + T(2 * (cell0 + i)) / T(kGrid), chi_x = T(-1) + T(2 * (cell0 + i) + 2) / T(kGrid);
             if (n == 1) {
-                if (nb < max_out) { blo[nb] = clo_x; bhi[nb] = chi_x; ++nb; }
+                if (nb < max_out) { out(clo_x, chi_x); ++nb; }
             } else {
                 // several roots in this cell: peel them off from the left by bisection on the count
                 T start = clo_x;
@@ -223,13 +234,29 @@ struct SturmChain10 {
                             clo = cm;
                         }
                     }
-                    blo[nb] = lo; bhi[nb] = hi; ++nb;
+                    out(lo, hi);
+                    ++nb;
                     start = hi;
                 }
             }
             c_left -= n;
         }
         return nb;
+    }
+
+    struct ArrayOut {
+        T* lo;
+        T* hi;
+        int n;
+        DRB_HD void operator()(T a, T b) { lo[n] = a; hi[n] = b; ++n; }
+    };
+
+    // Phase 1 only: brackets (blo[r], bhi[r]], each holding one real root (or a cluster).
+    DRB_HD int brackets_unit(T* blo, T* bhi, int max_out) const {
+        int c_left;
+        const unsigned long long cells = grid_cells(0, kGrid, c_left);
+        ArrayOut out{blo, bhi, 0};
+        return emit_brackets(0, kGrid, cells, c_left, max_out, out);
     }
 };
 
@@ -261,7 +288,7 @@ DRB_HD bool root_from_bracket(const T* coef, bool reversed, T lo, T hi, T& z) {
     T sc = T(0);
     DRB_UNROLL
     for (int i = 0; i <= 10; ++i) sc = t_max(sc, t_abs(coef[i]));
-    const T inv = sc > T(0) ? T(1) / sc : T(1);
+    const T inv = sc > T(0) ? t_rcp(sc) : T(1);
     DRB_UNROLL
     for (int i = 0; i <= 10; ++i) c[i] = (reversed ? coef[10 - i] : coef[i]) * inv;
     const T w = refine_bracket<T>(c, lo, hi);
@@ -271,7 +298,7 @@ DRB_HD bool root_from_bracket(const T* coef, bool reversed, T lo, T hi, T& z) {
     }
     const T aw = t_abs(w);
     if (!(aw < T(1)) || !(aw > T(1e-7))) return false;
-    z = T(1) / w;
+    z = t_rcp(w);
     return true;
 }
 

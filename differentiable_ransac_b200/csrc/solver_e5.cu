@@ -4,10 +4,13 @@
 // and the reference lines it replaces.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "../../include/drb.h"
 #include "device_cfg.cuh"
 #include "drb_common.cuh"
 #include "e5_math.cuh"
+#include "e5_coop.cuh"
 #include "e5_backward.cuh"
 
 namespace drb {
@@ -98,6 +101,7 @@ __device__ __forceinline__ void fetch_sample(const float* col, E5Sample<float>& 
     for (int i = 0; i < 11; ++i) S.P[i] = col[(e++) * kE5Stride];
 }
 
+// ---- the round-1 kernel: one hypothesis per THREAD (kept for A/B measurements: DRB_E5_SOLVER=thread) ----
 // Stage 1 + 2 (null space, constraints, elimination, z-polynomials, root isolation) run one sample per
 // thread.  Stage 3 (Newton refinement of a bracket, back-substitution, Gauss-Newton polish, normalisation)
 // is a per-ROOT job and samples have 0..10 roots, so leaving it per-thread means a warp runs as long as its
@@ -105,9 +109,9 @@ __device__ __forceinline__ void fetch_sample(const float* col, E5Sample<float>& 
 // sample in shared memory, the brackets of all 32 samples are numbered consecutively, and lane l works on
 // items l, l + 32, ... whoever they belong to.
 __global__ void __launch_bounds__(kE5Threads)
-solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
-                float* __restrict__ models, int32_t* __restrict__ nsol, float* __restrict__ cmodels,
-                int32_t* __restrict__ cids, int32_t* __restrict__ ccount) {
+solve_e5_thread_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
+                       float* __restrict__ models, int32_t* __restrict__ nsol, float* __restrict__ cmodels,
+                       int32_t* __restrict__ cids, int32_t* __restrict__ ccount) {
     extern __shared__ float smem[];
     __shared__ int wprefix[kE5Threads / 32][33];
     const unsigned FULL = 0xffffffffu;
@@ -241,6 +245,150 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
     }
 }
 
+
+// ---- the cooperative kernel: four lanes per hypothesis for the per-sample stages (e5_coop.cuh), one ROOT per
+// thread for the per-root stage, pooled over the CTA ------------------------------------------------------------
+constexpr int kCoThreads = 128;
+constexpr int kCoSamples = kCoThreads / kQuad;                       // 32 samples per CTA
+constexpr int kCoSmemBytes = kCoSamples * kCoStride * sizeof(float);   // 41 856 B
+
+struct QuadDev {
+    int q;            // lane within the quad
+    int base;         // first lane of the quad within the warp
+    unsigned mask;    // the quad's four lanes
+    __device__ __forceinline__ float shfl(float v, int src) const { return __shfl_sync(mask, v, base + src); }
+    __device__ __forceinline__ int shfl(int v, int src) const { return __shfl_sync(mask, v, base + src); }
+    __device__ __forceinline__ void sync() const { __syncwarp(mask); }
+};
+
+template <int MINB>      // CTAs per SM the register allocation aims at: 4 = 128 registers, 5 = 96 (what shared memory allows)
+__global__ void __launch_bounds__(kCoThreads, MINB)
+solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
+                float* __restrict__ models, int32_t* __restrict__ nsol, float* __restrict__ cmodels,
+                int32_t* __restrict__ cids, int32_t* __restrict__ ccount) {
+    extern __shared__ float smem[];
+    __shared__ int prefix[kCoThreads / 32][kCoSamples + 1];
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int sl = tid >> 2;                                   // the quad's sample slot in the CTA
+    const long long rows_all = (long long)B * K;
+    const long long row0 = (long long)blockIdx.x * kCoSamples;
+    const long long row = row0 + sl;
+    const bool alive = row < rows_all;
+    const long long rowc = alive ? row : rows_all - 1;        // dead quads of the last CTA redo the last sample
+    const int b = (int)(rowc / K);
+    const int k = (int)(rowc % K);
+    float* S = smem + sl * kCoStride;
+    QuadDev g{tid & 3, lane & ~3, 0xFu << (lane & ~3)};
+
+    // ---- stages 1 + 2: the quad's own sample ---------------------------------------------------------------
+    {
+        float p[5][4], P[11];
+        load_minimal5(matches, idx, rowc, b, N, p);
+        const bool ok = e5_coop_prepare<float, QuadDev>(g, p, S, P);
+        int nb = 0;
+        if (ok && alive) nb = e5_coop_isolate<float, QuadDev>(g, P, S);
+        if (g.q == 0) {
+            reinterpret_cast<int*>(S)[kCoNb] = nb;
+            reinterpret_cast<int*>(S)[kCoMask] = 0;
+        }
+    }
+    __syncthreads();
+    // ---- pool the brackets of the CTA's 32 samples: every warp scans the 32 counts for itself (no second barrier) ----
+    {
+        int incl = reinterpret_cast<const int*>(smem + lane * kCoStride)[kCoNb];
+        DRB_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += up;
+        }
+        prefix[tid >> 5][lane + 1] = incl;
+        if (lane == 0) prefix[tid >> 5][0] = 0;
+        __syncwarp();
+    }
+    const int* pre = prefix[tid >> 5];
+    const int total = pre[kCoSamples];
+    // ---- stage 3: one bracket per thread per trip (Newton in the bracket, back-substitution, polish, normalise) ---
+    for (int it = tid; it < total; it += kCoThreads) {
+        int lo = 0, hi = kCoSamples;                // owner = largest L with pre[L] <= it
+        DRB_UNROLL
+        for (int s_ = 0; s_ < 5; ++s_) {
+            const int mid = (lo + hi) >> 1;
+            if (pre[mid] <= it) lo = mid; else hi = mid;
+        }
+        const int j = it - pre[lo];
+        float* So = smem + lo * kCoStride;
+        E5Sample<float> smp;
+        co_fetch_sample<float>(So, smp);
+        float z, E[9];
+        bool valid = root_from_bracket<float>(smp.P, So[kCoRev + j] != 0.f, So[kCoLo + j], So[kCoHi + j], z);
+        valid = valid && e5_model_from_root<float>(smp, z, 2, E);
+        if (valid) {
+            DRB_UNROLL
+            for (int i = 0; i < 9; ++i) So[kCoQ + j * 9 + i] = E[i];
+            atomicOr(reinterpret_cast<int*>(So) + kCoMask, 1 << j);
+        }
+    }
+    __syncthreads();
+    // ---- the quad closes its own sample: holes left by dropped roots (lane 0), identity in the unused slots ----------
+    if (g.q == 0) {
+        const int vmask = reinterpret_cast<const int*>(S)[kCoMask];
+        const int nb = reinterpret_cast<const int*>(S)[kCoNb];
+        int n = 0;
+        for (int j = 0; j < nb; ++j) {
+            if (vmask & (1 << j)) {
+                if (j != n) {
+                    DRB_UNROLL
+                    for (int i = 0; i < 9; ++i) S[kCoQ + n * 9 + i] = S[kCoQ + j * 9 + i];
+                }
+                ++n;
+            }
+        }
+        reinterpret_cast<int*>(S)[kCoCount] = n;
+        if (alive) nsol[row] = n;
+    }
+    g.sync();
+    const int n = reinterpret_cast<const int*>(S)[kCoCount];
+    for (int e = 9 * n + g.q; e < 90; e += kQuad) {
+        const int i = e - 9 * ((e * 57) >> 9);                 // e mod 9 for e < 90
+        S[kCoQ + e] = (i == 0 || i == 4 || i == 8) ? 1.f : 0.f;
+    }
+    // Compact-list range of the sample.  One atomic per (warp, pair): rows are consecutive, so the quads of a pair
+    // form a contiguous group of lanes; the group leader reserves the group's total and every quad leader adds its
+    // exclusive prefix (the other three lanes of a quad contribute 0 and read the leader's position).
+    int pos = 0;
+    if (cmodels != nullptr) {
+        const int key = alive ? b : -1;
+        const unsigned grp = __match_any_sync(FULL, key);
+        const int mine = (g.q == 0) ? n : 0;
+        int inc = mine;
+        DRB_UNROLL
+        for (int o = 1; o < 32; o <<= 1) {
+            const int up = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += up;
+        }
+        const int first = __ffs(grp) - 1, last = 31 - __clz(grp);
+        const int before_group = __shfl_sync(FULL, inc - mine, first);
+        const int group_total = __shfl_sync(FULL, inc, last) - before_group;
+        int base = 0;
+        if (lane == first && alive && group_total > 0) base = atomicAdd(ccount + b, group_total);
+        base = __shfl_sync(FULL, base, first);
+        pos = g.shfl(base + (inc - mine) - before_group, 0);
+    }
+    g.sync();
+    if (alive) {
+        // dense: the sample's 90 floats are contiguous (360 B, 8-byte aligned), written by its quad
+        float2* dense = reinterpret_cast<float2*>(models + (size_t)row * 90);
+        for (int i = g.q; i < 45; i += kQuad) dense[i] = make_float2(S[kCoQ + 2 * i], S[kCoQ + 2 * i + 1]);
+        // compact list: the sample's models are contiguous (36 n bytes)
+        if (cmodels != nullptr) {
+            float* dst = cmodels + ((size_t)b * K * 10 + pos) * 9;
+            for (int e = g.q; e < n * 9; e += kQuad) dst[e] = S[kCoQ + e];
+            for (int s_ = g.q; s_ < n; s_ += kQuad) cids[(size_t)b * K * 10 + pos + s_] = k * 10 + s_;
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128)
 solve_e5_backward_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
                          const float* __restrict__ models, const int32_t* __restrict__ sel,
@@ -307,11 +455,34 @@ extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int
     if (!matches || !models || !nsol) return DRB_ERR_NULL_POINTER;
     if (cmodels && (!cids || !ccount)) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
-    static std::atomic<unsigned long long> configured{0};
-    if (!ensure_dynamic_smem(solve_e5_kernel, kE5SmemBytes, configured)) return DRB_ERR_CUDA;
     const long long rows = (long long)B * K;
-    solve_e5_kernel<<<(unsigned)((rows + kE5Threads - 1) / kE5Threads), kE5Threads, kE5SmemBytes,
-                      (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol, cmodels, cids, ccount);
+    static const bool per_thread = []() {      // A/B switch for measurements: the round-1 one-thread-per-hypothesis kernel
+        const char* e = getenv("DRB_E5_SOLVER");
+        return e != nullptr && e[0] == 't';
+    }();
+    if (per_thread) {
+        static std::atomic<unsigned long long> configured{0};
+        if (!ensure_dynamic_smem(solve_e5_thread_kernel, kE5SmemBytes, configured)) return DRB_ERR_CUDA;
+        solve_e5_thread_kernel<<<(unsigned)((rows + kE5Threads - 1) / kE5Threads), kE5Threads, kE5SmemBytes,
+                                 (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol, cmodels, cids, ccount);
+        return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
+    }
+    static const int minb = []() {             // measurement switch: DRB_E5_MINB=4 -> the 128-register build
+        const char* e = getenv("DRB_E5_MINB");
+        return (e != nullptr && e[0] == '4') ? 4 : 5;
+    }();
+    const unsigned grid = (unsigned)((rows + kCoSamples - 1) / kCoSamples);
+    if (minb == 4) {
+        static std::atomic<unsigned long long> configured{0};
+        if (!ensure_dynamic_smem(solve_e5_kernel<4>, kCoSmemBytes, configured)) return DRB_ERR_CUDA;
+        solve_e5_kernel<4><<<grid, kCoThreads, kCoSmemBytes, (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol,
+                                                                                      cmodels, cids, ccount);
+    } else {
+        static std::atomic<unsigned long long> configured{0};
+        if (!ensure_dynamic_smem(solve_e5_kernel<5>, kCoSmemBytes, configured)) return DRB_ERR_CUDA;
+        solve_e5_kernel<5><<<grid, kCoThreads, kCoSmemBytes, (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol,
+                                                                                      cmodels, cids, ccount);
+    }
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
 

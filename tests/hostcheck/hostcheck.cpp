@@ -3,11 +3,14 @@
 // suite (no GPU in the build container) can run the exact arithmetic of the
 // CUDA kernels against the oracle.  The package never loads this library; the
 // product path is the CUDA library and fails loudly without it.
+#include <atomic>
 #include <cmath>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include "e5_math.cuh"
+#include "e5_coop.cuh"
 #include "e5_backward.cuh"
 #include "f8_math.cuh"
 #include "rigid_math.cuh"
@@ -39,7 +42,96 @@ void run_e5(const T* pts, int K, T* models, int* nsol, int polish) {
 }
 }  // namespace
 
+// ---- the cooperative five-point stages (e5_coop.cuh) on the host: four threads are the quad's lanes, a barrier is
+// the warp's lock step.  A shuffle is publish / barrier / read / barrier; g.sync() is one barrier. ----------------
+struct QuadShared {
+    std::atomic<int> arrived{0};
+    std::atomic<int> phase{0};
+    float fslot[4];
+    int islot[4];
+    void barrier(int& local_phase) {
+        const int next = local_phase ^ 1;
+        if (arrived.fetch_add(1, std::memory_order_acq_rel) == 3) {
+            arrived.store(0, std::memory_order_relaxed);
+            phase.store(next, std::memory_order_release);
+        } else {
+            while (phase.load(std::memory_order_acquire) != next) std::this_thread::yield();
+        }
+        local_phase = next;
+    }
+};
+struct QuadHost {
+    int q;
+    QuadShared* sh;
+    int local_phase = 0;
+    float shfl(float v, int src) {
+        sh->fslot[q] = v;
+        sh->barrier(local_phase);
+        const float r = sh->fslot[src];
+        sh->barrier(local_phase);
+        return r;
+    }
+    int shfl(int v, int src) {
+        sh->islot[q] = v;
+        sh->barrier(local_phase);
+        const int r = sh->islot[src];
+        sh->barrier(local_phase);
+        return r;
+    }
+    void sync() { sh->barrier(local_phase); }
+};
+
+static void run_e5_coop(const float* pts, int K, float* models, int* nsol, int polish, float* aux) {
+    QuadShared sh;
+    std::vector<float> S(drb::kCoStride);
+    int nb_shared = 0;
+    auto lane = [&](int q) {
+        QuadHost g{q, &sh};
+        for (int k = 0; k < K; ++k) {
+            float p[5][4], P[11];
+            for (int j = 0; j < 5; ++j)
+                for (int c = 0; c < 4; ++c) p[j][c] = pts[(k * 5 + j) * 4 + c];
+            const bool ok = drb::e5_coop_prepare<float, QuadHost>(g, p, S.data(), P);
+            int nb = 0;
+            if (ok) nb = drb::e5_coop_isolate<float, QuadHost>(g, P, S.data());
+            if (q == 0) nb_shared = nb;
+            g.sync();
+            if (q == 0) {   // the per-root stage, serially (on the device: one bracket per lane, pooled)
+                float out[10][9];
+                for (int s = 0; s < 10; ++s)
+                    for (int i = 0; i < 9; ++i) out[s][i] = (i % 4 == 0) ? 1.f : 0.f;
+                int n = 0;
+                drb::E5Sample<float> smp;
+                drb::co_fetch_sample<float>(S.data(), smp);
+                for (int j = 0; j < nb_shared; ++j) {
+                    float z, E[9];
+                    if (!drb::root_from_bracket<float>(smp.P, S[drb::kCoRev + j] != 0.f, S[drb::kCoLo + j],
+                                                       S[drb::kCoHi + j], z))
+                        continue;
+                    if (!drb::e5_model_from_root<float>(smp, z, polish, E)) continue;
+                    std::memcpy(out[n++], E, sizeof(E));
+                }
+                nsol[k] = n;
+                std::memcpy(models + (size_t)k * 90, out, sizeof(out));
+                if (aux) {   // P (11), N (36) for stage-level comparisons
+                    std::memcpy(aux + (size_t)k * 47, smp.P, 11 * sizeof(float));
+                    std::memcpy(aux + (size_t)k * 47 + 11, smp.N, 36 * sizeof(float));
+                }
+            }
+            g.sync();
+        }
+    };
+    std::thread t1(lane, 1), t2(lane, 2), t3(lane, 3);
+    lane(0);
+    t1.join();
+    t2.join();
+    t3.join();
+}
+
 extern "C" {
+void hc_e5_coop_f32(const float* pts, int K, float* models, int* nsol, int polish, float* aux) {
+    run_e5_coop(pts, K, models, nsol, polish, aux);
+}
 void hc_e5_solve_f32(const float* pts, int K, float* models, int* nsol, int polish) {
     run_e5<float>(pts, K, models, nsol, polish);
 }

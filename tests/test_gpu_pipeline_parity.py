@@ -83,7 +83,7 @@ def test_the_benched_pipeline_picks_the_oracles_winner_or_a_tie(cfg2):
             worst_model_score = max(worst_model_score, rel_m)
             detail.append(dict(pair=b, ours_hyp=ours_hyp, oracle_hyp=ref["best"] // 10, ours=ours_score,
                                oracle=ref["score"], rel=rel, rel_score_of_our_model=rel_m))
-        report[sc] = dict(pairs=cfg2["B"], same_best_hypothesis=same, ties_within_1e-4=ties, worse=worse,
+        report[sc] = dict(pairs=cfg2["B"], same_best_hypothesis=same, ties_within_1e_4=ties, worse=worse,
                           worst_tie_rel=worst_tie, worst_rel_score_on_identical_model=worst_model_score, detail=detail)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "r2_pipeline_parity.json"), "w") as f:

@@ -409,3 +409,51 @@ def test_msac_tc_against_the_reference_golden(lib, golden, words):
     rel = (got - want).abs() / want.clamp_min(1.0)
     assert float(rel.max()) < 1e-4, float(rel.max())
     assert int(got.argmax()) == int(g["best"])
+
+
+def test_e5_cooperative_stages_match_the_serial_solver_against_fp64():
+    """csrc/e5_coop.cuh (four lanes per sample; on the host: four threads and a barrier) against the fp64 oracle
+    (nister.py:69-408) beside the one-thread-per-sample composition of the same headers: the cooperative split
+    changes summation orders and the pivoting bookkeeping, not what is found."""
+    import ctypes
+
+    import numpy as np
+
+    import hostcheck
+    from helpers import trace_constraint_residual
+    from oracle import nister
+
+    lib = hostcheck.load()
+    from differentiable_ransac_b200 import synth
+
+    m, _, inl = synth.relative_pose_pair(2000, 0.5, seed=3, noise=5e-4)
+    g = torch.Generator().manual_seed(21)
+    K = 256
+    idx = torch.stack([torch.randperm(2000, generator=g)[:5].sort().values for _ in range(K)])
+    inl_idx = inl.nonzero().flatten()
+    for k in range(0, K, 2):                       # half the samples all-inlier
+        idx[k] = inl_idx[torch.randperm(inl_idx.numel(), generator=g)[:5]].sort().values
+    pts = m[idx]
+    m64 = nister.five_point(pts.double()).reshape(K, 10, 3, 3)
+    genuine = (trace_constraint_residual(m64.reshape(-1, 3, 3)) < 1e-8).reshape(K, 10)
+    r = m64.flatten(2)
+    r = r / r.norm(dim=-1, keepdim=True)
+    ptsn = np.ascontiguousarray(pts.numpy(), dtype=np.float32)
+    found = {}
+    for fn, extra in (("hc_e5_solve_f32", False), ("hc_e5_coop_f32", True)):
+        models = np.zeros((K, 10, 9), np.float32)
+        nsol = np.zeros(K, np.int32)
+        args = [ptsn.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(K), models.ctypes.data_as(ctypes.c_void_p),
+                nsol.ctypes.data_as(ctypes.c_void_p), ctypes.c_int(2)]
+        if extra:
+            args.append(ctypes.c_void_p(0))
+        getattr(lib, fn)(*args)
+        ours, ns = torch.from_numpy(models).reshape(K, 10, 3, 3).double(), torch.from_numpy(nsol)
+        live = torch.arange(10)[None] < ns[:, None]
+        assert torch.allclose(ours.flatten(2).norm(dim=-1)[live], torch.ones(int(live.sum()), dtype=torch.float64),
+                              atol=1e-5)
+        c = torch.where(live[..., None, None], ours, torch.full_like(ours, 1e3)).flatten(2)
+        d = torch.minimum((c[:, :, None] - r[:, None]).norm(dim=-1), (c[:, :, None] + r[:, None]).norm(dim=-1)).min(1).values
+        found[fn] = float((d[genuine] < 1e-3).double().mean())
+        assert found[fn] >= 0.95 and float(d[genuine].median()) < 1e-5
+    assert abs(found["hc_e5_solve_f32"] - found["hc_e5_coop_f32"]) < 0.01
