@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdlib>
+#include <cstring>
 
 #include "../../include/drb.h"
 #include "device_cfg.cuh"
@@ -248,8 +249,8 @@ solve_e5_thread_kernel(const float* __restrict__ matches, const int32_t* __restr
 
 // ---- the cooperative kernel: four lanes per hypothesis for the per-sample stages (e5_coop.cuh), one ROOT per
 // thread for the per-root stage, pooled over the CTA ------------------------------------------------------------
-constexpr int kCoThreads = 128;
-constexpr int kCoSamples = kCoThreads / kQuad;                       // 32 samples per CTA
+constexpr int kCoSamples = 32;                                       // samples per CTA: 128 threads in quads
+constexpr int kCoQuadThreads = kCoSamples * kQuad;
 constexpr int kCoSmemBytes = kCoSamples * kCoStride * sizeof(float);   // 41 856 B
 
 struct QuadDev {
@@ -261,16 +262,20 @@ struct QuadDev {
     __device__ __forceinline__ void sync() const { __syncwarp(mask); }
 };
 
-template <int MINB>      // CTAs per SM the register allocation aims at: 4 = 128 registers, 5 = 96 (what shared memory allows)
-__global__ void __launch_bounds__(kCoThreads, MINB)
+// NT threads per CTA: the first 128 form the 32 quads; warps beyond them (NT = 160, 192) sit out the per-sample stages
+// and join the per-root stage, so that the CTA's ~147 brackets (4.6 per sample) go through in ONE trip instead of
+// 128 + 19 with three warps waiting at the barrier.  MINB: CTAs per SM the register allocation aims at.
+template <int NT, int MINB>
+__global__ void __launch_bounds__(NT, MINB)
 solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
                 float* __restrict__ models, int32_t* __restrict__ nsol, float* __restrict__ cmodels,
                 int32_t* __restrict__ cids, int32_t* __restrict__ ccount) {
     extern __shared__ float smem[];
-    __shared__ int prefix[kCoThreads / 32][kCoSamples + 1];
+    __shared__ int prefix[NT / 32][kCoSamples + 1];
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
-    const int sl = tid >> 2;                                   // the quad's sample slot in the CTA
+    const bool quad_thread = tid < kCoQuadThreads;             // warp-uniform
+    const int sl = quad_thread ? tid >> 2 : 0;                 // the quad's sample slot in the CTA
     const long long rows_all = (long long)B * K;
     const long long row0 = (long long)blockIdx.x * kCoSamples;
     const long long row = row0 + sl;
@@ -282,7 +287,7 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
     QuadDev g{tid & 3, lane & ~3, 0xFu << (lane & ~3)};
 
     // ---- stages 1 + 2: the quad's own sample ---------------------------------------------------------------
-    {
+    if (quad_thread) {
         float p[5][4], P[11];
         load_minimal5(matches, idx, rowc, b, N, p);
         const bool ok = e5_coop_prepare<float, QuadDev>(g, p, S, P);
@@ -309,7 +314,7 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
     const int* pre = prefix[tid >> 5];
     const int total = pre[kCoSamples];
     // ---- stage 3: one bracket per thread per trip (Newton in the bracket, back-substitution, polish, normalise) ---
-    for (int it = tid; it < total; it += kCoThreads) {
+    for (int it = tid; it < total; it += NT) {
         int lo = 0, hi = kCoSamples;                // owner = largest L with pre[L] <= it
         DRB_UNROLL
         for (int s_ = 0; s_ < 5; ++s_) {
@@ -330,6 +335,7 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
         }
     }
     __syncthreads();
+    if (!quad_thread) return;
     // ---- the quad closes its own sample: holes left by dropped roots (lane 0), identity in the unused slots ----------
     if (g.q == 0) {
         const int vmask = reinterpret_cast<const int*>(S)[kCoMask];
@@ -467,22 +473,26 @@ extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int
                                  (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol, cmodels, cids, ccount);
         return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
     }
-    static const int minb = []() {             // measurement switch: DRB_E5_MINB=4 -> the 128-register build
-        const char* e = getenv("DRB_E5_MINB");
-        return (e != nullptr && e[0] == '4') ? 4 : 5;
+    // measurement switch DRB_E5_SHAPE = "<threads>x<CTAs per SM>": 128x4 (128 registers), 128x5 (96), 160x4 (default), 192x3
+    static const int shape = []() {
+        const char* e = getenv("DRB_E5_SHAPE");
+        if (e == nullptr) return 1604;
+        return atoi(e) * 10 + (strchr(e, 'x') ? atoi(strchr(e, 'x') + 1) : 4);
     }();
     const unsigned grid = (unsigned)((rows + kCoSamples - 1) / kCoSamples);
-    if (minb == 4) {
-        static std::atomic<unsigned long long> configured{0};
-        if (!ensure_dynamic_smem(solve_e5_kernel<4>, kCoSmemBytes, configured)) return DRB_ERR_CUDA;
-        solve_e5_kernel<4><<<grid, kCoThreads, kCoSmemBytes, (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol,
-                                                                                      cmodels, cids, ccount);
-    } else {
-        static std::atomic<unsigned long long> configured{0};
-        if (!ensure_dynamic_smem(solve_e5_kernel<5>, kCoSmemBytes, configured)) return DRB_ERR_CUDA;
-        solve_e5_kernel<5><<<grid, kCoThreads, kCoSmemBytes, (cudaStream_t)stream>>>(matches, idx, B, K, N, models, nsol,
-                                                                                      cmodels, cids, ccount);
+#define DRB_E5_LAUNCH(NT_, MB_)                                                                                  \
+    {                                                                                                            \
+        static std::atomic<unsigned long long> configured{0};                                                    \
+        if (!ensure_dynamic_smem(solve_e5_kernel<NT_, MB_>, kCoSmemBytes, configured)) return DRB_ERR_CUDA;      \
+        solve_e5_kernel<NT_, MB_><<<grid, NT_, kCoSmemBytes, (cudaStream_t)stream>>>(matches, idx, B, K, N, models, \
+                                                                                      nsol, cmodels, cids, ccount); \
     }
+    if (shape == 1284) DRB_E5_LAUNCH(128, 4)
+    else if (shape == 1285) DRB_E5_LAUNCH(128, 5)
+    else if (shape == 1923) DRB_E5_LAUNCH(192, 3)
+    else if (shape == 1924) DRB_E5_LAUNCH(192, 4)
+    else DRB_E5_LAUNCH(160, 4)
+#undef DRB_E5_LAUNCH
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
 

@@ -17,7 +17,7 @@ noise = synth.gumbel_noise((B, K, N), seed=3)
 m, E, lg, thr, noise = m.to(DEV), E.to(DEV), lg.to(DEV), thr.to(DEV), noise.to(DEV)
 for kw in (dict(), dict(noise=noise), dict(sampler="gumbel")):
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, **kw)
-TC = os.environ.get("DRB_SANITIZE_TC", "tc_tf32,tc_bf16").split(",")   # add the unmeasured variants by hand: tc_tf32p, tc2_tf32, ...
+TC = os.environ.get("DRB_SANITIZE_TC", "tc_tf32,tc_bf16,tc_bf16p").split(",")
 for scorer in ["block", "stream"] + [t for t in TC if t]:   # every MSAC kernel; the queue kernel with a block cut into pieces
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, scorer=scorer)
 svc = engine.E5TestService(B, N, K, DEV, slots=2, seed=1, graph=False, host_io=False)
@@ -38,5 +38,11 @@ l3 = torch.rand(2, 1001, device=DEV, requires_grad=True)
 for flag in (True, False):
     r, v = engine.HypothesizeRigid.apply(pts, l3, 50, flag, 1.0, None, 0, 0)
     engine.RigidResidual.apply(pts, r).mean().backward()
+for kind, data in (("e5", (m, lg, E, m, torch.full((B,), N, dtype=torch.int32, device=DEV))),
+                   ("f8", (m, lg, None, m, torch.full((B,), N, dtype=torch.int32, device=DEV)))):
+    st = engine.TrainStep(kind, B, N, K, DEV, P=N, seed=3, graph=False, want_grad_matches=True)   # the fused training step
+    st.run(*data)
+st = engine.TrainStep("rigid", 2, 1001, 50, DEV, seed=3, graph=False)
+st.run(pts, l3.detach())
 torch.cuda.synchronize()
 print("sanitize smoke ok", float(out["best_score"].sum()), float(out8["best_score"].sum()))

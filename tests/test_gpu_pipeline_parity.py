@@ -6,10 +6,17 @@ correspondences): `drb_sample_sets` -> `drb_solve_e5` -> the scorer the pipeline
                -> oracle.scoring.msac_score(matches.double(), ...)      msac_score.py:12-55
                -> arg-max over the genuine models                       ransac.py:114
 
-Per pair the bar is: the same winning hypothesis (`best_id // 10`), or a winner whose score is within 1e-4
-relative of the oracle's best (a tie: on noise-free synthetic pairs every all-inlier sample scores the same to
-~1e-6, and which of them is "best" is decided by rounding -- in the reference too).  Every mismatch
-is classified and the counts are written to gpurun_out/r2_pipeline_parity.json.
+Per pair the outcome is classified:
+    same    the same winning hypothesis (`best_id // 10`)
+    tie     another hypothesis whose score is within 1e-4 relative of the oracle's best (on noise-free synthetic pairs
+            every all-inlier sample scores the same to ~1e-6, and which of them is "best" is decided by rounding -- in
+            the reference too)
+    higher  our winner scores MORE than the oracle's best by over 1e-4 (and the fp64 oracle, scoring OUR model,
+            confirms that score): the fp32 solver's model of an ill-conditioned sample is ~1e-5 away from the exact
+            minimal solution and happens to fit the consensus better.  Seen on at most one pair of the 32, by 1.5e-4
+    worse   our winner scores less than the oracle's best by over 1e-4: the solver lost the best model
+The bar: no `worse`, at most two `higher` and none beyond 1e-3.  The counts and every pair's numbers are written to
+gpurun_out/r2_pipeline_parity.json.
 
 Second bar (scores on identical inputs): the score our scorer gives OUR winning model equals the fp64 oracle's
 score of that same model within 1e-4 relative -- for the tensor-core scorer and for the FP32 work-queue kernel."""
@@ -62,8 +69,8 @@ def test_the_benched_pipeline_picks_the_oracles_winner_or_a_tie(cfg2):
     report = {}
     for sc in cfg2["scorers"]:
         o = cfg2["runs"][sc]
-        same = ties = worse = 0
-        worst_tie, worst_model_score = 0.0, 0.0
+        same = ties = worse = higher = 0
+        worst_tie, worst_model_score, worst_higher = 0.0, 0.0, 0.0
         detail = []
         for b in range(cfg2["B"]):
             ref = cfg2["oracle"][b]
@@ -74,6 +81,9 @@ def test_the_benched_pipeline_picks_the_oracles_winner_or_a_tie(cfg2):
             elif rel <= 1e-4:
                 ties += 1
                 worst_tie = max(worst_tie, rel)
+            elif ours_score > ref["score"]:
+                higher += 1
+                worst_higher = max(worst_higher, rel)
             else:
                 worse += 1
             # identical inputs: OUR winning model scored by the fp64 oracle
@@ -83,14 +93,16 @@ def test_the_benched_pipeline_picks_the_oracles_winner_or_a_tie(cfg2):
             worst_model_score = max(worst_model_score, rel_m)
             detail.append(dict(pair=b, ours_hyp=ours_hyp, oracle_hyp=ref["best"] // 10, ours=ours_score,
                                oracle=ref["score"], rel=rel, rel_score_of_our_model=rel_m))
-        report[sc] = dict(pairs=cfg2["B"], same_best_hypothesis=same, ties_within_1e_4=ties, worse=worse,
-                          worst_tie_rel=worst_tie, worst_rel_score_on_identical_model=worst_model_score, detail=detail)
+        report[sc] = dict(pairs=cfg2["B"], same_best_hypothesis=same, ties_within_1e_4=ties, higher_than_oracle=higher,
+                          worse=worse, worst_tie_rel=worst_tie, worst_higher_rel=worst_higher,
+                          worst_rel_score_on_identical_model=worst_model_score, detail=detail)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "r2_pipeline_parity.json"), "w") as f:
         json.dump(dict(workload="cfg2: 32 x 1000 x 2000, sample_sets(seed=42, offset=3)", report=report), f, indent=1)
     for sc, r in report.items():
         print(sc, {k: v for k, v in r.items() if k != "detail"})
         assert r["worse"] == 0, (sc, [d for d in r["detail"] if d["ours_hyp"] != d["oracle_hyp"] and d["rel"] > 1e-4])
+        assert r["higher_than_oracle"] <= 2 and r["worst_higher_rel"] <= 1e-3, (sc, r["higher_than_oracle"])
         assert r["worst_rel_score_on_identical_model"] <= 1e-4, (sc, r["worst_rel_score_on_identical_model"])
 
 
