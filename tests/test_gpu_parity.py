@@ -222,6 +222,34 @@ def test_stewenius_solutions_contained(drb, golden):
     assert (d < 2e-3).float().mean() > 0.9
 
 
+def test_stewenius_fp64_solution_set_is_found(drb, golden):
+    """Row a4: why one kernel serves both of the reference's five-point classes.  Run in fp64 (stewenius_64.npz, the
+    reference class itself; tests/test_oracle_golden.py shows its genuine models coincide with the fp64 Nister class's
+    to 1e-8, 224 of 224), the action-matrix solver (stewenius.py:20-80) defines a SET of essential matrices per
+    sample; the kernel finds that set -- the same bar as for the Nister class (>= 95 % within 1e-3 up to sign and
+    scale, median < 1e-5; measured 98.7 %), where the reference's own fp32 Stewenius run reaches its fp64 models far
+    less often."""
+    g, g64 = golden("stewenius"), golden("stewenius_64")
+    K = g["pts"].shape[0]
+    ref = unit(g64["E64"]).view(K, 10, 3, 3)
+    genuine = (trace_constraint_residual(unit(g64["E64"])) < 1e-8).view(K, 10)
+    models, nsol = drb.ops.solve_e5(g["pts"].to(DEV))
+    ours = models[0].cpu()
+    live = torch.arange(10)[None] < nsol[0].cpu()[:, None]
+    ours = torch.where(live[..., None, None], ours, torch.full_like(ours, 1e3))
+    d = match_up_to_sign(ours, ref)[genuine]
+    assert (d < 1e-3).float().mean() >= 0.95 and d.median() < 1e-5
+    # the reference's own fp32 run of the class against its fp64 run, same measure
+    ref32 = unit(g["E32"]).view(K, 10, 3, 3)
+    d32 = match_up_to_sign(ref32, ref)[genuine]
+    assert (d < 1e-3).float().mean() >= (d32 < 1e-3).float().mean()
+    # and the host mirror class routes to the same kernel with the reference's call shape
+    from differentiable_ransac_b200.estimators.essential_matrix_estimator_stewenius import EssentialMatrixEstimator
+    est = EssentialMatrixEstimator(DEV)
+    out = est.estimate_minimal_model(g["pts"].to(DEV))
+    assert out.shape == (K * 10, 3, 3) and torch.equal(out.view(K, 10, 3, 3), models[0])
+
+
 # ---- a9 MSAC + arg-max -----------------------------------------------------------------------------------
 def test_msac_scores_argmax_mask(drb, golden):
     g = golden("msac")
@@ -373,16 +401,22 @@ def test_e5_train_step_gradients_vs_reference(drb, golden):
     gl, rl, rl32 = logits.grad[0].cpu().double(), g64["sel_grad_logits"], g32["sel_grad_logits"].double()
     gm, rm, rm32 = matches.grad[0].cpu().double(), g64["sel_grad_matches"], g32["sel_grad_matches"].double()
     err_l, err_m = (gl - rl).norm() / rl.norm(), (gm - rm).norm() / rm.norm()
-    if same.all():
-        # identical model set: soft loss and gradients within 1e-4 relative of the fp64 reference
-        assert abs(loss.item() - g64["sel_loss"].item()) < 1e-4 * abs(g64["sel_loss"].item())
-        assert err_l < 1e-4 and err_m < 1e-4
+    # identical model set (measured on the B200: every model within 1e-3, gradients 1.5e-5 / 2.3e-5 from the fp64
+    # reference, profiles/r2_grad_parity.json): soft loss and gradients within 1e-4 relative of the fp64 reference
+    assert same.all()
+    assert abs(loss.item() - g64["sel_loss"].item()) < 1e-4 * abs(g64["sel_loss"].item())
+    assert err_l < 1e-4 and err_m < 1e-4
     # in any case: at least as close to the fp64 reference as the fp32 reference itself is
     assert err_l < max(1e-4, 1.5 * (rl32 - rl).norm() / rl.norm())
     assert err_m < max(1e-4, 1.5 * (rm32 - rm).norm() / rm.norm())
 
 
 def test_f8_train_step_gradients_vs_reference(drb, golden):
+    """The eight-point unit in PIXEL units.  This fixture's gradient is ill-conditioned by construction: 98.7 % of its
+    (model, point) terms sit above the clamp at 1, and merely rounding the reference's exact fp64 models to fp32
+    moves d loss / d models by 2.2 % (the fp32 reference's own gradient is 188 % away from its fp64 self).  Measured
+    on the B200: 9.2e-3 / 7.3e-3 (profiles/r2_grad_parity.json) -- hence the 1e-2 bar here; the well-conditioned
+    chain train.py actually runs is `test_f8_layer_train_gradients_vs_reference` below, at 1e-3."""
     g64 = golden("f8_train_64")
     matches = g64["matches"][None].to(DEV).requires_grad_(True)
     logits = g64["logits"][None].to(DEV).requires_grad_(True)
@@ -403,6 +437,38 @@ def test_f8_train_step_gradients_vs_reference(drb, golden):
     assert (gm - rm).norm() / rm.norm() < 1e-2
 
 
+def test_f8_layer_train_gradients_vs_reference(drb, golden):
+    """cfg3 as train.py runs it (`-fmat 1 -sam 3 -tr 1 -w2 1`): RANSACLayer.forward (points denormalised to pixels,
+    eight-point per sample) -> MatchLoss(fmat=1) (E = K2^T F K1 on K-normalised points) -> backward to the sampling
+    weights, against the reference's own run of the same chain in fp64 (tests/golden/make_golden_r2.py)."""
+    import types
+
+    from differentiable_ransac_b200.loss import MatchLoss
+    from differentiable_ransac_b200.model_cl import RANSACLayer
+    g64, g32 = golden("f8_layer_train_64"), golden("f8_layer_train_32")
+    K = g64["noise"].shape[0]
+    opt = types.SimpleNamespace(device=DEV, fmat=1, sampler=3, precision=1, tr=1, threshold=0.75, ransac_batch_size=K,
+                                weighted=0)
+    layer = RANSACLayer(opt)
+    layer.estimator.max_iterations = K
+    layer.estimator.sampler.injected_noise = g64["noise"].to(DEV)
+    pts = g64["points"].to(DEV)
+    w = g64["logits"].to(DEV).requires_grad_(True)
+    Kc, im = g64["K"].to(DEV), g64["im_size"].to(DEV)
+    Es, _ = layer.forward(pts, w, Kc, Kc, im, im, g64["F_gt"].to(DEV))
+    loss = MatchLoss(1).forward([Es], g64["gt_E"].numpy()[None], [pts[:, 0:2]], [pts[:, 2:4]], [Kc], [Kc], [im], [im])
+    loss.backward()
+    ref = g64["models"]
+    d = torch.minimum((Es.detach().cpu() - ref).flatten(1).norm(dim=1),
+                      (Es.detach().cpu() + ref).flatten(1).norm(dim=1)) / ref.flatten(1).norm(dim=1)
+    assert Es.shape == ref.shape and d.max() < 1e-3
+    assert abs(loss.item() - g64["loss"].item()) < 1e-4 * abs(g64["loss"].item())
+    gl, rl, rl32 = w.grad.cpu().double(), g64["grad_logits"], g32["grad_logits"].double()
+    err = (gl - rl).norm() / rl.norm()
+    assert err < 1e-3, float(err)
+    assert err < 1.5 * (rl32 - rl).norm() / rl.norm()       # at least as close to fp64 as the fp32 reference is (3.1e-4)
+
+
 def test_rigid_train_step_vs_reference(drb, golden):
     g = golden("rigid_train")
     points = g["points"][None].to(DEV)
@@ -418,7 +484,12 @@ def test_rigid_train_step_vs_reference(drb, golden):
     loss.backward()
     assert abs(loss.item() - g["loss"].item()) < 2e-3 * abs(g["loss"].item())
     gl, rl = logits.grad[0].cpu(), g["grad_logits"]
-    assert (gl - rl).norm() / rl.norm() < 2e-2
+    assert (gl - rl).norm() / rl.norm() < 2e-4           # the fp32 reference: itself 9.2e-5 from its fp64 run
+    # against the reference's fp64 run of the same branch (rigid_train_64): measured 4.8e-7 on the B200
+    g64 = golden("rigid_train_64")
+    assert abs(loss.item() - g64["loss"].item()) < 1e-5 * abs(g64["loss"].item())
+    assert torch.allclose(res[0].detach().cpu().double(), g64["residuals"], rtol=1e-5)
+    assert (gl.double() - g64["grad_logits"]).norm() / g64["grad_logits"].norm() < 1e-4
 
 
 # ---- full BASELINE sizes through size-independent properties -----------------------------------------------------------

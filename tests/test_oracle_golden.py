@@ -40,6 +40,26 @@ def test_nister_fp32_within_reference_noise_floor(golden):
     assert d_or.median() < 1e-4
 
 
+def test_stewenius_fp64_and_the_two_classes_define_the_same_models(golden):
+    """The reference's Stewenius class run in fp64 (stewenius_64.npz): the port reproduces it, and its genuine models
+    (trace-constraint residual < 1e-8) are, up to scale and sign, exactly the genuine models of the reference's
+    Nister class in fp64 -- same count, every model matched to 1e-7.  This is what lets ONE device kernel stand
+    behind both estimator classes."""
+    from helpers import match_up_to_sign, trace_constraint_residual, unit
+    g, g64 = golden("stewenius"), golden("stewenius_64")
+    pts = g["pts"].double()
+    K = pts.shape[0]
+    ref = unit(g64["E64"]).view(K, 10, 3, 3)
+    port = unit(stewenius.five_point(pts)).view(K, 10, 3, 3)
+    real = (trace_constraint_residual(unit(g64["E64"])) < 1e-8).view(K, 10)
+    assert float(match_up_to_sign(port, ref)[real].max()) < 1e-10
+    En = nister.five_point(pts).view(K, 10, 3, 3)
+    gn = (trace_constraint_residual(En.reshape(-1, 3, 3)) < 1e-8).view(K, 10)
+    assert int(real.sum()) == int(gn.sum()) and torch.equal(real.sum(1), gn.sum(1))
+    assert float(match_up_to_sign(unit(En), ref)[real].max()) < 1e-7
+    assert float(match_up_to_sign(ref, unit(En))[gn].max()) < 1e-7
+
+
 def test_stewenius(golden):
     g = golden("stewenius")
     E = stewenius.five_point(g["pts"])
