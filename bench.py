@@ -164,6 +164,44 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+class StartGate:
+    """Holds the GPU work of a timed region back until the host has enqueued it: `close(stream)` enqueues a stream
+    memory operation (cuStreamWaitValue32 on a flag in pinned host memory) that blocks `stream` -- and every stream
+    made to wait on it -- until `open()` stores 1 into the flag.  With the steps enqueued behind the gate, the CUDA
+    events around them time the device alone: the host's enqueue jitter (a few percent of a 20-step, ~3 ms window,
+    and the max over N ranks picks the unluckiest) stays outside.  At most `depth` steps are enqueued before the
+    gate opens, far below the driver's launch-queue depth.  Falls back to no gate when the driver call is
+    unavailable (DRB_BENCH_GATE=0 turns it off)."""
+
+    depth = 64
+
+    def __init__(self):
+        self.ok = os.environ.get("DRB_BENCH_GATE", "1") != "0"
+        try:
+            from cuda.bindings import driver as cu
+
+            self.cu = cu
+            self.flag = torch.zeros(1, dtype=torch.int32).pin_memory()
+        except Exception:
+            self.ok = False
+
+    def close(self, stream):
+        if not self.ok:
+            return False
+        self.flag[0] = 0
+        try:
+            (err,) = self.cu.cuStreamWaitValue32(stream.cuda_stream, self.flag.data_ptr(), 1,
+                                                 self.cu.CUstreamWaitValue_flags.CU_STREAM_WAIT_VALUE_EQ)
+            self.closed = err == self.cu.CUresult.CUDA_SUCCESS
+        except Exception:
+            self.closed = False
+        return self.closed
+
+    def open(self):
+        if self.ok:
+            self.flag[0] = 1
+
+
 def make_inputs(B, N, seed):
     from differentiable_ransac_b200 import synth
 
@@ -418,13 +456,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-slots", type=int, default=int(os.environ.get("DRB_E2E_SLOTS", "3")),
+    ap.add_argument("--e2e-slots", type=int, default=int(os.environ.get("DRB_E2E_SLOTS", "4")),
                     help="batches in flight in the end-to-end plugin calls (RANSACLayer.submit / collect)")
     ap.add_argument("--e2e-graph", type=int, default=int(os.environ.get("DRB_E2E_GRAPH", "1")),
                     help="1: each service slot replays one CUDA graph (kernels, copy-out) per batch")
     ap.add_argument("--value-graph", type=int, default=int(os.environ.get("DRB_VALUE_GRAPH", "1")),
                     help="1: the device-resident steps replay one CUDA graph per stream")
-    ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "3")),
+    ap.add_argument("--value-streams", type=int, default=int(os.environ.get("DRB_VALUE_STREAMS", "4")),
                     help="CUDA streams the K device-resident steps are issued over (1 = strictly serial)")
     args = ap.parse_args()
     # stdout carries exactly one JSON line: everything else a library prints there while we run (NCCL's version
@@ -512,12 +550,17 @@ def run_ours(args):
     main_stream = torch.cuda.current_stream()
     dsvc = engine.E5TestService(B, N, K, dev, slots=S, seed=42 + rank, graph=bool(args.value_graph), host_io=False)
 
-    def run_steps(n, first):
+    gate = StartGate()
+
+    def run_steps(n, first, gated=False):
         """n independent steps (fresh Philox offset each) through engine.E5TestService(host_io=False): issued
         round-robin over S streams (one CUDA graph per stream when --value-graph 1), so the latency-bound
         5-point kernel of one step overlaps the scoring kernel of the previous one.  Every step first copies ITS
-        inputs, device to device, from one of NB distinct places in HBM."""
+        inputs, device to device, from one of NB distinct places in HBM.  `gated`: the first steps (up to
+        StartGate.depth) are enqueued behind the start gate, which the caller has closed on the main stream."""
         for i in range(n):
+            if gated and i == StartGate.depth:
+                gate.open()
             dsvc.submit(packed=packed_all[(first + i) % NB])
         dsvc.join(main_stream)
         return dsvc.dev_out[(n - 1) % S]
@@ -530,9 +573,11 @@ def run_ours(args):
         clocks.start()
     t_begin, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     _barrier(dist)
+    gated = gate.close(main_stream)          # the slots' streams wait on the main stream (E5TestService.submit)
     t_begin.record(main_stream)
-    run_steps(args.steps, warmup)
+    run_steps(args.steps, warmup, gated=gated)
     t_end.record(main_stream)
+    gate.open()
     _barrier(dist)
     ms_total = _max_over_ranks(t_begin.elapsed_time(t_end), dev, dist)
     clock_info = clocks.stop() if rank == 0 else None
@@ -653,6 +698,9 @@ def run_ours(args):
                        "serial_ms_per_step and the roofline pass: L2 flushed by a 256 MB write before each launch; "
                        "e2e re-copies its inputs from the host every step",
                     value_streams=S, value_graph=bool(args.value_graph), serial_ms_per_step=ms_serial,
+                    start_gate=("the timed steps (the first %d of them) are enqueued behind a cuStreamWaitValue32 gate "
+                                "that opens when the host has enqueued them: the events time the device, not the host's "
+                                "enqueue jitter" % min(args.steps, StartGate.depth)) if gated else "off",
                     scorer=f"{msac_name} ({msac_kernel})",
                     e2e_mode=f"model_cl.RANSACLayer.submit / collect (the reference-facing plugin; test mode, adaptive "
                              f"exit and final refit off = the hot path proper), {slots} batches in flight (one stream "
@@ -799,11 +847,16 @@ def run_train(args):
     if rank == 0:
         clocks.start()
     t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    gate = StartGate()
     _barrier(dist)
+    gated = gate.close(main_stream)
     t0.record()
     for i in range(args.steps):
+        if gated and i == StartGate.depth:
+            gate.open()
         one_step(warmup + i)
     t1.record()
+    gate.open()
     _barrier(dist)
     ms_total = _max_over_ranks(t0.elapsed_time(t1), dev, dist)
     clock_info = clocks.stop() if rank == 0 else None
@@ -866,6 +919,7 @@ def run_train(args):
                          "backward; ONE CUDA graph replay per step; gradient: d loss / d logits [B,N]",
                     l2=f"the step's inputs rotate over {NB} distinct copies in HBM ({NB * in_bytes >> 20} MB > L2), copied "
                        "device to device inside the timed region",
+                    start_gate="on (see cfg2)" if gated else "off",
                     allreduce=(None if not do_ar else
                                dict(bytes=CLNET_PARAMS * 4, ms_alone=ar_ms, share_of_step=ar_ms / ms_per_step,
                                     placement="own stream, behind the step's backward; the next step waits for it "
