@@ -755,11 +755,9 @@ def _train_stage_table(cfg, data, dev):
                     B * N * 4 + B * K * (4 * s + 4 + 4 * s))
     if kind == "e5":
         gt = data["gt"].to(dev)
-        models, nsol = ops.solve_e5(m, idx)
-        sel, used = ops.select_closest(models, nsol, gt)
+        sel, used, _, _ = ops.solve_e5_select(m, idx, gt)
         valid = sel >= 0
-        st["solve_e5"] = (_time_stage(lambda: ops.solve_e5(m, idx)), B * K * (s * 16 + 360 + 4))
-        st["select_closest"] = (_time_stage(lambda: ops.select_closest(models, nsol, gt)), B * K * (360 + 4 + 36 + 4))
+        st["solve_e5_select"] = (_time_stage(lambda: ops.solve_e5_select(m, idx, gt)), B * K * (s * 16 + 36 + 4 + 4))
     elif kind == "f8":
         used, valid = ops.solve_f8(m, idx)
         valid = valid.bool()
@@ -771,25 +769,22 @@ def _train_stage_table(cfg, data, dev):
         st["solve_rigid3"] = (_time_stage(lambda: ops.solve_rigid3(m, idx, True)), B * K * (s * 24 + 64 + 1))
     g_row = torch.full((B, K), 1.0 / (B * K), device=dev)
     if kind == "rigid":
-        st["rigid_residual_fwd"] = (_time_stage(lambda: ops.rigid_residual_forward(m, used, want_ninl=False)),
-                                    B * N * 24 + B * K * (64 + 4))
-        st["rigid_residual_bwd"] = (_time_stage(lambda: ops.rigid_residual_backward(m, used, g_row)),
-                                    B * N * 24 + B * K * (64 + 4 + 64))
-        g_used = ops.rigid_residual_backward(m, used, g_row)
+        st["rigid_residual_fwd_bwd"] = (_time_stage(lambda: ops.rigid_residual_forward_backward(m, used, g_row)),
+                                        B * N * 24 + B * K * (64 + 4 + 4 + 64))
+        _, g_used = ops.rigid_residual_forward_backward(m, used, g_row)
         st["solve_rigid3_bwd"] = (_time_stage(lambda: ops.solve_rigid3_backward(m, idx, g_used.reshape(B, K, 16), True)),
                                   B * K * (s * 24 + 64 + s * 24))
         g_pts = ops.solve_rigid3_backward(m, idx, g_used.reshape(B, K, 16), True)
     else:
         pts, npts = data["pts"].to(dev), data["npts"].to(dev)
         P = pts.shape[1]
-        st["episym_fwd"] = (_time_stage(lambda: ops.episym_forward(pts, used, npts, valid)), B * P * 16 + B * K * (36 + 4))
-        st["episym_bwd"] = (_time_stage(lambda: ops.episym_backward(pts, used, g_row, npts, valid)),
-                            B * P * 16 + B * K * (36 + 4 + 36))
-        g_used = ops.episym_backward(pts, used, g_row, npts, valid)
+        st["episym_fwd_bwd"] = (_time_stage(lambda: ops.episym_forward_backward(pts, used, g_row, npts, valid)),
+                                B * P * 16 + B * K * (36 + 4 + 4 + 36))
+        _, g_used = ops.episym_forward_backward(pts, used, g_row, npts, valid)
         if kind == "e5":
-            st["solve_e5_bwd"] = (_time_stage(lambda: ops.solve_e5_backward(m, idx, models, sel, g_used.reshape(B, K, 9))),
+            st["solve_e5_bwd"] = (_time_stage(lambda: ops.solve_e5_backward_chosen(m, idx, used, sel, g_used.reshape(B, K, 9))),
                                   B * K * (s * 16 + 36 + 36 + s * 16))
-            g_pts = ops.solve_e5_backward(m, idx, models, sel, g_used.reshape(B, K, 9))
+            g_pts = ops.solve_e5_backward_chosen(m, idx, used, sel, g_used.reshape(B, K, 9))
         else:
             st["solve_f8_bwd"] = (_time_stage(lambda: ops.solve_f8_backward(m, idx, g_used.reshape(B, K, 9), used)),
                                   B * K * (s * 16 + 36 + 36 + s * 16))

@@ -23,6 +23,8 @@ _SIGNATURES = {
                             c_int),
     "drb_solve_e5": ([P, P, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
     "drb_solve_e5_backward": ([P, P, c_int, c_int, c_int, P, P, P, P, P], c_int),
+    "drb_solve_e5_select": ([P, P, P, c_int, c_int, c_int, c_int, P, P, P, P, P], c_int),
+    "drb_solve_e5_backward_chosen": ([P, P, c_int, c_int, c_int, P, P, P, P, P], c_int),
     "drb_select_closest": ([P, P, P, c_int, c_int, c_int, c_int, P, P, P], c_int),
     "drb_solve_f8": ([P, P, c_int, c_int, c_int, P, P, P], c_int),
     "drb_solve_f8_backward": ([P, P, c_int, c_int, c_int, P, P, P, P], c_int),
@@ -44,8 +46,10 @@ _SIGNATURES = {
     "drb_best_finalize": ([P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P], c_int),
     "drb_episym_forward": ([P, P, P, P, c_int, c_int, c_int, P, P], c_int),
     "drb_episym_backward": ([P, P, P, P, P, c_int, c_int, c_int, P, P], c_int),
+    "drb_episym_forward_backward": ([P, P, P, P, P, c_int, c_int, c_int, P, P, P], c_int),
     "drb_rigid_residual_forward": ([P, P, c_int, c_int, c_int, c_float, P, P, P], c_int),
     "drb_rigid_residual_backward": ([P, P, P, c_int, c_int, c_int, P, P], c_int),
+    "drb_rigid_residual_forward_backward": ([P, P, P, c_int, c_int, c_int, P, P, P], c_int),
     "drb_gather_backward": ([P, P, P, c_int, c_int, c_int, c_int, c_int, P, P, P], c_int),
 }
 

@@ -139,7 +139,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(kScoreThreads)
 episym_kernel(const float* __restrict__ pts, const int32_t* __restrict__ npts, const float* __restrict__ models,
               const uint8_t* __restrict__ mvalid, const float* __restrict__ g_row, int K, int P, int n_split,
-              float* __restrict__ out) {
+              float* __restrict__ out, float* __restrict__ row_out) {
     __shared__ __align__(128) float tiles[2 * kTile * 4];
     __shared__ __align__(8) uint64_t bars[2];
     const int b = blockIdx.y;
@@ -185,7 +185,10 @@ episym_kernel(const float* __restrict__ pts, const int32_t* __restrict__ npts, c
                 const float ys = r * r * w;
                 if (!BWD) {
                     acc += fminf(ys, 1.f);
-                } else if (ys < 1.f) {
+                } else if (!(ys < 1.f)) {
+                    acc += 1.f;                      // clamped term: value 1, no gradient (NaN counts as clamped)
+                } else {
+                    acc += ys;
                     // d ys = 2 r w dr - r^2 (ia^2 da + ic^2 dc)
                     const float cr = 2.f * r * w;
                     const float r2 = r * r;
@@ -218,6 +221,10 @@ episym_kernel(const float* __restrict__ pts, const int32_t* __restrict__ npts, c
             if (n_split == 1) out[((size_t)b * K + k) * 9 + i] = g[i] * gr;
             else atomicAdd(out + ((size_t)b * K + k) * 9 + i, g[i] * gr);
         }
+        if (row_out) {                               // fused forward + backward: the row sums come out of the same pass
+            if (n_split == 1) row_out[(size_t)b * K + k] = acc;
+            else atomicAdd(row_out + (size_t)b * K + k, acc);
+        }
     }
 }
 
@@ -226,7 +233,7 @@ template <bool BWD>
 __global__ void __launch_bounds__(kScoreThreads)
 rigid_residual_kernel(const float* __restrict__ points, const float* __restrict__ models,
                       const float* __restrict__ g_res, int K, int N, int n_split, float threshold,
-                      float* __restrict__ out, int32_t* __restrict__ ninl) {
+                      float* __restrict__ out, int32_t* __restrict__ ninl, float* __restrict__ res_out) {
     __shared__ __align__(128) float tiles[2 * kTileRigid * 6];
     __shared__ __align__(8) uint64_t bars[2];
     const int b = blockIdx.y;
@@ -265,6 +272,7 @@ rigid_residual_kernel(const float* __restrict__ points, const float* __restrict_
                     acc += d2;
                     cnt += d2 < threshold ? 1 : 0;
                 } else {
+                    acc = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, acc)));
                     g[0] -= dx * px; g[1] -= dx * py; g[2] -= dx * pz; g[3] -= dx;
                     g[4] -= dy * px; g[5] -= dy * py; g[6] -= dy * pz; g[7] -= dy;
                     g[8] -= dz * px; g[9] -= dz * py; g[10] -= dz * pz; g[11] -= dz;
@@ -288,6 +296,10 @@ rigid_residual_kernel(const float* __restrict__ points, const float* __restrict_
         for (int i = 0; i < 12; ++i) {
             if (n_split == 1) out[((size_t)b * K + k) * 16 + i] = g[i] * gr;
             else atomicAdd(out + ((size_t)b * K + k) * 16 + i, g[i] * gr);
+        }
+        if (res_out) {
+            if (n_split == 1) res_out[(size_t)b * K + k] = acc;
+            else atomicAdd(res_out + (size_t)b * K + k, acc);
         }
     }
 }
@@ -339,7 +351,8 @@ extern "C" int drb_episym_forward(const float* pts, const int32_t* npts, const f
     const int split = pick_split(gx * B, P);
     if (split > 1) cudaMemsetAsync(row_sum, 0, sizeof(float) * (size_t)B * K, (cudaStream_t)stream);
     episym_kernel<false><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(pts, npts, models, mvalid,
-                                                                                       nullptr, K, P, split, row_sum);
+                                                                                       nullptr, K, P, split, row_sum,
+                                                                                       nullptr);
     DRB_CHECK_LAUNCH();
 }
 
@@ -352,7 +365,21 @@ extern "C" int drb_episym_backward(const float* pts, const int32_t* npts, const 
     // inactive (invalid) models keep a zero gradient
     cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 9, (cudaStream_t)stream);
     episym_kernel<true><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(pts, npts, models, mvalid, g_row,
-                                                                                      K, P, split, g_models);
+                                                                                      K, P, split, g_models, nullptr);
+    DRB_CHECK_LAUNCH();
+}
+
+extern "C" int drb_episym_forward_backward(const float* pts, const int32_t* npts, const float* models,
+                                           const uint8_t* mvalid, const float* g_row, int B, int K, int P,
+                                           float* row_sum, float* g_models, void* stream) {
+    if (!pts || !models || !g_row || !row_sum || !g_models) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || P <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
+    const int gx = (K + kScoreThreads - 1) / kScoreThreads;
+    const int split = pick_split(gx * B, P);
+    cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 9, (cudaStream_t)stream);
+    cudaMemsetAsync(row_sum, 0, sizeof(float) * (size_t)B * K, (cudaStream_t)stream);   // inactive models: 0
+    episym_kernel<true><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(pts, npts, models, mvalid, g_row,
+                                                                                      K, P, split, g_models, row_sum);
     DRB_CHECK_LAUNCH();
 }
 
@@ -367,7 +394,7 @@ extern "C" int drb_rigid_residual_forward(const float* points, const float* mode
         if (ninl) cudaMemsetAsync(ninl, 0, sizeof(int32_t) * (size_t)B * K, (cudaStream_t)stream);
     }
     rigid_residual_kernel<false><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(
-        points, models, nullptr, K, N, split, threshold, res_sum, ninl);
+        points, models, nullptr, K, N, split, threshold, res_sum, ninl, nullptr);
     DRB_CHECK_LAUNCH();
 }
 
@@ -379,6 +406,19 @@ extern "C" int drb_rigid_residual_backward(const float* points, const float* mod
     const int split = pick_split(gx * B, N);
     cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 16, (cudaStream_t)stream);
     rigid_residual_kernel<true><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(
-        points, models, g_res, K, N, split, 0.f, g_models, nullptr);
+        points, models, g_res, K, N, split, 0.f, g_models, nullptr, nullptr);
+    DRB_CHECK_LAUNCH();
+}
+
+extern "C" int drb_rigid_residual_forward_backward(const float* points, const float* models, const float* g_res, int B,
+                                                   int K, int N, float* res_sum, float* g_models, void* stream) {
+    if (!points || !models || !g_res || !res_sum || !g_models) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || N <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
+    const int gx = (K + kScoreThreads - 1) / kScoreThreads;
+    const int split = pick_split(gx * B, N);
+    cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 16, (cudaStream_t)stream);
+    if (split > 1) cudaMemsetAsync(res_sum, 0, sizeof(float) * (size_t)B * K, (cudaStream_t)stream);
+    rigid_residual_kernel<true><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(
+        points, models, g_res, K, N, split, 0.f, g_models, nullptr, res_sum);
     DRB_CHECK_LAUNCH();
 }

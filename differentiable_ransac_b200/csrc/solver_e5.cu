@@ -269,7 +269,8 @@ template <int NT, int MINB>
 __global__ void __launch_bounds__(NT, MINB)
 solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
                 float* __restrict__ models, int32_t* __restrict__ nsol, float* __restrict__ cmodels,
-                int32_t* __restrict__ cids, int32_t* __restrict__ ccount) {
+                int32_t* __restrict__ cids, int32_t* __restrict__ ccount, const float* __restrict__ gt,
+                int sign_invariant, int32_t* __restrict__ sel, float* __restrict__ chosen) {
     extern __shared__ float smem[];
     __shared__ int prefix[NT / 32][kCoSamples + 1];
     const unsigned FULL = 0xffffffffu;
@@ -382,10 +383,39 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
         pos = g.shfl(base + (inc - mine) - before_group, 0);
     }
     g.sync();
+    // ---- train mode (ransac.py:87-96): the slot closest to the ground-truth model, picked while the solutions are
+    // still in shared memory; lane q looks at slots q, q + 4, q + 8, the quad keeps the lowest slot of the minimum ----
+    if (gt != nullptr) {
+        float bd = INFINITY;
+        int bs = -1;
+        for (int s_ = g.q; s_ < n; s_ += kQuad) {
+            float dp = 0.f, dn = 0.f;
+            DRB_UNROLL
+            for (int i = 0; i < 9; ++i) {
+                const float mv = S[kCoQ + s_ * 9 + i], gv = __ldg(gt + b * 9 + i);
+                dp = fmaf(mv - gv, mv - gv, dp);
+                dn = fmaf(mv + gv, mv + gv, dn);
+            }
+            const float d = sign_invariant ? fminf(dp, dn) : dp;
+            if (d < bd) { bd = d; bs = s_; }
+        }
+        DRB_UNROLL
+        for (int o = 1; o < kQuad; o <<= 1) {
+            const float od = g.shfl(bd, g.q ^ o);
+            const int os = g.shfl(bs, g.q ^ o);
+            if (os >= 0 && (bs < 0 || od < bd || (od == bd && os < bs))) { bd = od; bs = os; }
+        }
+        if (alive) {
+            if (g.q == 0) sel[row] = bs;
+            for (int i = g.q; i < 9; i += kQuad)
+                chosen[(size_t)row * 9 + i] = bs >= 0 ? S[kCoQ + bs * 9 + i] : ((i == 0 || i == 4 || i == 8) ? 1.f : 0.f);
+        }
+    }
     if (alive) {
         // dense: the sample's 90 floats are contiguous (360 B, 8-byte aligned), written by its quad
         float2* dense = reinterpret_cast<float2*>(models + (size_t)row * 90);
-        for (int i = g.q; i < 45; i += kQuad) dense[i] = make_float2(S[kCoQ + 2 * i], S[kCoQ + 2 * i + 1]);
+        if (models != nullptr)
+            for (int i = g.q; i < 45; i += kQuad) dense[i] = make_float2(S[kCoQ + 2 * i], S[kCoQ + 2 * i + 1]);
         // compact list: the sample's models are contiguous (36 n bytes)
         if (cmodels != nullptr) {
             float* dst = cmodels + ((size_t)b * K * 10 + pos) * 9;
@@ -395,9 +425,10 @@ solve_e5_kernel(const float* __restrict__ matches, const int32_t* __restrict__ i
     }
 }
 
+// `models` is the dense [B,K,10,9] output (model_stride 90: slot sel is read) or the chosen models [B,K,9] (stride 9).
 __global__ void __launch_bounds__(128)
 solve_e5_backward_kernel(const float* __restrict__ matches, const int32_t* __restrict__ idx, int B, int K, int N,
-                         const float* __restrict__ models, const int32_t* __restrict__ sel,
+                         const float* __restrict__ models, int model_stride, const int32_t* __restrict__ sel,
                          const float* __restrict__ g_model, float* __restrict__ g_pts) {
     const long long row = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= (long long)B * K) return;
@@ -410,7 +441,7 @@ solve_e5_backward_kernel(const float* __restrict__ matches, const int32_t* __res
         load_minimal5(matches, idx, row, b, N, p);
         DRB_UNROLL
         for (int i = 0; i < 9; ++i) {
-            E[i] = models[(size_t)row * 90 + s * 9 + i];
+            E[i] = models[(size_t)row * model_stride + (model_stride == 90 ? s * 9 : 0) + i];
             g[i] = g_model[(size_t)row * 9 + i];
         }
         ok = e5_backward<float>(p, E, g, gp);
@@ -456,17 +487,15 @@ __global__ void select_closest_kernel(const float* __restrict__ models, const in
 
 using namespace drb;
 
-extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int K, int N, float* models,
-                            int32_t* nsol, float* cmodels, int32_t* cids, int32_t* ccount, void* stream) {
-    if (!matches || !models || !nsol) return DRB_ERR_NULL_POINTER;
-    if (cmodels && (!cids || !ccount)) return DRB_ERR_NULL_POINTER;
-    if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
+static int launch_solve_e5(const float* matches, const int32_t* idx, int B, int K, int N, float* models, int32_t* nsol,
+                           float* cmodels, int32_t* cids, int32_t* ccount, const float* gt, int sign_invariant,
+                           int32_t* sel, float* chosen, void* stream) {
     const long long rows = (long long)B * K;
     static const bool per_thread = []() {      // A/B switch for measurements: the round-1 one-thread-per-hypothesis kernel
         const char* e = getenv("DRB_E5_SOLVER");
         return e != nullptr && e[0] == 't';
     }();
-    if (per_thread) {
+    if (per_thread && gt == nullptr && models != nullptr) {
         static std::atomic<unsigned long long> configured{0};
         if (!ensure_dynamic_smem(solve_e5_thread_kernel, kE5SmemBytes, configured)) return DRB_ERR_CUDA;
         solve_e5_thread_kernel<<<(unsigned)((rows + kE5Threads - 1) / kE5Threads), kE5Threads, kE5SmemBytes,
@@ -484,8 +513,8 @@ extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int
     {                                                                                                            \
         static std::atomic<unsigned long long> configured{0};                                                    \
         if (!ensure_dynamic_smem(solve_e5_kernel<NT_, MB_>, kCoSmemBytes, configured)) return DRB_ERR_CUDA;      \
-        solve_e5_kernel<NT_, MB_><<<grid, NT_, kCoSmemBytes, (cudaStream_t)stream>>>(matches, idx, B, K, N, models, \
-                                                                                      nsol, cmodels, cids, ccount); \
+        solve_e5_kernel<NT_, MB_><<<grid, NT_, kCoSmemBytes, (cudaStream_t)stream>>>(                            \
+            matches, idx, B, K, N, models, nsol, cmodels, cids, ccount, gt, sign_invariant, sel, chosen);        \
     }
     if (shape == 1284) DRB_E5_LAUNCH(128, 4)
     else if (shape == 1285) DRB_E5_LAUNCH(128, 5)
@@ -496,6 +525,24 @@ extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
 
+extern "C" int drb_solve_e5(const float* matches, const int32_t* idx, int B, int K, int N, float* models,
+                            int32_t* nsol, float* cmodels, int32_t* cids, int32_t* ccount, void* stream) {
+    if (!matches || !models || !nsol) return DRB_ERR_NULL_POINTER;
+    if (cmodels && (!cids || !ccount)) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
+    return launch_solve_e5(matches, idx, B, K, N, models, nsol, cmodels, cids, ccount, nullptr, 0, nullptr, nullptr,
+                           stream);
+}
+
+extern "C" int drb_solve_e5_select(const float* matches, const int32_t* idx, const float* gt, int sign_invariant, int B,
+                                   int K, int N, float* models, int32_t* nsol, int32_t* sel, float* chosen,
+                                   void* stream) {
+    if (!matches || !gt || !nsol || !sel || !chosen) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
+    return launch_solve_e5(matches, idx, B, K, N, models, nsol, nullptr, nullptr, nullptr, gt, sign_invariant, sel,
+                           chosen, stream);
+}
+
 extern "C" int drb_solve_e5_backward(const float* matches, const int32_t* idx, int B, int K, int N,
                                      const float* models, const int32_t* sel, const float* g_model, float* g_pts,
                                      void* stream) {
@@ -503,7 +550,18 @@ extern "C" int drb_solve_e5_backward(const float* matches, const int32_t* idx, i
     if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
     const long long rows = (long long)B * K;
     solve_e5_backward_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
-        matches, idx, B, K, N, models, sel, g_model, g_pts);
+        matches, idx, B, K, N, models, 90, sel, g_model, g_pts);
+    return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
+}
+
+extern "C" int drb_solve_e5_backward_chosen(const float* matches, const int32_t* idx, int B, int K, int N,
+                                            const float* chosen, const int32_t* sel, const float* g_model, float* g_pts,
+                                            void* stream) {
+    if (!matches || !chosen || !sel || !g_model || !g_pts) return DRB_ERR_NULL_POINTER;
+    if (B <= 0 || K <= 0 || (idx && N <= 0)) return DRB_ERR_BAD_SHAPE;
+    const long long rows = (long long)B * K;
+    solve_e5_backward_kernel<<<(unsigned)((rows + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+        matches, idx, B, K, N, chosen, 9, sel, g_model, g_pts);
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
 

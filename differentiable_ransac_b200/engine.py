@@ -284,9 +284,8 @@ class HypothesizeE5(_HypothesizeBase):
     @staticmethod
     def forward(ctx, matches, logits, gt, K, tau=1.0, noise=None, seed=0, offset=0, sign_invariant=True):
         idx, lse, sel_key, _ = ops.sample(logits, K, 5, tau, noise, seed, offset, want_lse=True)
-        models, nsol = ops.solve_e5(matches, idx)
-        sel, chosen = ops.select_closest(models, nsol, gt, sign_invariant)
-        ctx.save_for_backward(ops._f32(matches), ops._f32(logits), idx, lse, sel_key, models, sel)
+        sel, chosen, _, _ = ops.solve_e5_select(matches, idx, gt, sign_invariant)      # solve + slot choice, one launch
+        ctx.save_for_backward(ops._f32(matches), ops._f32(logits), idx, lse, sel_key, chosen, sel)
         ctx.tau, ctx.noise, ctx.seed, ctx.offset = float(tau), noise, int(seed), int(offset)
         valid = sel >= 0
         ctx.mark_non_differentiable(valid)
@@ -294,8 +293,8 @@ class HypothesizeE5(_HypothesizeBase):
 
     @staticmethod
     def backward(ctx, g_chosen, _g_valid):
-        matches, logits, idx, lse, sel_key, models, sel = ctx.saved_tensors
-        g_pts = ops.solve_e5_backward(matches, idx, models, sel, g_chosen.reshape(*sel.shape, 9))
+        matches, logits, idx, lse, sel_key, chosen, sel = ctx.saved_tensors
+        g_pts = ops.solve_e5_backward_chosen(matches, idx, chosen, sel, g_chosen.reshape(*sel.shape, 9))
         gm, gl = _HypothesizeBase._backward_common(ctx, g_pts)
         return gm, gl, None, None, None, None, None, None, None
 
@@ -431,8 +430,7 @@ class TrainStep:
         m, lg, ctr = self.matches, self.logits, self.counter
         idx, lse, sel_key, _ = ops.sample(lg, K, s, self.tau, None, self.seed, 0, want_lse=True, offset_dev=ctr)
         if self.kind == "e5":
-            models, nsol = ops.solve_e5(m, idx)
-            sel, used = ops.select_closest(models, nsol, self.gt, self.sign_invariant)
+            sel, used, _, _ = ops.solve_e5_select(m, idx, self.gt, self.sign_invariant)
             valid = sel >= 0
         elif self.kind == "f8":
             used, valid = ops.solve_f8(m, idx)
@@ -440,26 +438,24 @@ class TrainStep:
         else:
             used, valid = ops.solve_rigid3(m, idx, self.flag)
             valid = valid.bool()
+        # d mean_b(loss_b) / d row depends only on which models are valid: known BEFORE the loss pass, so the loss and
+        # its gradient with respect to the models come out of ONE pass over the points
         v = valid.to(torch.float32)
         if self.kind == "rigid":
-            row, _ = ops.rigid_residual_forward(m, used, want_ninl=False)
-            row = torch.where(valid, row, torch.zeros_like(row))          # invalid models carry NaN
             denom = v.sum(1).clamp_min(1.0) * float(N)
-        else:
-            row = ops.episym_forward(self.pts, used, self.npts, valid)
-            denom = v.sum(1).clamp_min(1.0) * self.npts.to(torch.float32).clamp_min(1.0)
-        loss_pairs = (row * v).sum(1) / denom
-        g_row = v / (denom[:, None] * float(B))                            # d mean_b(loss_b) / d row
-        if self.kind == "rigid":
-            g_used = ops.rigid_residual_backward(m, torch.where(valid[..., None, None], used, torch.zeros_like(used)),
-                                                 g_row)
+            g_row = v / (denom[:, None] * float(B))
+            row, g_used = ops.rigid_residual_forward_backward(
+                m, torch.where(valid[..., None, None], used, torch.zeros_like(used)), g_row)   # invalid models carry NaN
             g_pts = ops.solve_rigid3_backward(m, idx, g_used.reshape(B, K, 16), self.flag)
         else:
-            g_used = ops.episym_backward(self.pts, used, g_row, self.npts, valid)
+            denom = v.sum(1).clamp_min(1.0) * self.npts.to(torch.float32).clamp_min(1.0)
+            g_row = v / (denom[:, None] * float(B))
+            row, g_used = ops.episym_forward_backward(self.pts, used, g_row, self.npts, valid)
             if self.kind == "e5":
-                g_pts = ops.solve_e5_backward(m, idx, models, sel, g_used.reshape(B, K, 9))
+                g_pts = ops.solve_e5_backward_chosen(m, idx, used, sel, g_used.reshape(B, K, 9))
             else:
                 g_pts = ops.solve_f8_backward(m, idx, g_used.reshape(B, K, 9), used)
+        loss_pairs = (row * v).sum(1) / denom
         g_sel, gm = ops.gather_backward(m, idx, g_pts, want_grad_matches=self.want_gm)
         gl = ops.sample_backward(lg, idx, lse, sel_key, g_sel, self.tau, None, self.seed, 0, offset_dev=ctr)
         ctr.add_(1)

@@ -204,6 +204,31 @@ def solve_e5_backward(matches, idx, models, sel, g_model):
     return g_pts
 
 
+def solve_e5_select(matches, idx, gt, sign_invariant=True, want_models=False):
+    """Train mode in one launch: five-point solve + the slot closest to gt [B,3,3].
+    -> sel [B,K] int32 (-1: none), chosen [B,K,3,3], nsol [B,K] (, models [B,K,10,3,3] when want_models)."""
+    matches, idx, B, K, N = _rows(matches, idx, 5, 4)
+    dev = matches.device
+    models = torch.empty(B, K, E5_SLOTS, 3, 3, dtype=torch.float32, device=dev) if want_models else None
+    nsol = torch.empty(B, K, dtype=torch.int32, device=dev)
+    sel = torch.empty(B, K, dtype=torch.int32, device=dev)
+    chosen = torch.empty(B, K, 3, 3, dtype=torch.float32, device=dev)
+    lib = _lib.load()
+    check(lib.drb_solve_e5_select(_p(matches), _p(idx), _p(_f32(gt).reshape(B, 9)), int(bool(sign_invariant)), B, K, N,
+                                  _p(models), _p(nsol), _p(sel), _p(chosen), _stream()), "drb_solve_e5_select")
+    return sel, chosen, nsol, models
+
+
+def solve_e5_backward_chosen(matches, idx, chosen, sel, g_model):
+    """`solve_e5_backward` from the chosen models [B,K,3,3] alone."""
+    matches, idx, B, K, N = _rows(matches, idx, 5, 4)
+    g_pts = torch.empty(B, K, 5, 4, dtype=torch.float32, device=matches.device)
+    lib = _lib.load()
+    check(lib.drb_solve_e5_backward_chosen(_p(matches), _p(idx), B, K, N, _p(_f32(chosen)), _p(_i32(sel)),
+                                           _p(_f32(g_model)), _p(g_pts), _stream()), "drb_solve_e5_backward_chosen")
+    return g_pts
+
+
 def select_closest(models, nsol, gt, sign_invariant=True):
     """models [B,K,S,3,3], nsol [B,K], gt [B,3,3] -> sel [B,K] int32, chosen [B,K,3,3]."""
     models = _f32(models)
@@ -442,6 +467,36 @@ def episym_backward(pts, models, g_row, npts=None, mvalid=None):
                                   _p(None if mvalid is None else mvalid.to(torch.uint8).contiguous()),
                                   _p(_f32(g_row)), B, K, P, _p(out), _stream()), "drb_episym_backward")
     return out
+
+
+def episym_forward_backward(pts, models, g_row, npts=None, mvalid=None):
+    """One pass over the points: (row_sum [B,K], g_models [B,K,3,3]) = (episym_forward, episym_backward)."""
+    pts = _f32(pts)
+    B, P, _ = pts.shape
+    models = _f32(models).reshape(B, -1, 9)
+    K = models.shape[1]
+    row = torch.empty(B, K, dtype=torch.float32, device=pts.device)
+    out = torch.empty(B, K, 3, 3, dtype=torch.float32, device=pts.device)
+    lib = _lib.load()
+    check(lib.drb_episym_forward_backward(_p(pts), _p(None if npts is None else _i32(npts)), _p(models),
+                                          _p(None if mvalid is None else mvalid.to(torch.uint8).contiguous()),
+                                          _p(_f32(g_row)), B, K, P, _p(row), _p(out), _stream()),
+          "drb_episym_forward_backward")
+    return row, out
+
+
+def rigid_residual_forward_backward(points, models, g_res):
+    """One pass over the points: (res_sum [B,K], g_models [B,K,4,4])."""
+    points = _f32(points)
+    B, N, _ = points.shape
+    models = _f32(models).reshape(B, -1, 16)
+    K = models.shape[1]
+    res = torch.empty(B, K, dtype=torch.float32, device=points.device)
+    out = torch.empty(B, K, 4, 4, dtype=torch.float32, device=points.device)
+    lib = _lib.load()
+    check(lib.drb_rigid_residual_forward_backward(_p(points), _p(models), _p(_f32(g_res)), B, K, N, _p(res), _p(out),
+                                                  _stream()), "drb_rigid_residual_forward_backward")
+    return res, out
 
 
 def rigid_residual_forward(points, models, threshold=0.03, want_ninl=True):

@@ -104,6 +104,17 @@ int drb_solve_e5(const float* matches, const int32_t* idx, int B, int K, int N,
 int drb_solve_e5_backward(const float* matches, const int32_t* idx, int B, int K, int N,
                           const float* models, const int32_t* sel, const float* g_model,
                           float* g_pts, void* stream);
+/* Train mode in one launch (ransac.py:78-96): the five-point solve AND the choice of the slot closest to the ground
+ * truth gt[B,9] (Frobenius; up to sign when sign_invariant), made while the solutions are still on chip.
+ * sel[B,K] = chosen slot or -1, chosen[B,K,9] = that model (identity when none).  models (nullable) = the dense
+ * [B,K,10,9] output of drb_solve_e5 when a caller wants all slots too.                        */
+int drb_solve_e5_select(const float* matches, const int32_t* idx, const float* gt, int sign_invariant,
+                        int B, int K, int N, float* models, int32_t* nsol, int32_t* sel, float* chosen, void* stream);
+/* drb_solve_e5_backward given only the chosen models [B,K,9] (what drb_solve_e5_select leaves behind).  */
+int drb_solve_e5_backward_chosen(const float* matches, const int32_t* idx, int B, int K, int N,
+                                 const float* chosen, const int32_t* sel, const float* g_model, float* g_pts,
+                                 void* stream);
+
 
 /* Train-mode slot selection, ransac.py:87-96: per sample the slot closest to gt[B,9] in
  * Frobenius norm (sign_invariant != 0: min(||E-gt||, ||E+gt||)).  Writes
@@ -198,6 +209,12 @@ int drb_episym_forward(const float* pts, const int32_t* npts, const float* model
 int drb_episym_backward(const float* pts, const int32_t* npts, const float* models, const uint8_t* mvalid,
                         const float* g_row, int B, int K, int P, float* g_models, void* stream);
 
+/* Both in ONE pass over the points (the training step knows g_row before the loss value: it depends only on which
+ * models are valid): row_sum[B,K] as drb_episym_forward, g_models[B,K,9] as drb_episym_backward.            */
+int drb_episym_forward_backward(const float* pts, const int32_t* npts, const float* models, const uint8_t* mvalid,
+                                const float* g_row, int B, int K, int P, float* row_sum, float* g_models,
+                                void* stream);
+
 /* ---- a8: rigid squared residual -------------------------------------------------------------
  * Replaces squared_residual (rigid_transformation_SVD_based_solver.py:76-89).
  * points[B,N,6], models[B,K,16] -> res_sum[B,K] = sum_n ||q - (R p + t)||^2,
@@ -207,6 +224,10 @@ int drb_rigid_residual_forward(const float* points, const float* models, int B, 
 /* g_res[B,K] -> g_models[B,K,16] (only the 3x4 [R|t] block is written).                      */
 int drb_rigid_residual_backward(const float* points, const float* models, const float* g_res,
                                 int B, int K, int N, float* g_models, void* stream);
+
+/* res_sum and g_models in one pass over the points (see drb_episym_forward_backward).          */
+int drb_rigid_residual_forward_backward(const float* points, const float* models, const float* g_res,
+                                        int B, int K, int N, float* res_sum, float* g_models, void* stream);
 
 /* ---- a2 backward: scatter minimal-sample gradients ----------------------------------------------
  * g_pts[B,K,s,D] = dL/d minimal  ->  g_sel[B,K,s] = sum_c matches[n,c] g_pts[...,c] and (nullable)

@@ -82,3 +82,40 @@ def test_train_step_equals_the_autograd_path(kind, graph):
     a = float(a)
     b, _ = step.run(m, lg, gt, pts, npts)
     assert a != float(b)
+
+
+def test_fused_entries_equal_their_parts():
+    """drb_solve_e5_select = drb_solve_e5 + drb_select_closest; drb_episym_forward_backward and
+    drb_rigid_residual_forward_backward = their forward and backward launches (one pass over the points instead of
+    two); drb_solve_e5_backward_chosen = drb_solve_e5_backward."""
+    from differentiable_ransac_b200 import ops, synth
+    B, N, K = 3, 700, 150
+    m, gt, inl = synth.relative_pose_batch(B, N, seed=61, noise=2e-4)
+    pts, npts = _inlier_pack(m, inl)
+    lg = synth.logits_regime(B, N, "L0", seed=5)
+    m, gt, lg, pts, npts = m.to(DEV), gt.to(DEV), lg.to(DEV), pts.to(DEV), npts.to(DEV)
+    idx = ops.sample_sets(lg, K, 5, seed=3)
+    models, nsol = ops.solve_e5(m, idx)
+    for si in (True, False):
+        sel0, ch0 = ops.select_closest(models, nsol, gt, si)
+        sel1, ch1, nsol1, dense = ops.solve_e5_select(m, idx, gt, si, want_models=True)
+        assert torch.equal(sel0, sel1) and torch.equal(ch0, ch1) and torch.equal(nsol, nsol1) and torch.equal(dense, models)
+    sel, chosen, _, none = ops.solve_e5_select(m, idx, gt, True)
+    assert none is None and torch.equal(chosen, ch0 if False else ops.select_closest(models, nsol, gt, True)[1])
+    valid = sel >= 0
+    g_row = torch.rand(B, K, device=DEV) * valid
+    row0 = ops.episym_forward(pts, chosen, npts, valid)
+    g0 = ops.episym_backward(pts, chosen, g_row, npts, valid)
+    row1, g1 = ops.episym_forward_backward(pts, chosen, g_row, npts, valid)
+    assert torch.allclose(row0, row1, rtol=1e-6, atol=1e-6) and torch.allclose(g0, g1, rtol=1e-6, atol=1e-9)
+    gm = torch.randn(B, K, 9, device=DEV)
+    assert torch.equal(ops.solve_e5_backward(m, idx, models, sel, gm), ops.solve_e5_backward_chosen(m, idx, chosen, sel, gm))
+    rp = torch.stack([synth.rigid_pair(1500, 0.7, seed=70 + b)[0] for b in range(2)]).to(DEV)
+    l3 = synth.logits_regime(2, 1500, "L1", seed=2).to(DEV)
+    rm, rv = ops.solve_rigid3(rp, ops.sample_sets(l3, 40, 3, seed=1), True)
+    rm = torch.where(rv.bool()[..., None, None], rm, torch.zeros_like(rm))
+    g_res = torch.rand(2, 40, device=DEV)
+    r0, _ = ops.rigid_residual_forward(rp, rm, want_ninl=False)
+    gg0 = ops.rigid_residual_backward(rp, rm, g_res)
+    r1, gg1 = ops.rigid_residual_forward_backward(rp, rm, g_res)
+    assert torch.allclose(r0, r1, rtol=1e-5) and torch.allclose(gg0, gg1, rtol=1e-6, atol=1e-9)
