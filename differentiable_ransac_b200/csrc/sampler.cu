@@ -411,8 +411,6 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
     const unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int b = blockIdx.y;
-    const int k = blockIdx.x * kTrainWarps + warp;
-    const bool live = k < K;
     const float* logits_b = logits + (size_t)b * N;
     const int n_chunks = (N + kTrainChunk - 1) / kTrainChunk;
 
@@ -453,9 +451,24 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
     DRB_UNROLL
     for (int w = 1; w < kTrainWarps; ++w) wsum += red[w];
     const float x0 = -(2.f * S) / (0.6931471805599453f * wsum);
-
-    const long long row = (long long)b * K + k;
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
+
+    // The CTA keeps its pair's tables and walks over groups of kTrainWarps hypotheses: the per-CTA set-up above (three
+    // passes over the logits behind global-load latency and block barriers: 13 % of the instructions and a quarter of
+    // the stall samples when every CTA served one group) is paid once per CTA, not once per group.
+    for (int kg = blockIdx.x; kg * kTrainWarps < K; kg += gridDim.x) {
+    const int k = kg * kTrainWarps + warp;
+    const bool live = k < K;
+    const long long row = (long long)b * K + k;
+    if (kg != (int)blockIdx.x) {
+        if (n_chunks > 1) {          // the sweep left the LAST chunk's tables behind
+            __syncthreads();
+            build(0, false);
+            __syncthreads();
+        }
+        if (lane == 0) cand_n[warp] = 0;
+        __syncwarp();
+    }
     float top_v = -INFINITY, thr = -INFINITY, zacc = 0.f;
     int top_i = -1;
     // sweep 1: filtered, all chunks
@@ -490,8 +503,15 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
         __syncwarp();
         if (lane < S) top_i = win_i[warp][lane];
     }
-    // sweep 2 (rare): the hypotheses whose list came out short or overflowed, unfiltered
-    if (__syncthreads_or(redo ? 1 : 0)) {
+    // sweep 2 (rare): the hypotheses whose list came out short or overflowed, unfiltered.  With one chunk the tables
+    // are still in place and the warp redoes its sweep on its own: no block barrier, so the warps of a CTA walk over
+    // their groups independently (a barrier here makes every group as slow as its slowest warp).
+    if (n_chunks == 1) {
+        float zdummy = 0.f;
+        if (redo)
+            train_sweep<S, false>(wtab, winv, 0, ((N + 127) / 128) * 128, (uint32_t)k, (uint32_t)b, (uint32_t)offset, k0,
+                                  k1, x0, nullptr, nullptr, nullptr, zdummy, top_v, top_i, thr, lane);
+    } else if (__syncthreads_or(redo ? 1 : 0)) {
         for (int c = 0; c < n_chunks; ++c) {
             if (n_chunks > 1) {
                 __syncthreads();
@@ -506,7 +526,7 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
                                       lane);
         }
     }
-    if (!live) return;
+    if (!live) continue;             // (a warp without a hypothesis still takes part in the block barriers above)
     DRB_UNROLL
     for (int o = 16; o > 0; o >>= 1) zacc += __shfl_xor_sync(FULL, zacc, o);
     // Z = sum w / e = -(1 / ln 2) * zacc ;  lse = lmax + ln Z
@@ -527,6 +547,7 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
         for (int i = 1; i < 4; ++i) bits = ((top_i & 3) == i) ? rr[i] : bits;
         sel_key_out[(size_t)row * S + rank] = __ldg(logits_b + top_i) + gumbel_from_bits(bits);
     }
+    }   // hypothesis groups of this CTA
 }
 
 template <int S>
@@ -717,7 +738,12 @@ extern "C" int drb_sample(const float* logits, const float* noise, uint64_t seed
         // training forward with in-kernel noise at tau = 1
         const bool one_chunk = N <= train_chunk(8);
         const int tw = one_chunk ? 8 : 16;
-        const dim3 tgrid((K + tw - 1) / tw, B);
+        // One group of `tw` hypotheses per CTA.  (Measured on the B200, round 2: capping the grid at one wave of CTAs
+        // that walk over several groups with their tables built once is NOT faster -- 0.128 vs 0.124 ms at cfg5, 0.444
+        // vs 0.432 at cfg3: with ~7 waves of short CTAs the set-up of one CTA hides under the sweeps of its
+        // neighbours.  The kernel keeps the group loop; the launch does not use it.)
+        const int groups = (K + tw - 1) / tw;
+        const dim3 tgrid(groups, B);
 #define DRB_LAUNCH_TRAIN(S_)                                                                                      \
     case S_:                                                                                                      \
         if (one_chunk)                                                                                            \
