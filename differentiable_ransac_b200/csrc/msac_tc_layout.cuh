@@ -168,13 +168,47 @@ DRB_HD void model_rows(const float* m, bool present, bool pair, float* cr, float
     }
 }
 
-// One operand row: the three K blocks of 16 (v = 15 values), A side [hi | lo | hi], B side [hi | hi | lo].
-// `row48` receives the 48 floats in K order.
-DRB_HD void operand_row(const float* v, bool a_side, float* row48) {
+// "Folded" pair variant (words + 128): the threshold moves into the denominator rows, j' = -(1.5 thr)^2 j < 0, so that
+// the soft inlier term of a pair of neighbouring models becomes
+//     max(0, 1 - r0^2 / (j0 T)) = 1 + t max(r0^2 j1', -p),   p = j0' j1' > 0,  t = 1 / p
+// -- per two pairs FMUL2, FMUL, MUFU.RCP, FMUL2, 2 FMNMX (ALU pipe), 2 FFMA that accumulate: 7 FMA-pipe cycles
+// instead of 10, no separate clamp and no separate add.  The sixteenth K slot (zero in the other variants) flags the
+// rows that must not count (past N, or a correspondence that is not finite): their features are (0, ..., 0, 1) and
+// every model carries (1e18, -1) there, so such a row gives r = 1e18, j' = -1, p = 1, t = 1, max(-1e36, -1) = -1:
+// exactly -1, which cancels the "1 +" that the epilogue adds once per thread and tile at the end of a unit -- no
+// mask in the inner loop.  Absent / non-finite / all-zero models become r = 0 | 1e18, j' = -1 (the sign matters: p
+// must stay positive).
+DRB_HD void model_rows_folded(const float* m, bool present, float jscale, float* cr, float* cj, float& cr15, float& cj15) {
+    bool finite = true;
+    DRB_UNROLL
+    for (int q = 0; q < 9; ++q) finite = finite && (t_abs(m[q]) <= 3.0e38f);   // false for NaN and Inf
+    cr15 = 1.0e18f;
+    cj15 = -1.f;
+    if (present && finite) {
+        coefficients(m, cr, cj);
+        float mass = 0.f;
+        DRB_UNROLL
+        for (int i = 0; i < kFeat; ++i) mass += t_abs(cj[i]);
+        if (mass > 0.f) {                     // j is not identically zero
+            DRB_UNROLL
+            for (int i = 0; i < kFeat; ++i) cj[i] *= jscale;
+            return;
+        }
+    }
+    DRB_UNROLL
+    for (int i = 0; i < kFeat; ++i) cr[i] = cj[i] = 0.f;
+    cj[kFeat - 1] = -1.f;
+    if (present) cr[kFeat - 1] = 1.0e18f;
+}
+
+// One operand row: the three K blocks of 16 (v = 15 values + v15, the sixteenth slot), A side [hi | lo | hi], B side
+// [hi | hi | lo].  `row48` receives the 48 floats in K order.
+DRB_HD void operand_row(const float* v, bool a_side, float* row48, float v15 = 0.f) {
     DRB_UNROLL
     for (int i = 0; i < kBlk; ++i) {
         float hi = 0.f, lo = 0.f;
         if (i < kFeat) tf32_split(v[i], hi, lo);
+        else hi = tf32_round(v15);             // 0, 1, -1 or 1e18: one TF32 word is enough
         row48[i] = hi;
         row48[kBlk + i] = a_side ? lo : hi;
         row48[2 * kBlk + i] = a_side ? hi : lo;
@@ -226,12 +260,13 @@ DRB_HD void bf16_split3(float x, uint16_t* w) {
     w[2] = bf16_rn(r2);
 }
 // the 48 32-bit words of one operand row (v = 15 values)
-DRB_HD void operand_row_bf16(const float* v, bool a_side, uint32_t* row48w) {
+DRB_HD void operand_row_bf16(const float* v, bool a_side, uint32_t* row48w, float v15 = 0.f) {
     uint16_t e[kK16];
     DRB_UNROLL
     for (int i = 0; i < kBlk; ++i) {
         uint16_t w[3] = {0, 0, 0};
         if (i < kFeat) bf16_split3(v[i], w);
+        else w[0] = bf16_rn(v15);              // 0, 1, -1 or 1e18: one BF16 word is enough
         // block order of the word index: A (0,0,0,1,1,2), B (0,1,2,0,1,0)
         e[0 * kBlk + i] = w[0];
         e[1 * kBlk + i] = a_side ? w[0] : w[1];
@@ -259,12 +294,12 @@ DRB_HD uint32_t instr_desc_mn(int m, int n, bool bf16) {
     return (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
 }
 // TF32 variant as 32-bit words, so both variants share the image writers
-DRB_HD void operand_row_words(const float* v, bool a_side, bool bf16, uint32_t* row48w) {
+DRB_HD void operand_row_words(const float* v, bool a_side, bool bf16, uint32_t* row48w, float v15 = 0.f) {
     if (bf16) {
-        operand_row_bf16(v, a_side, row48w);
+        operand_row_bf16(v, a_side, row48w, v15);
     } else {
         float row48[kK];
-        operand_row(v, a_side, row48);
+        operand_row(v, a_side, row48, v15);
         DRB_UNROLL
         for (int k = 0; k < kK; ++k) {
 #if defined(__CUDA_ARCH__)

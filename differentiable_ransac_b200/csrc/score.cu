@@ -349,7 +349,8 @@ extern "C" int drb_episym_forward(const float* pts, const int32_t* npts, const f
     if (B <= 0 || K <= 0 || P <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
     const int gx = (K + kScoreThreads - 1) / kScoreThreads;
     const int split = pick_split(gx * B, P);
-    if (split > 1) cudaMemsetAsync(row_sum, 0, sizeof(float) * (size_t)B * K, (cudaStream_t)stream);
+    // inactive (invalid) models keep a zero row sum: callers multiply by the validity flag, and 0 * garbage may be NaN
+    if (split > 1 || mvalid) cudaMemsetAsync(row_sum, 0, sizeof(float) * (size_t)B * K, (cudaStream_t)stream);
     episym_kernel<false><<<dim3(gx, B, split), kScoreThreads, 0, (cudaStream_t)stream>>>(pts, npts, models, mvalid,
                                                                                        nullptr, K, P, split, row_sum,
                                                                                        nullptr);

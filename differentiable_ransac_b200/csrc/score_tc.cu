@@ -43,6 +43,14 @@
 #include "tc_ptx.cuh"
 #include "tile_pipe.cuh"
 
+// Ablation switches for profiles/microbench/tc_ablate.py (bit 0: no MMAs are issued, bit 1: the epilogue skips its
+// arithmetic, bit 2: the epilogue skips tcgen05.ld, bit 3: a multiply stands in for MUFU.RCP, bit 4: the accumulator
+// is handed back right after the tile's last tcgen05.ld instead of after its arithmetic).  The product build is 0:
+// every switch is a compile-time constant and the kernel's SASS does not change.
+#ifndef DRB_TC_ABLATE
+#define DRB_TC_ABLATE 0
+#endif
+
 namespace drb {
 namespace tc {
 
@@ -71,17 +79,30 @@ static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
 // ---- launch 1: correspondences -> operand images ------------------------------------------------------
 // images[b][t] = the kABytes image of correspondences [128 t, 128 t + 128) of pair b; rows past N are zero
 // (the scorer's epilogue masks them).
-template <bool BF16>
+// PADFLAG (the folded variant, msac_tc_layout.cuh): a row past N -- or a correspondence that is not finite, which the
+// other variants turn into 0 through FFMA.SAT -- is (0, ..., 0, 1): the sixteenth slot makes every model answer
+// (r, j') = (1e18, -1), a term of exactly 0.
+template <bool BF16, bool PADFLAG>
 __global__ void __launch_bounds__(kTileM)
 msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, uint32_t* __restrict__ images) {
     const int b = blockIdx.y, t = blockIdx.x, row = threadIdx.x;
     const int n = t * kTileM + row;
     uint32_t row48[kK];
-    if (n < N) {
-        const float4 p = __ldg(reinterpret_cast<const float4*>(matches) + (size_t)b * N + n);
+    bool real = n < N;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (real) {
+        p = __ldg(reinterpret_cast<const float4*>(matches) + (size_t)b * N + n);
+        if (PADFLAG) real = fabsf(p.x) <= 1.0e18f && fabsf(p.y) <= 1.0e18f && fabsf(p.z) <= 1.0e18f && fabsf(p.w) <= 1.0e18f;
+    }
+    if (real) {
         float f[kFeat];
         features(p.x, p.y, p.z, p.w, f);
         operand_row_words(f, true, BF16, row48);
+    } else if (PADFLAG) {
+        float f[kFeat];
+        DRB_UNROLL
+        for (int k = 0; k < kFeat; ++k) f[k] = 0.f;
+        operand_row_words(f, true, BF16, row48, 1.f);
     } else {
         DRB_UNROLL
         for (int k = 0; k < kK; ++k) row48[k] = 0u;
@@ -94,7 +115,8 @@ msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, uin
 }
 
 // ---- launch 2 -----------------------------------------------------------------------------------------
-template <bool BF16, bool PAIR, int EPI>
+// PAIR: 0 one reciprocal per pair; 1 one per two neighbouring models; 2 the folded form of 1 (msac_tc_layout.cuh)
+template <bool BF16, int PAIR, int EPI>
 __global__ void __launch_bounds__(threads_of(EPI), 1)
 score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restrict__ models,
                      const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
@@ -172,7 +194,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                     const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
                     const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN);
                     DRB_UNROLL
-                    for (int k = 0; k < kKSteps; ++k) {
+                    for (int k = 0; k < ((DRB_TC_ABLATE & 1) ? 0 : kKSteps); ++k) {
                         if (BF16) mma_bf16(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
                         else mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
                     }
@@ -203,15 +225,20 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 float m[9];
                 DRB_UNROLL
                 for (int q = 0; q < 9; ++q) m[q] = mi < cnt ? __ldg(models + ((size_t)b * M + mi) * 9 + q) : 0.f;
-                float cr[kFeat], cj[kFeat];
+                float cr[kFeat], cj[kFeat], cr15 = 0.f, cj15 = 0.f;
                 uint32_t row48[kK];
-                model_rows(m, mi < cnt, PAIR, cr, cj);
-                operand_row_words(cr, false, BF16, row48);
+                if (PAIR == 2) {
+                    const float th = 1.5f * __ldg(thr + b);
+                    model_rows_folded(m, mi < cnt, -(th * th), cr, cj, cr15, cj15);
+                } else {
+                    model_rows(m, mi < cnt, PAIR != 0, cr, cj);
+                }
+                operand_row_words(cr, false, BF16, row48, cr15);
                 DRB_UNROLL
                 for (int c = 0; c < kK / 4; ++c)
                     *reinterpret_cast<uint4*>(img + image_index(column_r(i), 4 * c)) =
                         make_uint4(row48[4 * c], row48[4 * c + 1], row48[4 * c + 2], row48[4 * c + 3]);
-                operand_row_words(cj, false, BF16, row48);
+                operand_row_words(cj, false, BF16, row48, cj15);
                 DRB_UNROLL
                 for (int c = 0; c < kK / 4; ++c)
                     *reinterpret_cast<uint4*>(img + image_index(PAIR ? column_j_swapped(i) : column_j(i), 4 * c)) =
@@ -248,21 +275,46 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 __syncwarp();          // tcgen05.ld is .sync.aligned: the warp must be converged
                 tc_fence_after();
                 // a row past N contributes 0: max(0, min(1, u * nci + 0)) with u * nci <= 0 (or NaN -> 0)
-                const float one = (t * kTileM + quarter * 32 + lane < N) ? 1.f : 0.f;
+                const float one = (PAIR == 2 || t * kTileM + quarter * 32 + lane < N) ? 1.f : 0.f;   // (unused when PAIR == 2)
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(rd.idx * kTileN + half * kCols);
                 DRB_UNROLL
                 for (int c = 0; c < kChunks; ++c) {
                     uint32_t v[32];
-                    tmem_ld32(taddr + (uint32_t)(c * 32), v);
-                    tmem_ld_wait();
+                    if (DRB_TC_ABLATE & 4) {
+                        DRB_UNROLL
+                        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(1.f + (float)(t + i + lane));
+                    } else {
+                        tmem_ld32(taddr + (uint32_t)(c * 32), v);
+                        tmem_ld_wait();
+                    }
+                    if (c == kChunks - 1 && (DRB_TC_ABLATE & 16)) {
+                        // measured and not kept: handing the accumulator back here, before the arithmetic of the last
+                        // chunk, is 2 % slower (0.1096 vs 0.1075 ms, profiles/r2_tc_ablate.jsonl)
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
+                    }
+                    if (DRB_TC_ABLATE & 2) {
+                        acc[c * 8] = pk2_add(acc[c * 8], pk2_make(__uint_as_float(v[0]), __uint_as_float(v[31])));
+                        continue;
+                    }
                     DRB_UNROLL
                     for (int q = 0; q < 8; ++q) {
                         const pk2 R = pk2_make(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]));
                         const pk2 R2 = pk2_mul(R, R);
-                        if (PAIR) {
+                        if (PAIR == 2) {
+                            // columns (r0, r1, j1', j0'), j' = -T j: term = 1 + t max(r^2 j_other', -p), t = 1 / p, p = j0' j1'
+                            const float ja = __uint_as_float(v[4 * q + 2]), jb = __uint_as_float(v[4 * q + 3]);
+                            const float pp = ja * jb;
+                            const float tt = (DRB_TC_ABLATE & 8) ? pp * 0.37f : rcp_approx(pp);
+                            float w0, w1, a0, a1;
+                            pk2_split(pk2_mul(R2, pk2_make(ja, jb)), w0, w1);
+                            pk2_split(acc[c * 8 + q], a0, a1);
+                            acc[c * 8 + q] = pk2_make(fmaf(tt, fmaxf(w0, -pp), a0), fmaf(tt, fmaxf(w1, -pp), a1));
+                        } else if (PAIR) {
                             // columns (r0, r1, j1, j0): (1/j0, 1/j1) = rcp(j0 j1) (j1, j0) -- one reciprocal per two pairs
                             const float ja = __uint_as_float(v[4 * q + 2]), jb = __uint_as_float(v[4 * q + 3]);
-                            const float tn = rcp_approx(ja * jb) * nci;
+                            const float tn = ((DRB_TC_ABLATE & 8) ? (ja * jb) * 0.37f : rcp_approx(ja * jb)) * nci;
                             float w0, w1;
                             pk2_split(pk2_mul(R2, pk2_make(ja, jb)), w0, w1);
                             acc[c * 8 + q] = pk2_add(acc[c * 8 + q], pk2_make(fma_sat(w0, tn, one), fma_sat(w1, tn, one)));
@@ -274,15 +326,23 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                         }
                     }
                 }
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
+                if (!(DRB_TC_ABLATE & 16)) {
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
+                }
                 rd.advance(2);
             }
             // ---- sum over the 128 lanes: butterfly reduce-scatter inside the warp, then the four quarters -----
             float a[2 * kAcc];
             DRB_UNROLL
             for (int i = 0; i < kAcc; ++i) pk2_split(acc[i], a[2 * i], a[2 * i + 1]);
+            if (PAIR == 2) {
+                // the "1 +" of the row this thread met in every tile (a flagged row answered exactly -1)
+                const float rows = (float)tiles;
+                DRB_UNROLL
+                for (int i = 0; i < 2 * kAcc; ++i) a[i] += rows;
+            }
             DRB_UNROLL
             for (int w = kAcc, o = 16; o > 0; w >>= 1, o >>= 1) {
                 const bool up = (lane & o) != 0;
@@ -301,8 +361,9 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
             for (int i = 0; i < kPer; ++i) pp[quarter * kTileModels + half * (kCols / 2) + kPer * lane + i] = a[i];
             asm volatile("bar.sync 1, %0;" ::"n"(EPI * 32) : "memory");
             if (et < kTileModels) {
-                const float score = ((pp[0 * kTileModels + et] + pp[1 * kTileModels + et]) + pp[2 * kTileModels + et]) +
-                                    pp[3 * kTileModels + et];
+                float score = ((pp[0 * kTileModels + et] + pp[1 * kTileModels + et]) + pp[2 * kTileModels + et]) +
+                              pp[3 * kTileModels + et];
+                if (PAIR == 2) score = fmaxf(score, 0.f);    // -inf / NaN of a degenerate denominator (p underflows): 0
                 const int mi = mt * kTileModels + et;
                 const bool live = mi < cnt;
                 if (live && scores) scores[(size_t)b * M + mi] = score;
@@ -353,13 +414,13 @@ extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
 
 namespace drb {
 namespace tc {
-template <bool BF16, bool PAIR, int EPI>
+template <bool BF16, int PAIR, int EPI>
 static int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr,
                   int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
     static std::atomic<unsigned long long> configured{0};
     if (!ensure_dynamic_smem(score_msac_tc_kernel<BF16, PAIR, EPI>, kSmemBytes, configured)) return DRB_ERR_CUDA;
     const int tiles = (N + kTileM - 1) / kTileM;
-    msac_tc_features_kernel<BF16><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
+    msac_tc_features_kernel<BF16, PAIR == 2><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kTileModels - 1) / kTileModels);
     const int grid = (int)(max_units < tc_sm_count() ? max_units : tc_sm_count());
     score_msac_tc_kernel<BF16, PAIR, EPI><<<grid, threads_of(EPI), kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
@@ -381,15 +442,16 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair; + 32 = 16 epilogue warps instead
     // of 8; + 64 = the model-stationary arrangement of score_tc2.cu (the last three not yet measured on hardware)
     const int split = words & 15;
-    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0;
-    if ((split != 2 && split != 3) || (words & ~127)) return DRB_ERR_UNSUPPORTED;
+    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0, fold = (words & 128) != 0;
+    if ((split != 2 && split != 3) || (words & ~255) || (fold && (!pair || v2))) return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
     if (v2) return tc2::dispatch(split == 3, e16, pair, matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
 #define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
 #define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16>(DRB_TC_ARGS) : tc::launch<BF, PR, 8>(DRB_TC_ARGS))
-    if (pair) return split == 3 ? DRB_TC_PICK(true, true) : DRB_TC_PICK(false, true);
-    return split == 3 ? DRB_TC_PICK(true, false) : DRB_TC_PICK(false, false);
+    if (fold) return split == 3 ? DRB_TC_PICK(true, 2) : DRB_TC_PICK(false, 2);
+    if (pair) return split == 3 ? DRB_TC_PICK(true, 1) : DRB_TC_PICK(false, 1);
+    return split == 3 ? DRB_TC_PICK(true, 0) : DRB_TC_PICK(false, 0);
 #undef DRB_TC_PICK
 #undef DRB_TC_ARGS
 }

@@ -30,6 +30,10 @@
 #include "tc_ptx.cuh"
 #include "tile_pipe.cuh"
 
+#ifndef DRB_TC_ABLATE   // profiles/microbench/tc_ablate.py (see score_tc.cu): bit 0 no MMAs, bit 1 no epilogue arithmetic
+#define DRB_TC_ABLATE 0
+#endif
+
 namespace drb {
 namespace tc2 {
 using namespace drb::tc;
@@ -158,7 +162,7 @@ score_msac_tc2_kernel(const uint32_t* __restrict__ images, const float* __restri
                     const uint32_t d_r = tmem_base + (uint32_t)(kColD0 + rd.idx * kColDStride);
                     const uint32_t d_j = d_r + (uint32_t)kPts;
                     DRB_UNROLL
-                    for (int k = 0; k < kKSteps; ++k) {
+                    for (int k = 0; k < ((DRB_TC_ABLATE & 1) ? 0 : kKSteps); ++k) {
                         // a K step covers 8 columns of the model operand: 8 TF32 words, or 16 BF16 elements packed
                         // two per column with the even K index in the low half (the packing is this file's one
                         // assumption that neither CUTLASS's tmem_frg layout algebra nor the host model pins down;
@@ -263,7 +267,9 @@ score_msac_tc2_kernel(const uint32_t* __restrict__ images, const float* __restri
                 // past N has r = j = 0 and would take its neighbour with it (0 * inf), so when N is odd the last
                 // tile -- the only place where a real and an absent correspondence share a pair -- takes the plain path.
                 const bool paired = PAIR && !((N & 1) && t == tiles - 1);
-                if (paired) {
+                if (DRB_TC_ABLATE & 2) {
+                    acc[0] = pk2_add(acc[0], pk2_make(__uint_as_float(vr[0] ^ vr[kCols - 1]), __uint_as_float(vj[0] ^ vj[kCols - 1])));
+                } else if (paired) {
                     DRB_UNROLL
                     for (int i = 0; i < kCols / 2; ++i) {
                         const float j0 = __uint_as_float(vj[2 * i]), j1 = __uint_as_float(vj[2 * i + 1]);

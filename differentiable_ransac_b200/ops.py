@@ -356,7 +356,10 @@ def solve_rigid3_backward(points, idx, g_model, flag=True):
 _MSAC_KERNEL = os.environ.get("DRB_MSAC_KERNEL", "stream")
 # tensor-core scorer variants -> the `words` argument of drb_score_msac_tc: operand split (2 TF32 / 3 BF16 words),
 # "p" = one reciprocal per model pair (+16), "_e16" = 16 epilogue warps instead of 8 (+32)
-_TC_WORDS = {"tc": 3, "tc_bf16": 3, "tc_tf32": 2, "tc_bf16p": 3 + 16, "tc_tf32p": 2 + 16}
+# a trailing "p": one reciprocal per pair of neighbouring models (+16); "q": the same with the threshold folded into
+# the denominator rows and the clamp moved to the ALU pipe (+128, msac_tc_layout.cuh::model_rows_folded)
+_TC_WORDS = {"tc": 3, "tc_bf16": 3, "tc_tf32": 2, "tc_bf16p": 3 + 16, "tc_tf32p": 2 + 16, "tc_bf16q": 3 + 16 + 128,
+             "tc_tf32q": 2 + 16 + 128}
 _TC_WORDS.update({k + "_e16": v + 32 for k, v in list(_TC_WORDS.items()) if k != "tc"})
 # "tc2_*": the model-stationary arrangement (csrc/score_tc2.cu, +64)
 _TC_WORDS.update({"tc2_tf32": 2 + 64, "tc2_bf16": 3 + 64, "tc2_tf32_e16": 2 + 64 + 32, "tc2_bf16_e16": 3 + 64 + 32,

@@ -182,7 +182,11 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
  *  + 64  the model-stationary arrangement of score_tc2.cu: a unit's 128 models live in tensor memory as the A
  *        operand, only tiles of 80 correspondences pass through shared memory (a third of the operand traffic,
  *        one accumulator register per thread); with + 16 it pairs neighbouring correspondences
- * (+ 16 / + 32 / + 64 are built and host-checked, not yet measured on hardware.)  B <= 1024; matches 16-byte
+ *  + 128 (with + 16, not with + 64) the threshold folded into the denominator rows, j' = -(1.5 thr)^2 j, and the
+ *        term written 1 + t max(r^2 j_other', -p), p = j0' j1', t = 1 / p: the clamp runs on the ALU pipe and the
+ *        multiply-add accumulates, 7 FMA-pipe cycles per two pairs instead of 10; rows past N and correspondences
+ *        that are not finite are flagged in the sixteenth K slot and answer exactly -1 (msac_tc_layout.cuh)
+ * (every variant is pinned to the fp64 oracle on the B200, tests/test_gpu_score_tc.py.)  B <= 1024; matches 16-byte
  * aligned.  Needs a 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents
  * irrelevant on entry: the call writes the operand images of the correspondences there first).           */
 size_t drb_score_msac_tc_workspace_bytes(int B, int N);

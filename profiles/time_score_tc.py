@@ -24,16 +24,17 @@ flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)
 idx = ops.sample_sets(lg, K, 5, seed=7, offset=0)
 models, nsol, cm, cid, cc = ops.solve_e5(m, idx, compact=True)
 
+KERNS = tuple(sys.argv[2:]) or ("block", "stream", "tc_tf32", "tc_bf16", "tc_tf32p", "tc_bf16p", "tc_tf32q", "tc_bf16q", "tc_tf32_e16", "tc_tf32p_e16", "tc_bf16p_e16",
+             "tc2_tf32", "tc2_tf32_e16", "tc2_bf16", "tc2_tf32p", "tc2_tf32p_e16")
 s_ref, b_ref = ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=True, kernel="block")
-s_tc, b_tc = ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=True, kernel="tc")
+s_tc, b_tc = ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=True, kernel=KERNS[-1] if sys.argv[2:] else "tc")
 torch.cuda.synchronize()
 live = torch.arange(cm.shape[1], device=dev)[None] < cc[:, None]
 rel = ((s_tc - s_ref).abs() / s_ref.clamp_min(1.0))[live]
 print(json.dumps(dict(check="tc vs block", max_rel=float(rel.max()), same_best=int((b_tc == b_ref).sum()), pairs=B)),
       flush=True)
 
-for kern in ("block", "stream", "tc_tf32", "tc_bf16", "tc_tf32p", "tc_bf16p", "tc_tf32_e16", "tc_tf32p_e16", "tc_bf16p_e16",
-             "tc2_tf32", "tc2_tf32_e16", "tc2_bf16", "tc2_tf32p", "tc2_tf32p_e16") * 2:
+for kern in KERNS * 2:
     for _ in range(3):
         ops.score_msac(m, cm, thr, count=cc, ids=cid, want_scores=False, kernel=kern)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(20)]

@@ -349,7 +349,7 @@ static float desc_fetch(const std::vector<uint32_t>& smem, uint64_t desc, int ro
 int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, float thr, int words, float* scores,
                       int* lossless) {
     using namespace drb::tc;
-    const bool bf16 = (words & 15) == 3, pair = (words & 16) != 0;
+    const bool bf16 = (words & 15) == 3, pair = (words & 16) != 0, fold = (words & 128) != 0;
     const uint32_t idesc = bf16 ? instr_desc_bf16() : instr_desc();
     const int mmaN = (int)((idesc >> 17) & 0x3f) << 3, mmaM = (int)((idesc >> 24) & 0x1f) << 4;
     if (mmaN != kTileN || mmaM != kTileM) return -1;
@@ -365,13 +365,14 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
     for (int m0 = 0; m0 < M; m0 += kTileModels) {
         // the builder warps
         for (int i = 0; i < kTileModels; ++i) {
-            float m[9], cr[kFeat], cj[kFeat];
+            float m[9], cr[kFeat], cj[kFeat], cr15 = 0.f, cj15 = 0.f;
             uint32_t row48[kK];
             for (int q = 0; q < 9; ++q) m[q] = (m0 + i < M) ? models[(size_t)(m0 + i) * 9 + q] : 0.f;
-            model_rows(m, m0 + i < M, pair, cr, cj);
-            operand_row_words(cr, false, bf16, row48);
+            if (fold) model_rows_folded(m, m0 + i < M, -(th * th), cr, cj, cr15, cj15);
+            else model_rows(m, m0 + i < M, pair, cr, cj);
+            operand_row_words(cr, false, bf16, row48, cr15);
             for (int k = 0; k < kK; ++k) smem[b_addr / 4 + image_index(column_r(i), k)] = row48[k];
-            operand_row_words(cj, false, bf16, row48);
+            operand_row_words(cj, false, bf16, row48, cj15);
             for (int k = 0; k < kK; ++k)
                 smem[b_addr / 4 + image_index(pair ? column_j_swapped(i) : column_j(i), k)] = row48[k];
         }
@@ -381,10 +382,17 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
             for (int row = 0; row < kTileM; ++row) {
                 const int n = t * kTileM + row;
                 uint32_t row48[kK];
-                if (n < N) {
+                bool real = n < N;
+                if (real && fold)
+                    for (int q = 0; q < 4; ++q) real = real && std::fabs(matches[n * 4 + q]) <= 1.0e18f;
+                if (real) {
                     float f[kFeat];
                     features(matches[n * 4], matches[n * 4 + 1], matches[n * 4 + 2], matches[n * 4 + 3], f);
                     operand_row_words(f, true, bf16, row48);
+                } else if (fold) {
+                    float f[kFeat];
+                    for (int k = 0; k < kFeat; ++k) f[k] = 0.f;
+                    operand_row_words(f, true, bf16, row48, 1.f);
                 } else {
                     for (int k = 0; k < kK; ++k) row48[k] = 0u;
                 }
@@ -421,6 +429,13 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
                                 for (int h = 0; h < 2; ++h) {
                                     const float r = D[(size_t)row * kTileN + col + h];
                                     float v;
+                                    if (fold) {
+                                        // columns (r0, r1, j1', j0'): the term minus its "1 +", t max(r^2 j_other', -p)
+                                        const float pp = ja * jb, tt = 1.f / pp, w = (r * r) * (h ? jb : ja);
+                                        const float mx = (w != w) ? -pp : (w > -pp ? w : -pp);    // FMNMX: NaN loses
+                                        lane_sum[(size_t)row * kTileModels + half * 64 + 2 * (c * 8 + q) + h] += tt * mx;
+                                        continue;
+                                    }
                                     if (pair) {
                                         v = ((r * r) * (h ? jb : ja)) * tn + one;     // columns (r0, r1, j1, j0)
                                     } else {
@@ -436,8 +451,11 @@ int hc_msac_tc_scores(const float* matches, int N, const float* models, int M, f
         }
         for (int i = 0; i < kTileModels; ++i) {
             float q4[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int row = 0; row < kTileM; ++row) q4[row >> 5] += lane_sum[(size_t)row * kTileModels + i];
-            if (m0 + i < M) scores[m0 + i] = ((q4[0] + q4[1]) + q4[2]) + q4[3];
+            for (int row = 0; row < kTileM; ++row)
+                q4[row >> 5] += lane_sum[(size_t)row * kTileModels + i] + (fold ? (float)tiles : 0.f);
+            float sc = ((q4[0] + q4[1]) + q4[2]) + q4[3];
+            if (fold) sc = (sc != sc) ? 0.f : (sc < 0.f ? 0.f : sc);
+            if (m0 + i < M) scores[m0 + i] = sc;
         }
     }
     return 0;

@@ -119,3 +119,20 @@ def test_fused_entries_equal_their_parts():
     gg0 = ops.rigid_residual_backward(rp, rm, g_res)
     r1, gg1 = ops.rigid_residual_forward_backward(rp, rm, g_res)
     assert torch.allclose(r0, r1, rtol=1e-5) and torch.allclose(gg0, gg1, rtol=1e-6, atol=1e-9)
+
+
+def test_episym_forward_zeroes_the_rows_of_invalid_models():
+    """Regression: with a validity mask and one split the rows of invalid models were left as allocated
+    (torch.empty), so `row * valid` in engine.match_loss could be 0 * NaN."""
+    from differentiable_ransac_b200 import ops
+    B, K, P = 2, 96, 300
+    g = torch.Generator().manual_seed(5)
+    pts = (torch.rand(B, P, 4, generator=g) - 0.5).to(DEV)
+    models = torch.randn(B, K, 3, 3, generator=g).to(DEV)
+    valid = (torch.rand(B, K, generator=g) < 0.5).to(DEV)
+    for _ in range(4):
+        poison = torch.full((B, K), float("nan"), device=DEV)    # the block the next torch.empty(B, K) gets
+        del poison
+        row = ops.episym_forward(pts, models, None, valid)
+        assert torch.isfinite(row).all()
+        assert (row[~valid] == 0).all() and (row[valid] > 0).all()

@@ -251,7 +251,7 @@ def _tc_scores(lib, matches, models, thr, words=2):
     return torch.from_numpy(out)
 
 
-@pytest.mark.parametrize("words", [2, 3, 2 + 16, 3 + 16])
+@pytest.mark.parametrize("words", [2, 3, 2 + 16, 3 + 16, 2 + 16 + 128, 3 + 16 + 128])
 @pytest.mark.parametrize("N,K", [(2000, 40), (333, 30), (128, 20)])
 def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K, words):
     """The 3xTF32 contraction over 15 monomials, built and decoded exactly as score_tc.cu does it (images ->
@@ -279,7 +279,7 @@ def test_msac_tc_operands_reproduce_the_oracle_scores(lib, N, K, words):
     assert (got - fp32).abs().max() / fp32.max() < 1e-4
 
 
-@pytest.mark.parametrize("words", [2, 3, 2 + 16, 3 + 16])
+@pytest.mark.parametrize("words", [2, 3, 2 + 16, 3 + 16, 2 + 16 + 128, 3 + 16 + 128])
 def test_msac_tc_nan_models_score_zero(lib, words):
     from differentiable_ransac_b200 import synth
 
