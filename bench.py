@@ -77,7 +77,7 @@ def tensor_side(n_models, n_points, kernel_ms, scorer):
     one per two in the pair-reciprocal variants, against 16 results per SM per clock.  Never raises."""
     try:
         bf16 = "bf16" in scorer or scorer == "tc"
-        pair = scorer.replace("_e16", "").endswith("p")
+        pair = scorer.replace("_e16", "").replace("_s", "").endswith(("p", "q"))
         tiles = -(-n_points // 128) * -(-n_models // 128)            # lower bound: per-pair tails add a little
         flop = tiles * 6 * 2.0 * 128 * 256 * (16 if bf16 else 8)
         try:
@@ -100,13 +100,16 @@ def tensor_side(n_models, n_points, kernel_ms, scorer):
         return dict(tensor_note=f"unavailable: {e}")
 
 
-def load_traffic(kernel):
+def load_traffic(kernel, warm=False):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full captures
-    (profiles/r2_traffic.json, else round 1's)."""
+    (profiles/r2_traffic.json, else round 1's).  Default: ncu's own cache control (L2 flushed before the kernel);
+    warm=True: the capture with --cache-control none, when one exists."""
     for name in ("r2_traffic.json", "r1_traffic.json"):
         try:
             with open(os.path.join(ROOT, "profiles", name)) as f:
                 t = json.load(f)[kernel]
+            if warm:
+                return int(t["dram_bytes_read_warm_l2"]) + int(t["dram_bytes_write_warm_l2"])
             return int(t["dram_bytes_read"]) + int(t["dram_bytes_write"])
         except Exception:
             continue
@@ -719,6 +722,10 @@ def run_ours(args):
         gpu_launches=launches_per_step * args.steps,
         roofline=dict(bound="hbm", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                       traffic=load_traffic(msac_name if not is_tc else f"score_msac_tc_kernel<{msac_kernel}>"),
+                      traffic_warm_l2=load_traffic(f"score_msac_tc_kernel<{msac_kernel}>", warm=True) if is_tc else None,
+                      traffic_note="`traffic` is ncu's cold-L2 figure (it flushes the L2 before the kernel: the operand "
+                                   "images and models the previous launches of the step left in L2 come back from HBM); "
+                                   "`traffic_warm_l2` is the same launch captured with --cache-control none",
                       kernel=msac_name, kernel_ms=score_ms, algorithmic_bytes=score_bytes,
                       peak_source=peak_src, models_scored=n_valid,
                       note=("FP32-issue bound, not HBM bound (SURVEY H8)" if not is_tc else

@@ -54,27 +54,33 @@
 namespace drb {
 namespace tc {
 
-constexpr int kStagesA = 4;
 constexpr int kWarpProducer = 0;
 constexpr int kWarpMma = 1;
 constexpr int kWarpBuild0 = 2;       // warps 2, 3
 constexpr int kBuildThreads = 64;
-constexpr int kWarpEpi0 = 4;         // epilogue warps 4 .. 4 + EPI - 1 (EPI = 8, or 16: not yet measured)
+constexpr int kWarpEpi0 = 4;         // epilogue warps 4 .. 4 + EPI - 1 (EPI = 8 or 16)
 constexpr int threads_of(int epi_warps) { return (kWarpEpi0 + epi_warps) * 32; }
 constexpr int kTmemCols = 512;       // two accumulators of kTileN columns
 constexpr int kMaxPairs = 1024;
 
-// dynamic shared memory carve-up (bytes)
-constexpr int kOffA = 0;
-constexpr int kOffB = kOffA + kStagesA * kABytes;            //  98304
-constexpr int kOffBars = kOffB + 2 * kBBytes;                // 196608
-constexpr int kNumBars = 2 * kStagesA + 2 + 2 + 2 + 2;        // a_full/a_empty, d_full, d_empty, b_full, b_empty
-constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
-constexpr int kOffPrefix = kOffTmemPtr + 16;
-constexpr int kOffPart = kOffPrefix + (kMaxPairs + 1) * 4 + 12;
-constexpr int kSmemBytes = kOffPart + 2 * 4 * kTileModels * 4;   // part[unit parity][lane quarter][model of the tile]
-static_assert(kOffPart % 16 == 0, "alignment");
-static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+// dynamic shared memory carve-up (bytes) for STAGES correspondence stages
+template <int STAGES>
+struct Carve {
+    static constexpr int kOffA = 0;
+    static constexpr int kOffB = kOffA + STAGES * kABytes;            //  98304 with four stages
+    static constexpr int kOffBars = kOffB + 2 * kBBytes;              // 196608
+    static constexpr int kNumBars = 2 * STAGES + 2 + 2 + 2 + 2;       // a_full/a_empty, d_full, d_empty, b_full, b_empty
+    static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
+    static constexpr int kOffPrefix = kOffTmemPtr + 16;
+    static constexpr int kOffPart = kOffPrefix + (kMaxPairs + 1) * 4 + 12;
+    static constexpr int kSmemBytes = kOffPart + 2 * 4 * kTileModels * 4;   // part[unit parity][lane quarter][model of the tile]
+    static_assert(kOffPart % 16 == 0, "alignment");
+    static_assert(kSmemBytes <= 227 * 1024, "shared memory budget");
+};
+// The "slim" build (words + 256): 128 registers per thread instead of 168 and three correspondence stages instead of
+// four, so that a CTA leaves 16 K registers and ~50 KB of shared memory of its SM free -- room for one five-point CTA
+// (160 threads x 96 registers, 43 KB) of the NEXT batch on another stream while this one is being scored.
+constexpr int stages_of(bool slim) { return slim ? 3 : 4; }
 
 // ---- launch 1: correspondences -> operand images ------------------------------------------------------
 // images[b][t] = the kABytes image of correspondences [128 t, 128 t + 128) of pair b; rows past N are zero
@@ -116,23 +122,26 @@ msac_tc_features_kernel(const float* __restrict__ matches, int N, int tiles, uin
 
 // ---- launch 2 -----------------------------------------------------------------------------------------
 // PAIR: 0 one reciprocal per pair; 1 one per two neighbouring models; 2 the folded form of 1 (msac_tc_layout.cuh)
-template <bool BF16, int PAIR, int EPI>
-__global__ void __launch_bounds__(threads_of(EPI), 1)
+template <bool BF16, int PAIR, int EPI, bool SLIM>
+__global__ void __launch_bounds__(SLIM ? 512 : threads_of(EPI), 1)
 score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restrict__ models,
                      const int32_t* __restrict__ count, const int32_t* __restrict__ ids, const float* __restrict__ thr,
                      int B, int M, int N, int tiles, float* __restrict__ scores,
                      unsigned long long* __restrict__ best_packed) {
+    constexpr int kStagesA = stages_of(SLIM);
+    using C = Carve<kStagesA>;
+    constexpr int kOffA = C::kOffA, kOffB = C::kOffB;
     extern __shared__ __align__(1024) uint8_t smem[];
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kOffBars);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + kStagesA;
     uint64_t* d_full = bars + 2 * kStagesA;
     uint64_t* d_empty = d_full + 2;
     uint64_t* b_full = d_empty + 2;
     uint64_t* b_empty = b_full + 2;
-    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + kOffTmemPtr);
-    int* prefix = reinterpret_cast<int*>(smem + kOffPrefix);
-    float* part = reinterpret_cast<float*>(smem + kOffPart);
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kOffTmemPtr);
+    int* prefix = reinterpret_cast<int*>(smem + C::kOffPrefix);
+    float* part = reinterpret_cast<float*>(smem + C::kOffPart);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -414,16 +423,17 @@ extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
 
 namespace drb {
 namespace tc {
-template <bool BF16, int PAIR, int EPI>
+template <bool BF16, int PAIR, int EPI, bool SLIM>
 static int launch(const float* matches, const float* models, const int32_t* count, const int32_t* ids, const float* thr,
                   int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images, cudaStream_t s) {
     static std::atomic<unsigned long long> configured{0};
-    if (!ensure_dynamic_smem(score_msac_tc_kernel<BF16, PAIR, EPI>, kSmemBytes, configured)) return DRB_ERR_CUDA;
+    constexpr int kSmemBytes = Carve<stages_of(SLIM)>::kSmemBytes;
+    if (!ensure_dynamic_smem(score_msac_tc_kernel<BF16, PAIR, EPI, SLIM>, kSmemBytes, configured)) return DRB_ERR_CUDA;
     const int tiles = (N + kTileM - 1) / kTileM;
     msac_tc_features_kernel<BF16, PAIR == 2><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
     const long long max_units = (long long)B * ((M + kTileModels - 1) / kTileModels);
     const int grid = (int)(max_units < tc_sm_count() ? max_units : tc_sm_count());
-    score_msac_tc_kernel<BF16, PAIR, EPI><<<grid, threads_of(EPI), kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
+    score_msac_tc_kernel<BF16, PAIR, EPI, SLIM><<<grid, threads_of(EPI), kSmemBytes, s>>>(images, models, count, ids, thr, B, M, N, tiles, scores,
                                                                   best_packed);
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
@@ -442,13 +452,16 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair; + 32 = 16 epilogue warps instead
     // of 8; + 64 = the model-stationary arrangement of score_tc2.cu (the last three not yet measured on hardware)
     const int split = words & 15;
-    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0, fold = (words & 128) != 0;
-    if ((split != 2 && split != 3) || (words & ~255) || (fold && (!pair || v2))) return DRB_ERR_UNSUPPORTED;
+    const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0, fold = (words & 128) != 0,
+               slim = (words & 256) != 0;
+    if ((split != 2 && split != 3) || (words & ~511) || (fold && (!pair || v2)) || (slim && (!pair || fold || e16 || v2)))
+        return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
     if (v2) return tc2::dispatch(split == 3, e16, pair, matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
 #define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
-#define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16>(DRB_TC_ARGS) : tc::launch<BF, PR, 8>(DRB_TC_ARGS))
+#define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16, false>(DRB_TC_ARGS) : tc::launch<BF, PR, 8, false>(DRB_TC_ARGS))
+    if (slim) return split == 3 ? tc::launch<true, 1, 8, true>(DRB_TC_ARGS) : tc::launch<false, 1, 8, true>(DRB_TC_ARGS);
     if (fold) return split == 3 ? DRB_TC_PICK(true, 2) : DRB_TC_PICK(false, 2);
     if (pair) return split == 3 ? DRB_TC_PICK(true, 1) : DRB_TC_PICK(false, 1);
     return split == 3 ? DRB_TC_PICK(true, 0) : DRB_TC_PICK(false, 0);

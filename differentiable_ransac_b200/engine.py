@@ -29,6 +29,8 @@ from . import ops
 #   "tc_bf16"  three BF16 words per operand: exact operands, fp32-level scores (5e-6 against fp64 on the host model),
 #              same time
 #   "tc_bf16p" the same with ONE reciprocal per pair of neighbouring models (halves the SFU work)
+#   "tc_bf16p_s" tc_bf16p built slim (128 registers, three stages): 3 % slower alone, but it leaves room on every SM for a
+#              five-point CTA of the next batch -- the pipelined step is 2.6 % faster (0.1395 vs 0.1432 ms at cfg2)
 #   "block"    FP32, one CTA per 32 models; bit-identical to what `ransac_e5_test(scorer="block")` returns
 #   "stream"   FP32 work queue
 SERVICE_SCORER = os.environ.get("DRB_SERVICE_SCORER", "auto")
@@ -73,7 +75,7 @@ def tc_scorer_agrees(device, scorer="tc_tf32", tol=5e-4):
 
 def service_scorer(device, B, requested=None):
     """The scorer a pipelined service uses: `requested` (or SERVICE_SCORER) if it names one; "auto" -> the first of
-    "tc_bf16p", "tc_bf16", "tc_tf32" that agrees with the FP32 kernel on this device (tc_scorer_agrees), else "block".  A
+    "tc_bf16p_s", "tc_bf16p", "tc_bf16", "tc_tf32" that agrees with the FP32 kernel on this device (tc_scorer_agrees), else "block".  A
     tensor-core scorer named by SERVICE_SCORER is checked the same way and replaced by "block" (with a warning) if
     it fails; one passed explicitly by the caller is taken as is.  drb_score_msac_tc takes at most 1024 pairs."""
     if requested is not None:
@@ -83,7 +85,7 @@ def service_scorer(device, B, requested=None):
         return name
     if int(B) > 1024:
         return "block"
-    for cand in (("tc_bf16p", "tc_bf16", "tc_tf32") if name == "auto" else (name,)):
+    for cand in (("tc_bf16p_s", "tc_bf16p", "tc_bf16", "tc_tf32") if name == "auto" else (name,)):
         if tc_scorer_agrees(device, cand):
             return cand
     import warnings

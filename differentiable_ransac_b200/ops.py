@@ -361,6 +361,8 @@ _MSAC_KERNEL = os.environ.get("DRB_MSAC_KERNEL", "stream")
 _TC_WORDS = {"tc": 3, "tc_bf16": 3, "tc_tf32": 2, "tc_bf16p": 3 + 16, "tc_tf32p": 2 + 16, "tc_bf16q": 3 + 16 + 128,
              "tc_tf32q": 2 + 16 + 128}
 _TC_WORDS.update({k + "_e16": v + 32 for k, v in list(_TC_WORDS.items()) if k != "tc"})
+# "*_s": the slim build of the pair variant (+256: 128 registers, three stages; leaves room for a five-point CTA on the SM)
+_TC_WORDS.update({"tc_bf16p_s": 3 + 16 + 256, "tc_tf32p_s": 2 + 16 + 256})
 # "tc2_*": the model-stationary arrangement (csrc/score_tc2.cu, +64)
 _TC_WORDS.update({"tc2_tf32": 2 + 64, "tc2_bf16": 3 + 64, "tc2_tf32_e16": 2 + 64 + 32, "tc2_bf16_e16": 3 + 64 + 32,
                   "tc2_tf32p": 2 + 64 + 16, "tc2_bf16p": 3 + 64 + 16, "tc2_tf32p_e16": 2 + 64 + 16 + 32,

@@ -186,6 +186,8 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
  *        term written 1 + t max(r^2 j_other', -p), p = j0' j1', t = 1 / p: the clamp runs on the ALU pipe and the
  *        multiply-add accumulates, 7 FMA-pipe cycles per two pairs instead of 10; rows past N and correspondences
  *        that are not finite are flagged in the sixteenth K slot and answer exactly -1 (msac_tc_layout.cuh)
+ *  + 256 (with + 16 alone) the slim build: 128 registers per thread and three correspondence stages, which leaves 16 K
+ *        registers and ~50 KB of shared memory of every SM to a five-point CTA of the next batch on another stream
  * (every variant is pinned to the fp64 oracle on the B200, tests/test_gpu_score_tc.py.)  B <= 1024; matches 16-byte
  * aligned.  Needs a 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents
  * irrelevant on entry: the call writes the operand images of the correspondences there first).           */

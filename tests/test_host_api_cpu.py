@@ -99,8 +99,9 @@ def test_service_scorer_selection_logic(monkeypatch):
         return types.SimpleNamespace(score_msac=score_msac)
 
     monkeypatch.setattr(engine, "SERVICE_SCORER", "auto")
-    for bad, want in ((set(), "tc_bf16p"), ({"tc_bf16p"}, "tc_bf16"), ({"tc_bf16p", "tc_bf16"}, "tc_tf32"),
-                      ({"tc_bf16p", "tc_bf16", "tc_tf32"}, "block")):
+    for bad, want in ((set(), "tc_bf16p_s"), ({"tc_bf16p_s"}, "tc_bf16p"), ({"tc_bf16p_s", "tc_bf16p"}, "tc_bf16"),
+                      ({"tc_bf16p_s", "tc_bf16p", "tc_bf16"}, "tc_tf32"),
+                      ({"tc_bf16p_s", "tc_bf16p", "tc_bf16", "tc_tf32"}, "block")):
         monkeypatch.setattr(engine, "ops", stand_in(bad))
         monkeypatch.setattr(engine, "_TC_CHECKED", {})
         with warnings.catch_warnings(record=True) as caught:
