@@ -180,6 +180,10 @@ class StartGate:
 
     def __init__(self):
         self.ok = os.environ.get("DRB_BENCH_GATE", "1") != "0"
+        # under a profiler that serialises kernels (ncu waits for each launch to finish inside the launch call) a
+        # closed gate is a deadlock: the host cannot reach open()
+        if any(k.startswith(("NV_COMPUTE_PROFILER", "CUDA_INJECTION", "NV_NSIGHT")) for k in os.environ):
+            self.ok = False
         try:
             from cuda.bindings import driver as cu
 
