@@ -329,7 +329,8 @@ sample_sets_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t off
 // the backward (which regenerates it) and the exact kernel agree with it to rounding.
 //
 // Top-s without a running top-s: P(t_n > x) = 1 - 2^(x w_n) ~ -x w_n ln 2, so the number of elements above
-// x0 = -2s / (W ln 2), W = sum_n w_n, is Poisson with mean ~2s.  The sweep only APPENDS those few to a
+// x0 = -3s / (W ln 2), W = sum_n w_n, is Poisson with mean ~3s (fewer than s -- a second sweep -- with probability
+// 0.6 % at s = 3, 0.09 % at s = 5; the mean was 2s until round 2: 6.2 % / 2.9 %).  The sweep only APPENDS those few to a
 // per-hypothesis list in shared memory; the s largest of the list are ranked after the sweep.  Fewer than s
 // (or more than the list holds) sends the hypothesis through a second, unfiltered sweep with the warp-shared
 // running top-s (a few percent of the hypotheses for reference-like weights; every one in the worst case).
@@ -450,7 +451,7 @@ sample_train_kernel(const float* __restrict__ logits, uint64_t seed, uint64_t of
     wsum = red[0];
     DRB_UNROLL
     for (int w = 1; w < kTrainWarps; ++w) wsum += red[w];
-    const float x0 = -(2.f * S) / (0.6931471805599453f * wsum);
+    const float x0 = -(3.f * S) / (0.6931471805599453f * wsum);
     const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(offset >> 32);
 
     // The CTA keeps its pair's tables and walks over groups of kTrainWarps hypotheses: the per-CTA set-up above (three

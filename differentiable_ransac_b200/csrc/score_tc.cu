@@ -45,7 +45,8 @@
 
 // Ablation switches for profiles/microbench/tc_ablate.py (bit 0: no MMAs are issued, bit 1: the epilogue skips its
 // arithmetic, bit 2: the epilogue skips tcgen05.ld, bit 3: a multiply stands in for MUFU.RCP, bit 4: the accumulator
-// is handed back right after the tile's last tcgen05.ld instead of after its arithmetic).  The product build is 0:
+// is handed back right after the tile's last tcgen05.ld instead of after its arithmetic, bit 5 / bit 6: four / three of
+// the six K steps are issued -- what fewer tensor flops would buy).  The product build is 0:
 // every switch is a compile-time constant and the kernel's SASS does not change.
 #ifndef DRB_TC_ABLATE
 #define DRB_TC_ABLATE 0
@@ -203,7 +204,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                     const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
                     const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN);
                     DRB_UNROLL
-                    for (int k = 0; k < ((DRB_TC_ABLATE & 1) ? 0 : kKSteps); ++k) {
+                    for (int k = 0; k < ((DRB_TC_ABLATE & 1) ? 0 : (DRB_TC_ABLATE & 32) ? 4 : (DRB_TC_ABLATE & 64) ? 3 : kKSteps); ++k) {
                         if (BF16) mma_bf16(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
                         else mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
                     }
