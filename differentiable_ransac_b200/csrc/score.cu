@@ -10,6 +10,8 @@
 // warp-wide broadcast, and nothing of size M x N ever exists.
 #include <cuda_runtime.h>
 
+#include <cstdlib>
+
 #include "../../include/drb.h"
 #include "drb_common.cuh"
 #include "f32x2.cuh"
@@ -304,6 +306,105 @@ rigid_residual_kernel(const float* __restrict__ points, const float* __restrict_
     }
 }
 
+
+// ---- rigid residual from the points' second moments -------------------------------------------------------------
+// sum_n ||q_n - (R p_n + t)||^2 and its gradient in (R, t) are quadratic forms in the model whose coefficients are
+// sums over the points ALONE:
+//     S_pp = sum p p',  S_qp = sum q p',  s_p = sum p,  s_q = sum q,  s_qq = sum |q|^2          (22 numbers)
+//     sum d_i p_j = S_qp[i][j] - R_i . S_pp[:, j] - t_i s_p[j],      sum d_i = s_q[i] - R_i . s_p - N t_i
+//     sum |d|^2   = s_qq - 2 sum_i (R_i . S_qp[i] + t_i s_q[i]) + sum_i (R_i S_pp R_i' + 2 t_i R_i . s_p + N t_i^2)
+// so a pair costs O(N + K) instead of the O(N K) of rigid_residual_kernel (cfg4, N = 50 000, K = 1 000: 1.05 ms ->
+// tens of microseconds).  The moments are accumulated in fp64 from exact products of the fp32 coordinates (the sums
+// cancel for a model that fits: 5e4 points of |q|^2 ~ 3 against a residual sum of ~15) and every CTA recomputes its
+// pair's 22 moments -- 1.2 MB from L2 at cfg4 -- rather than taking a workspace through the ABI.  Same results as the
+// per-point kernel to fp32 rounding (closer to the reference run in fp64); the per-point kernel stays for callers
+// that want the inlier counts, which are not a function of the moments.
+constexpr int kMomThreads = 256;
+constexpr int kMoments = 22;
+
+template <bool BWD>
+__global__ void __launch_bounds__(kMomThreads)
+rigid_residual_moments_kernel(const float* __restrict__ points, const float* __restrict__ models,
+                              const float* __restrict__ g_res, int K, int N, float* __restrict__ g_models,
+                              float* __restrict__ res_out) {
+    __shared__ double red[kMomThreads / 32][kMoments];
+    __shared__ double mom[kMoments];
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double s[kMoments];
+    DRB_UNROLL
+    for (int i = 0; i < kMoments; ++i) s[i] = 0.0;
+    const float2* src = reinterpret_cast<const float2*>(points + (size_t)b * N * 6);
+    for (int n = threadIdx.x; n < N; n += kMomThreads) {
+        const float2 a = __ldg(src + 3 * n), c = __ldg(src + 3 * n + 1), e = __ldg(src + 3 * n + 2);
+        const double p[3] = {(double)a.x, (double)a.y, (double)c.x}, q[3] = {(double)c.y, (double)e.x, (double)e.y};
+        // S_pp (xx, xy, xz, yy, yz, zz) | S_qp row-major | s_p | s_q | s_qq
+        s[0] = fma(p[0], p[0], s[0]); s[1] = fma(p[0], p[1], s[1]); s[2] = fma(p[0], p[2], s[2]);
+        s[3] = fma(p[1], p[1], s[3]); s[4] = fma(p[1], p[2], s[4]); s[5] = fma(p[2], p[2], s[5]);
+        DRB_UNROLL
+        for (int i = 0; i < 3; ++i) {
+            DRB_UNROLL
+            for (int j = 0; j < 3; ++j) s[6 + 3 * i + j] = fma(q[i], p[j], s[6 + 3 * i + j]);
+            s[15 + i] += p[i];
+            s[18 + i] += q[i];
+            s[21] = fma(q[i], q[i], s[21]);
+        }
+    }
+    DRB_UNROLL
+    for (int i = 0; i < kMoments; ++i) {
+        DRB_UNROLL
+        for (int o = 16; o > 0; o >>= 1) s[i] += __shfl_xor_sync(0xffffffffu, s[i], o);
+    }
+    if (lane == 0) {
+        DRB_UNROLL
+        for (int i = 0; i < kMoments; ++i) red[warp][i] = s[i];
+    }
+    __syncthreads();
+    if (threadIdx.x < kMoments) {
+        double t = 0.0;
+        DRB_UNROLL
+        for (int w = 0; w < kMomThreads / 32; ++w) t += red[w][threadIdx.x];
+        mom[threadIdx.x] = t;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * kMomThreads + threadIdx.x;
+    if (k >= K) return;
+    const float* mp = models + ((size_t)b * K + k) * 16;
+    const double Spp[3][3] = {{mom[0], mom[1], mom[2]}, {mom[1], mom[3], mom[4]}, {mom[2], mom[4], mom[5]}};
+    const double nd = (double)N;
+    double res = mom[21];
+    double g[12];
+    DRB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const double r[3] = {(double)__ldg(mp + 4 * i), (double)__ldg(mp + 4 * i + 1), (double)__ldg(mp + 4 * i + 2)};
+        const double t = (double)__ldg(mp + 4 * i + 3);
+        double rS[3];                    // R_i . S_pp[:, j]
+        DRB_UNROLL
+        for (int j = 0; j < 3; ++j) rS[j] = r[0] * Spp[0][j] + r[1] * Spp[1][j] + r[2] * Spp[2][j];
+        const double r_sp = r[0] * mom[15] + r[1] * mom[16] + r[2] * mom[17];
+        const double r_sqp = r[0] * mom[6 + 3 * i] + r[1] * mom[7 + 3 * i] + r[2] * mom[8 + 3 * i];
+        res += -2.0 * (r_sqp + t * mom[18 + i]) + (rS[0] * r[0] + rS[1] * r[1] + rS[2] * r[2]) + 2.0 * t * r_sp + nd * t * t;
+        DRB_UNROLL
+        for (int j = 0; j < 3; ++j) g[4 * i + j] = -(mom[6 + 3 * i + j] - rS[j] - t * mom[15 + j]);   // -sum d_i p_j
+        g[4 * i + 3] = -(mom[18 + i] - r_sp - nd * t);                                                  // -sum d_i
+    }
+    if (res_out) res_out[(size_t)b * K + k] = (float)res;
+    if (BWD) {
+        const double gr = 2.0 * (double)__ldg(g_res + (size_t)b * K + k);
+        DRB_UNROLL
+        for (int i = 0; i < 12; ++i) g_models[((size_t)b * K + k) * 16 + i] = (float)(g[i] * gr);
+    }
+}
+
+// measurement switch: DRB_RIGID_RESIDUAL=points keeps the O(N K) kernel for the calls that do not need it
+static bool rigid_by_moments() {
+    static const bool on = []() {
+        const char* e = getenv("DRB_RIGID_RESIDUAL");
+        return !(e != nullptr && e[0] == 'p');
+    }();
+    return on;
+}
+
 static int pick_split(int ctas, int n_items) {
     // enough CTAs to cover 148 SMs a few times over, but never slices thinner than a tile
     int split = (148 * 4 + ctas - 1) / ctas;
@@ -388,6 +489,11 @@ extern "C" int drb_rigid_residual_forward(const float* points, const float* mode
                                           float threshold, float* res_sum, int32_t* ninl, void* stream) {
     if (!points || !models || !res_sum) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || N <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
+    if (!ninl && rigid_by_moments()) {
+        rigid_residual_moments_kernel<false><<<dim3((K + kMomThreads - 1) / kMomThreads, B), kMomThreads, 0,
+                                               (cudaStream_t)stream>>>(points, models, nullptr, K, N, nullptr, res_sum);
+        DRB_CHECK_LAUNCH();
+    }
     const int gx = (K + kScoreThreads - 1) / kScoreThreads;
     const int split = pick_split(gx * B, N);
     if (split > 1) {
@@ -403,6 +509,12 @@ extern "C" int drb_rigid_residual_backward(const float* points, const float* mod
                                            int N, float* g_models, void* stream) {
     if (!points || !models || !g_res || !g_models) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || N <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
+    if (rigid_by_moments()) {
+        cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 16, (cudaStream_t)stream);   // the fourth rows
+        rigid_residual_moments_kernel<true><<<dim3((K + kMomThreads - 1) / kMomThreads, B), kMomThreads, 0,
+                                              (cudaStream_t)stream>>>(points, models, g_res, K, N, g_models, nullptr);
+        DRB_CHECK_LAUNCH();
+    }
     const int gx = (K + kScoreThreads - 1) / kScoreThreads;
     const int split = pick_split(gx * B, N);
     cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 16, (cudaStream_t)stream);
@@ -415,6 +527,12 @@ extern "C" int drb_rigid_residual_forward_backward(const float* points, const fl
                                                    int K, int N, float* res_sum, float* g_models, void* stream) {
     if (!points || !models || !g_res || !res_sum || !g_models) return DRB_ERR_NULL_POINTER;
     if (B <= 0 || K <= 0 || N <= 0 || B > 65535) return DRB_ERR_BAD_SHAPE;
+    if (rigid_by_moments()) {
+        cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 16, (cudaStream_t)stream);   // the fourth rows
+        rigid_residual_moments_kernel<true><<<dim3((K + kMomThreads - 1) / kMomThreads, B), kMomThreads, 0,
+                                              (cudaStream_t)stream>>>(points, models, g_res, K, N, g_models, res_sum);
+        DRB_CHECK_LAUNCH();
+    }
     const int gx = (K + kScoreThreads - 1) / kScoreThreads;
     const int split = pick_split(gx * B, N);
     cudaMemsetAsync(g_models, 0, sizeof(float) * (size_t)B * K * 16, (cudaStream_t)stream);
