@@ -136,6 +136,24 @@ def ransac_e5_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=
     return out
 
 
+def ransac_e5_test_f64(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False,
+                       sampler="sets"):
+    """`ransac_e5_test` with the solver, MSAC, arg-max and winner mask in float64 -- what the reference computes under
+    `-pr 2` (utils.py:42, model_cl.py:164-170: the sampler's one-hot carries the dtype and the chain follows by type
+    promotion).  The samples are drawn exactly as in the fp32 path (same sampler, same noise).  Returns the same
+    dict with float64 models and scores (csrc/fp64_path.cu; built for results, not for the roofline)."""
+    idx = _draw(ops._f32(logits), K, 5, tau, noise, seed, offset, sampler)
+    models, nsol = ops.solve_e5_f64(matches, idx)
+    scores = ops.score_msac_f64(matches, models, thr, nsol)
+    best_id, best_score, best_model, mask, ninl = ops.best_finalize_f64(matches, models, scores, thr)
+    out = dict(best_model=best_model, best_id=best_id, best_score=best_score, mask=mask.view(torch.bool), ninl=ninl,
+               idx=idx, models=models, nsol=nsol,
+               best_hyp=torch.div(best_id, ops.E5_SLOTS, rounding_mode="floor"), best_slot=best_id % ops.E5_SLOTS)
+    if want_scores:
+        out["scores"] = scores
+    return out
+
+
 def ransac_f8_test(matches, logits, K, thr, tau=1.0, noise=None, seed=0, offset=0, want_scores=False,
                    sampler="sets"):
     idx = _draw(logits, K, 8, tau, noise, seed, offset, sampler)

@@ -37,19 +37,20 @@ _PRECISION_NOTED = set()
 
 
 def _dtype(opt):
-    """`-pr` (utils.py:42): 0 = fp16, 1 = fp32, 2 = fp64 -- in the reference the dtype of every tensor on the path
-    (test.py:13-18, nister.py:121-122).  The device path computes the sample -> solve -> score chain in fp32 whatever
-    `-pr` says (inputs are converted on the way in, results come back in the requested dtype); what already runs in
-    fp64 regardless is the final refit, pose recovery and the backward adjoints.  Said once per process instead of
-    silently: an fp64 run of the reference is what the parity fixtures compare against, not what this path computes."""
+    """`-pr` (utils.py:42): 0 = fp16, 1 = fp32, 2 = fp64 -- in the reference the dtype of the sampler's one-hot, which
+    the rest of the chain follows by type promotion (test.py:13-18, nister.py:121-122).  `-pr 2` runs the test-mode
+    five-point chain (solver, MSAC, arg-max, winner mask) in float64 on the device (csrc/fp64_path.cu,
+    engine.ransac_e5_test_f64) when the adaptive exit and LO are off; every other chain computes in fp32 whatever `-pr`
+    says (inputs converted on the way in, results returned in the requested dtype; refit, pose recovery and the
+    backward adjoints are fp64 regardless).  Said once per process instead of silently."""
     p = getattr(opt, "precision", 1)
     if p != 1 and p not in _PRECISION_NOTED:
         import warnings
 
         _PRECISION_NOTED.add(p)
-        warnings.warn(f"-pr {p}: the CUDA hypothesize-and-score path computes in fp32 (refit, pose recovery and backward "
-                      f"adjoints in fp64); tensors are converted at the boundary and returned as "
-                      f"{'float64' if p == 2 else 'float16'}")
+        warnings.warn(f"-pr {p}: only the test-mode five-point chain without adaptive exit / LO has a float64 device path; "
+                      f"the other CUDA chains compute in fp32 (refit, pose recovery and backward adjoints in fp64) and "
+                      f"return {'float64' if p == 2 else 'float16'} tensors")
     return {2: torch.float64, 0: torch.float16}.get(p, torch.float32)
 
 

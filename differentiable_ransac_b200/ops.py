@@ -527,3 +527,60 @@ def rigid_residual_backward(points, models, g_res):
     check(lib.drb_rigid_residual_backward(_p(points), _p(models), _p(_f32(g_res)), B, K, N, _p(out), _stream()),
           "drb_rigid_residual_backward")
     return out
+
+
+# ---- the float64 chain (`-pr 2`; csrc/fp64_path.cu) -----------------------------------------------------------
+def _f64(t):
+    if t.device.type != "cuda":
+        raise _lib.DrbError("the CUDA path needs CUDA tensors (there is no CPU fallback)")
+    return t.detach().to(torch.float64).contiguous()
+
+
+def solve_e5_f64(matches, idx):
+    """matches [B,N,4] (any float dtype; computed in float64), idx [B,K,5] -> models [B,K,10,3,3] float64 (identity in
+    the unused slots), nsol [B,K]."""
+    m = _f64(matches)
+    B, N, _ = m.shape
+    idx = _i32(idx)
+    K = idx.shape[1]
+    models = torch.empty(B, K, E5_SLOTS, 3, 3, dtype=torch.float64, device=m.device)
+    nsol = torch.empty(B, K, dtype=torch.int32, device=m.device)
+    check(_lib.load().drb_solve_e5_f64(_p(m), _p(idx), B, K, N, _p(models), _p(nsol), _stream()), "drb_solve_e5_f64")
+    return models, nsol
+
+
+def score_msac_f64(matches, models, thr, nsol=None):
+    """matches [B,N,4], models [B,K,S,3,3] (or [B,M,3,3] with nsol=None), thr [B] -> scores [B,K*S] float64 (-1 for a
+    slot without a model)."""
+    m = _f64(matches)
+    B, N, _ = m.shape
+    md = _f64(models)
+    if nsol is not None:
+        K, S = md.shape[1], md.shape[2]
+    else:
+        md = md.reshape(B, -1, 9)
+        K, S = md.shape[1], 1
+    scores = torch.empty(B, K * S, dtype=torch.float64, device=m.device)
+    check(_lib.load().drb_score_msac_f64(_p(m), _p(md), _p(None if nsol is None else _i32(nsol)), _p(_f64(thr).reshape(B)),
+                                         B, K, S, N, _p(scores), _stream()), "drb_score_msac_f64")
+    return scores
+
+
+def best_finalize_f64(matches, models, scores, thr):
+    """-> best_id [B] (first maximum; -1 when no slot holds a model), best_score [B] f64, best_model [B,3,3] f64,
+    mask [B,N] uint8, ninl [B]."""
+    m = _f64(matches)
+    B, N, _ = m.shape
+    md = _f64(models).reshape(B, -1, 9)
+    sc = _f64(scores).reshape(B, -1)
+    M = md.shape[1]
+    dev = m.device
+    best_id = torch.empty(B, dtype=torch.int32, device=dev)
+    best_score = torch.empty(B, dtype=torch.float64, device=dev)
+    best_model = torch.empty(B, 3, 3, dtype=torch.float64, device=dev)
+    mask = torch.empty(B, N, dtype=torch.uint8, device=dev)
+    ninl = torch.empty(B, dtype=torch.int32, device=dev)
+    check(_lib.load().drb_best_finalize_f64(_p(m), _p(md), _p(sc), _p(_f64(thr).reshape(B)), B, M, N, _p(best_id),
+                                            _p(best_score), _p(best_model), _p(mask), _p(ninl), _stream()),
+          "drb_best_finalize_f64")
+    return best_id, best_score, best_model, mask, ninl

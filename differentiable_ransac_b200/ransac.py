@@ -196,7 +196,10 @@ class RANSAC(object):
             return engine.ransac_test_adaptive(m, lg, rbs, self.max_iterations, thr, self.sample_size,
                                                self.confidence, self.eps, self.sampler.tau, noise, self.sampler.seed,
                                                off, adaptive_exponent=self.estimator.sample_size)
-        out = self._run()(m, lg, K, thr, self.sampler.tau, noise, self.sampler.seed, off)
+        run = self._run()
+        if self.sample_size == 5 and getattr(self.sampler, "dtype", torch.float32) == torch.float64:
+            run = engine.ransac_e5_test_f64        # `-pr 2`: solver, MSAC, arg-max and mask in float64 (fp64_path.cu)
+        out = run(m, lg, K, thr, self.sampler.tau, noise, self.sampler.seed, off)
         out["iterations"] = torch.full((m.shape[0],), K, dtype=torch.int32, device=m.device)
         return out
 
@@ -222,7 +225,8 @@ class RANSAC(object):
         return best
 
     def _test(self, matches, logits, thr):
-        m, lg = matches[None].float(), logits[None].float()
+        f64 = getattr(self.sampler, "dtype", torch.float32) == torch.float64      # `-pr 2`
+        m, lg = (matches[None].double() if f64 else matches[None].float()), logits[None].float()
         noise = self.sampler.injected_noise
         if noise is not None:
             noise = noise.reshape(1, -1, noise.shape[-1])

@@ -196,6 +196,23 @@ int drb_score_msac_tc(const float* matches, const float* models, const int32_t* 
                       const float* thr, int B, int M, int N, int words,
                       float* scores, unsigned long long* best_packed, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* ---- the same chain in double precision (`-pr 2`: utils.py:42, model_cl.py:164-170) -------------------------
+ * In the reference the precision flag sets the dtype of the sampler's one-hot, and the minimal samples, the five-point
+ * solver (nister.py:121-122) and MSAC (msac_score.py:12-55) follow by type promotion.  These entries run that chain in
+ * float64 on the device with the same templated math as the fp32 kernels (fp64_path.cu): built for results, not for
+ * the roofline.  matches[B,N,4] (or [B*K,5,4] when idx is null), thr[B] are DOUBLE.
+ *   drb_solve_e5_f64      idx[B,K,5] -> models[B,K,10,9] (identity in the unused slots), nsol[B,K]
+ *   drb_score_msac_f64    models[B,K*slots,9], nsol[B,K] (nullable: every slot holds a model) -> scores[B,K*slots]
+ *                         (-1 for an empty slot)
+ *   drb_best_finalize_f64 scores[B,M] -> best_id[B] (first maximum, like torch.argmax at ransac.py:114; -1 if none),
+ *                         best_score[B], best_model[B,9], mask[B,N] (d2 < (1.5 thr)^2), ninl[B]                     */
+int drb_solve_e5_f64(const double* matches, const int32_t* idx, int B, int K, int N, double* models, int32_t* nsol,
+                     void* stream);
+int drb_score_msac_f64(const double* matches, const double* models, const int32_t* nsol, const double* thr, int B,
+                       int K, int slots, int N, double* scores, void* stream);
+int drb_best_finalize_f64(const double* matches, const double* models, const double* scores, const double* thr,
+                          int B, int M, int N, int32_t* best_id, double* best_score, double* best_model,
+                          uint8_t* mask, int32_t* ninl, void* stream);
 /* Decode best_packed and produce the winner's model, score, id and inlier mask
  * (d2 < (1.5 thr)^2, msac_score.py:44) -- the only mask ransac.py:116-118 ever uses.
  * models_dense[B,Md,9] is indexed by best id.  best_id[B], best_score[B], best_model[B,9],
