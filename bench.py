@@ -888,21 +888,44 @@ def run_train(args):
         ar_ms = _max_over_ranks(a0.elapsed_time(a1) / 50, dev, dist)
 
     # ---- e2e: pinned host batch in, loss on the host, every step ------------------------------------
+    # A training loop is sequential in its steps (step i + 1 needs the weights step i produced), but not in its DATA: the
+    # next batch is known.  As a DataLoader with pinned memory does, the batch of step i + 1 is copied host -> device on
+    # a copy stream into one of two staging sets while step i computes; the step itself starts with a device-to-device
+    # copy of its staged batch into the graph's static buffers, and the host reads the step's loss before it goes on.
     loss_h = torch.empty(1).pin_memory()
+    keys = [k_ for k_ in ("matches", "logits", "gt", "pts", "npts") if torch.is_tensor(host.get(k_))]
+    stage = [{k_: torch.empty_like(devd[k_]) for k_ in keys} for _ in range(2)]
+    copy_stream = torch.cuda.Stream(device=dev)
+    ev_ready = [torch.cuda.Event() for _ in range(2)]
+    ev_free = [torch.cuda.Event() for _ in range(2)]
+    for e_ in ev_free:
+        e_.record(main_stream)
 
-    def e2e_step():
-        step.load(host["matches"], host["logits"], host.get("gt"), host["pts"], host["npts"])
+    def prefetch(j):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(ev_free[j % 2])          # the step that used this staging set has copied it out
+            for k_ in keys:
+                stage[j % 2][k_].copy_(host[k_], non_blocking=True)
+            ev_ready[j % 2].record(copy_stream)
+
+    def e2e_step(j):
+        prefetch(j + 1)
+        main_stream.wait_event(ev_ready[j % 2])
+        st_ = stage[j % 2]
+        step.load(st_["matches"], st_["logits"], st_.get("gt"), st_.get("pts"), st_.get("npts"))
+        ev_free[j % 2].record(main_stream)
         loss = one_step(0, rotate=False)
         loss_h.copy_(loss, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the training loop reads the loss (train.py:175)
+        main_stream.synchronize()                           # the training loop reads the loss (train.py:175)
         return float(loss_h)
 
-    for _ in range(warmup):
-        e2e_step()
+    prefetch(0)
+    for j in range(warmup):
+        e2e_step(j)
     _barrier(dist)
     th0 = time.perf_counter()
-    for _ in range(args.steps):
-        last_loss = e2e_step()
+    for j in range(warmup, warmup + args.steps):
+        last_loss = e2e_step(j)
     torch.cuda.synchronize()
     e2e_ms = _max_over_ranks((time.perf_counter() - th0) * 1e3, dev, dist)
     e2e_value = world * B * K * args.steps / (e2e_ms / 1e3)
@@ -935,7 +958,9 @@ def run_train(args):
                                dict(bytes=CLNET_PARAMS * 4, ms_alone=ar_ms, share_of_step=ar_ms / ms_per_step,
                                     placement="own stream, behind the step's backward; the next step waits for it "
                                               "(critical path, as in data-parallel train.py)")),
-                    e2e_mode="every step: H2D of the pinned host batch into the step's static buffers, graph replay, D2H of "
+                    e2e_mode="every step: H2D of the NEXT step's pinned host batch on a copy stream into one of two staging sets "
+                             "(a DataLoader's prefetch) while this step runs; the step = device-to-device copy of its staged "
+                             "batch into the static buffers, graph replay, D2H of "
                              "the loss, host synchronisation (a training loop is sequential: no batches in flight); timed "
                              "on the host clock",
                     last_loss=last_loss, parallelism=f"pairs sharded over {world} GPU(s)"),

@@ -43,6 +43,7 @@ _SIGNATURES = {
     "drb_score_msac_stream": ([P, P, P, P, P, c_int, c_int, c_int, P, P, P, ctypes.c_size_t, P], c_int),
     "drb_score_msac_tc_workspace_bytes": ([c_int, c_int], ctypes.c_size_t),
     "drb_score_msac_tc": ([P, P, P, P, P, c_int, c_int, c_int, c_int, P, P, P, ctypes.c_size_t, P], c_int),
+    "drb_copy_h2d_async": ([P, P, ctypes.c_size_t, P], c_int),
     "drb_solve_e5_f64": ([P, P, c_int, c_int, c_int, P, P, P], c_int),
     "drb_score_msac_f64": ([P, P, P, P, c_int, c_int, c_int, c_int, P, P], c_int),
     "drb_best_finalize_f64": ([P, P, P, P, c_int, c_int, c_int, P, P, P, P, P, P], c_int),

@@ -58,3 +58,15 @@ extern "C" int drb_gather_backward(const float* matches, const int32_t* idx, con
         matches, idx, g_pts, total, K, N, s, D, g_sel, grad_matches);
     return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
 }
+
+// Host -> device copy of a caller's buffer on a stream: cudaMemcpyAsync behind the C ABI, so that the pipelined
+// service enqueues a batch's inputs with one foreign call per tensor instead of a framework dispatch each (the host
+// side of a 0.14 ms step has ~100 us to spare in all).  Asynchronous when `src` is pinned.
+extern "C" int drb_copy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* stream) {
+    if (!dst_device || !src_host) return DRB_ERR_NULL_POINTER;
+    if (bytes == 0) return DRB_OK;
+    return cudaMemcpyAsync(dst_device, src_host, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream) == cudaSuccess
+               ? DRB_OK
+               : DRB_ERR_CUDA;
+}
+

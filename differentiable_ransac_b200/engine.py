@@ -565,6 +565,15 @@ class E5TestService:
         # batch i draws with offset i exactly as in eager mode when the slots are used round-robin
         self.counters = [torch.full((1,), s, dtype=torch.int64, device=self.device) for s in range(self.slots)]
         self.graphs = [None] * self.slots
+        # Host-side cost of a step (the device needs 0.14 ms at cfg2; Python has to stay well below that): the views
+        # of the slot buffers are made once, the input copies go through one foreign call each (drb_copy_h2d_async)
+        # and `result_views` hands out the same objects every time -- they alias the slot's pinned buffers.
+        self._in_views = [(b_[: B * N * 4].view(B, N, 4), b_[B * N * 4: B * N * 5].view(B, N), b_[B * N * 5:])
+                          for b_ in self.dev_in]
+        self._in_ptrs = [tuple(v.data_ptr() for v in views) for views in self._in_views]
+        self._in_bytes = (B * N * 16, B * N * 4, B * 4)
+        self._copy = ops._lib.load().drb_copy_h2d_async
+        self._views = [None] * self.slots
 
     def _body(self, slot, offset, offset_dev):
         B, N = self.B, self.N
@@ -611,10 +620,13 @@ class E5TestService:
         if host is None:
             buf.copy_(self.host_in[slot], non_blocking=True)
             return
-        m, lg, thr = host
-        buf[: B * N * 4].view(B, N, 4).copy_(m, non_blocking=True)
-        buf[B * N * 4: B * N * 5].view(B, N).copy_(lg, non_blocking=True)
-        buf[B * N * 5:].copy_(thr, non_blocking=True)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        for src, dst, ptr, nbytes in zip(host, self._in_views[slot], self._in_ptrs[slot], self._in_bytes):
+            if (src.dtype == torch.float32 and src.device.type == "cpu" and src.is_contiguous()
+                    and src.numel() * 4 == nbytes):
+                ops.check(self._copy(ptr, src.data_ptr(), nbytes, stream), "drb_copy_h2d_async")
+            else:                                   # another dtype / layout / a device tensor: the framework's copy
+                dst.copy_(src.reshape(dst.shape), non_blocking=True)
 
     def submit(self, slot=None, packed=None, host=None):
         """Enqueue one batch; returns the slot.  host_io: the batch staged in `host_in[slot]`, or `host` =
@@ -681,6 +693,20 @@ class E5TestService:
         if self.want_mask:
             res["mask"] = (self.host_mask if self.host_io else self.dev_mask)[slot].view(torch.bool)
         return res
+
+    def result_views(self, slot):
+        """`result(slot)` for callers in a hurry (RANSACLayer.collect): waits for the slot's batch and returns
+        (list_B[model [3,3]], mask [B,N] bool | None, score [B]) -- the SAME view objects on every call, aliasing the
+        slot's pinned output buffers (valid until the slot is submitted again)."""
+        self.done[slot].synchronize()
+        self.busy[slot] = False
+        v = self._views[slot]
+        if v is None:
+            B = self.B
+            out = (self.host_out if self.host_io else self.dev_out)[slot]
+            mask = (self.host_mask if self.host_io else self.dev_mask)[slot].view(torch.bool) if self.want_mask else None
+            v = self._views[slot] = (list(out[: 9 * B].view(B, 3, 3).unbind(0)), mask, out[10 * B: 11 * B])
+        return v
 
     def drain(self):
         for s in range(self.slots):

@@ -8,6 +8,7 @@ from __future__ import annotations
 
 import time
 
+import numpy as np
 import torch
 import torch.nn as nn
 
@@ -154,19 +155,26 @@ class RANSACLayer(nn.Module):
                                              want_mask=True)
             self._svc_key = key
             self._thr_pinned = [torch.empty(B, dtype=torch.float32).pin_memory() for _ in range(int(slots))]
+            self._thr_np = [t.numpy() for t in self._thr_pinned]
         svc = self._svc
         slot = svc.step % svc.slots
         if svc.busy[slot]:
             svc.done[slot].synchronize()           # its results were not collected: they are overwritten
         thr = self._thr_pinned[slot]
-        thr.copy_(self.thresholds(K1, K2, B, "cpu"))
+        if (torch.is_tensor(K1) and torch.is_tensor(K2) and K1.device.type == "cpu" and K2.device.type == "cpu"
+                and K1.dtype == torch.float32 and K2.dtype == torch.float32):
+            # ransac.py:49-53 on the host without a dozen framework dispatches (the step has ~100 us of host time)
+            k1, k2 = K1.numpy(), K2.numpy()
+            np.divide(4.0 * float(drv.threshold), k1[..., 0, 0] + k1[..., 1, 1] + k1[..., 0, 0] + k2[..., 1, 1],
+                      out=self._thr_np[slot], casting="unsafe")
+        else:
+            thr.copy_(self.thresholds(K1, K2, B, "cpu"))
         return svc.submit(slot, host=(points, weights, thr))
 
     def collect(self, ticket):
         """-> (list_B[E_b [3,3]], masks [B,N] bool, scores [B]) of the batch `submit` returned `ticket` for: views
         of the slot's pinned host buffers, valid until the slot is submitted again (`slots` submits later)."""
-        r = self._svc.result(ticket)
-        return list(r["best_model"].unbind(0)), r["mask"], r["best_score"]
+        return self._svc.result_views(ticket)
 
 
 class RANSACLayer3D(nn.Module):

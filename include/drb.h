@@ -196,6 +196,10 @@ int drb_score_msac_tc(const float* matches, const float* models, const int32_t* 
                       const float* thr, int B, int M, int N, int words,
                       float* scores, unsigned long long* best_packed, void* workspace,
                       size_t workspace_bytes, void* stream);
+/* Host -> device copy of a caller's buffer on `stream` (cudaMemcpyAsync; asynchronous when src is pinned): the
+ * pipelined service (engine.E5TestService / RANSACLayer.submit) enqueues a batch's inputs through it.            */
+int drb_copy_h2d_async(void* dst_device, const void* src_host, size_t bytes, void* stream);
+
 /* ---- the same chain in double precision (`-pr 2`: utils.py:42, model_cl.py:164-170) -------------------------
  * In the reference the precision flag sets the dtype of the sampler's one-hot, and the minimal samples, the five-point
  * solver (nister.py:121-122) and MSAC (msac_score.py:12-55) follow by type promotion.  These entries run that chain in

@@ -17,7 +17,7 @@ noise = synth.gumbel_noise((B, K, N), seed=3)
 m, E, lg, thr, noise = m.to(DEV), E.to(DEV), lg.to(DEV), thr.to(DEV), noise.to(DEV)
 for kw in (dict(), dict(noise=noise), dict(sampler="gumbel")):
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, **kw)
-TC = os.environ.get("DRB_SANITIZE_TC", "tc_tf32,tc_bf16,tc_bf16p").split(",")
+TC = os.environ.get("DRB_SANITIZE_TC", "tc_tf32,tc_bf16,tc_bf16p,tc_bf16p_s,tc_bf16q,tc_tf32q").split(",")
 for scorer in ["block", "stream"] + [t for t in TC if t]:   # every MSAC kernel; the queue kernel with a block cut into pieces
     out = engine.ransac_e5_test(m, lg, K, thr, want_scores=True, scorer=scorer)
 svc = engine.E5TestService(B, N, K, DEV, slots=2, seed=1, graph=False, host_io=False)
@@ -44,5 +44,9 @@ for kind, data in (("e5", (m, lg, E, m, torch.full((B,), N, dtype=torch.int32, d
     st.run(*data)
 st = engine.TrainStep("rigid", 2, 1001, 50, DEV, seed=3, graph=False)
 st.run(pts, l3.detach())
+out64 = engine.ransac_e5_test_f64(m, lg, K, thr, noise=noise, want_scores=True)      # the float64 chain (fp64_path.cu)
+ops.rigid_residual_forward_backward(pts, r.detach(), torch.ones(2, 50, device=DEV))  # moments kernel, N = 1001
+ops.rigid_residual_forward(pts, r.detach(), want_ninl=True)                          # per-point kernel (inlier counts)
+ops.rigid_residual_forward(pts, r.detach(), want_ninl=False)                         # moments kernel
 torch.cuda.synchronize()
 print("sanitize smoke ok", float(out["best_score"].sum()), float(out8["best_score"].sum()))
