@@ -28,10 +28,13 @@
 //                   of the four lane quarters (the scores do not depend on the schedule)
 //   A unit = (pair, 128 consecutive models); units are dealt round-robin to the CTAs.
 //
-// Measured on B200 (cfg2, 139 000 models x 2000 correspondences): 0.122 ms against 0.215 ms for the FP32 work
-// queue; XU pipe (the reciprocals) 67 %, tensor pipe 17 % (profiles/r1_ncu_score_msac_tc.txt, DESIGN.md
-// section 10).  Operand images / column mapping / descriptors are also checked on the host
-// (tests/test_host_math.py::test_msac_tc_*).
+// Measured on B200 (cfg2, 139 000 models x 2000 correspondences): 0.1075 ms for the pair-reciprocal BF16 variant
+// (0.122 ms with one reciprocal per pair) against 0.215 ms for the FP32 work queue.  What bounds it (round-2
+// ablations, DESIGN.md section 10, profiles/r2_tc_ablate.jsonl): the tensor side alone takes 0.085 ms -- 78 % of the
+// dense BF16 rate this pool sustains under its power cap -- and the epilogue alone 0.095-0.10 ms (issue-bound: 305
+// instructions per warp and tile); neither the XU nor the FMA pipe is the limiter.  Every variant is pinned to the
+// fp64 oracle on the B200 (tests/test_gpu_score_tc.py); operand images / column mapping / descriptors are also
+// checked on the host (tests/test_host_math.py::test_msac_tc_*).
 #include <cuda_runtime.h>
 
 #include "../../include/drb.h"
@@ -451,7 +454,8 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
         (reinterpret_cast<uintptr_t>(matches) & 15))
         return DRB_ERR_BAD_SHAPE;
     // words: 2 = TF32 x 2, 3 = BF16 x 3; + 16 = one reciprocal per model pair; + 32 = 16 epilogue warps instead
-    // of 8; + 64 = the model-stationary arrangement of score_tc2.cu (the last three not yet measured on hardware)
+    // of 8; + 64 = the model-stationary arrangement of score_tc2.cu; + 128 = folded threshold; + 256 = slim build
+    // (all measured on the B200: DESIGN.md section 10)
     const int split = words & 15;
     const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0, fold = (words & 128) != 0,
                slim = (words & 256) != 0;

@@ -372,8 +372,8 @@ _TC_WORDS.update({"tc2_tf32": 2 + 64, "tc2_bf16": 3 + 64, "tc2_tf32_e16": 2 + 64
 def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, best=None, kernel=None):
     """matches [B,N,4], models [B,M,9|3,3], thr [B] -> scores [B,M] | None, best_packed [B] (int64 view of u64).
     `best` may be a caller-zeroed [B] int64 buffer.  kernel="stream": the evenly split persistent grid
-    (drb_score_msac_stream); "block": one CTA per (pair, 32 models) (drb_score_msac); "tc": the experimental
-    tensor-core scorer (drb_score_msac_tc), never chosen by default."""
+    (drb_score_msac_stream); "block": one CTA per (pair, 32 models) (drb_score_msac); "tc_*": the tensor-core scorer
+    (drb_score_msac_tc, _TC_WORDS above; the pipelined service's default, every variant pinned to the fp64 oracle)."""
     kernel = kernel or _MSAC_KERNEL
     matches = _f32(matches)
     B, N, _ = matches.shape
@@ -394,9 +394,9 @@ def score_msac(matches, models, thr, count=None, ids=None, want_scores=True, bes
         check(lib.drb_score_msac(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N, _p(scores), _p(best),
                                  _stream()), "drb_score_msac")
     elif kernel in _TC_WORDS:
-        # experimental tensor-core scorer (csrc/score_tc.cu): opt-in only, see DESIGN.md section 10.
+        # tensor-core scorer (csrc/score_tc.cu, score_tc2.cu), DESIGN.md section 10.
         # "tc" = "tc_bf16": three BF16 words per operand (fp32-level scores); "tc_tf32": two TF32 words;
-        # a trailing "p": one reciprocal per model pair; "_e16": 16 epilogue warps (neither measured on hardware yet)
+        # a trailing "p": one reciprocal per model pair; "_e16": 16 epilogue warps; "_s": the slim build
         nbytes = int(lib.drb_score_msac_tc_workspace_bytes(B, N))
         ws = torch.empty((nbytes + 7) // 8, dtype=torch.int64, device=matches.device)
         check(lib.drb_score_msac_tc(_p(matches), _p(models), _p(count), _p(ids), _p(thr), B, M, N,
