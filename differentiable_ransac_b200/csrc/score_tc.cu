@@ -49,7 +49,8 @@
 // Ablation switches for profiles/microbench/tc_ablate.py (bit 0: no MMAs are issued, bit 1: the epilogue skips its
 // arithmetic, bit 2: the epilogue skips tcgen05.ld, bit 3: a multiply stands in for MUFU.RCP, bit 4: the accumulator
 // is handed back right after the tile's last tcgen05.ld instead of after its arithmetic, bit 5 / bit 6: four / three of
-// the six K steps are issued -- what fewer tensor flops would buy).  The product build is 0:
+// the six K steps are issued -- what fewer tensor flops would buy, bit 7: the idle roles poll their barriers without
+// the nanosleep back-off).  The product build is 0:
 // every switch is a compile-time constant and the kernel's SASS does not change.
 #ifndef DRB_TC_ABLATE
 #define DRB_TC_ABLATE 0
@@ -57,6 +58,32 @@
 
 namespace drb {
 namespace tc {
+
+// Waits of the single-thread roles (producer, MMA issuer) and of the builders: poll, then sleep 100 ns.  mbar_wait
+// re-issues mbarrier.try_wait as fast as the warp can -- a quarter of the kernel's executed instructions were such
+// polls, issued on the sub-partitions the epilogue warps need; with the back-off the kernel is 2-3 % faster
+// (0.1117 -> 0.1086 ms at cfg2; a suspend-time hint on try_wait: 0.1097).  The epilogue warps keep the plain wait:
+// their wake-up latency is on the critical path.  DRB_TC_ABLATE bit 7 restores the plain wait everywhere.
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity) {
+    if (DRB_TC_ABLATE & 128) {
+        mbar_wait(bar, parity);
+        return;
+    }
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+        if (done) break;
+        __nanosleep(100);
+    }
+}
 
 constexpr int kWarpProducer = 0;
 constexpr int kWarpMma = 1;
@@ -183,7 +210,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 const uint32_t* src = images + (size_t)b * tiles * (kABytes / 4);
 #pragma unroll 1
                 for (int t = 0; t < tiles; ++t) {
-                    mbar_wait(&a_empty[ra.idx], ra.phase ^ 1u);
+                    mbar_wait_idle(&a_empty[ra.idx], ra.phase ^ 1u);
                     mbar_expect_tx(&a_full[ra.idx], kABytes);
                     bulk_g2s(smem + kOffA + ra.idx * kABytes, src + (size_t)t * (kABytes / 4), kABytes, &a_full[ra.idx]);
                     ra.advance(kStagesA);
@@ -197,12 +224,12 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
             Ring ra, rd, rb;
 #pragma unroll 1
             for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
-                mbar_wait(&b_full[rb.idx], rb.phase);
+                mbar_wait_idle(&b_full[rb.idx], rb.phase);
                 const uint64_t bdesc = smem_desc(smem_u32(smem + kOffB + rb.idx * kBBytes));
 #pragma unroll 1
                 for (int t = 0; t < tiles; ++t) {
-                    mbar_wait(&d_empty[rd.idx], rd.phase ^ 1u);
-                    mbar_wait(&a_full[ra.idx], ra.phase);
+                    mbar_wait_idle(&d_empty[rd.idx], rd.phase ^ 1u);
+                    mbar_wait_idle(&a_full[ra.idx], ra.phase);
                     tc_fence_after();
                     const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
                     const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN);
@@ -229,7 +256,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
             int b, mt;
             unit_of(prefix, B, u, b, mt);
             const int cnt = count ? min(__ldg(count + b), M) : M;
-            mbar_wait(&b_empty[rb.idx], rb.phase ^ 1u);
+            mbar_wait_idle(&b_empty[rb.idx], rb.phase ^ 1u);
             uint32_t* img = reinterpret_cast<uint32_t*>(smem + kOffB + rb.idx * kBBytes);
             DRB_UNROLL
             for (int rep = 0; rep < kTileModels / kBuildThreads; ++rep) {

@@ -17,7 +17,8 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 CSRC = os.path.join(ROOT, "differentiable_ransac_b200", "csrc")
 OUT = os.path.join(HERE, "build")
 ABLATIONS = {0: "none", 16: "early release of the accumulator", 1: "no MMA", 2: "no epilogue math", 3: "no MMA, no math",
-             8: "no MUFU", 32: "4 of 6 K steps", 64: "3 of 6 K steps", 34: "4 of 6 K steps, no epilogue math"}
+             8: "no MUFU", 32: "4 of 6 K steps", 64: "3 of 6 K steps", 34: "4 of 6 K steps, no epilogue math",
+             128: "idle roles poll without the nanosleep back-off"}
 if os.environ.get("DRB_ABLATE_ONLY"):
     ABLATIONS = {int(k): ABLATIONS.get(int(k), "?") for k in os.environ["DRB_ABLATE_ONLY"].split(",")}
 
