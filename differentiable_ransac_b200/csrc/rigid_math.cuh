@@ -268,4 +268,51 @@ DRB_HD bool rigid3_backward(const T (*pts)[6], int flag, const T* g, T (*gp)[6])
     return true;
 }
 
+// ---- rigid residual from the points' second moments (score.cu: rigid_residual_moments_kernel) -------------------
+// sum_n ||q_n - (R p_n + t)||^2 and its gradient in (R, t) are quadratic forms in the model whose coefficients are 22
+// sums over the points alone (rigid_transformation_SVD_based_solver.py:76-89 computes the same sum point by point):
+//     mom[0..5] = S_pp (xx, xy, xz, yy, yz, zz),  mom[6..14] = S_qp row-major,  mom[15..17] = s_p,  mom[18..20] = s_q,
+//     mom[21] = sum |q|^2
+//     sum d_i p_j = S_qp[i][j] - R_i . S_pp[:, j] - t_i s_p[j],      sum d_i = s_q[i] - R_i . s_p - N t_i
+//     sum |d|^2   = s_qq - 2 sum_i (R_i . S_qp[i] + t_i s_q[i]) + sum_i (R_i S_pp R_i' + 2 t_i R_i . s_p + N t_i^2)
+// AT is the accumulation type: double on the device (the sums cancel for a model that fits).
+constexpr int kRigidMoments = 22;
+
+template <class AT>
+DRB_HD void rigid_moments_add(const AT* p, const AT* q, AT* s) {
+    s[0] += p[0] * p[0]; s[1] += p[0] * p[1]; s[2] += p[0] * p[2];
+    s[3] += p[1] * p[1]; s[4] += p[1] * p[2]; s[5] += p[2] * p[2];
+    DRB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        DRB_UNROLL
+        for (int j = 0; j < 3; ++j) s[6 + 3 * i + j] += q[i] * p[j];
+        s[15 + i] += p[i];
+        s[18 + i] += q[i];
+        s[21] += q[i] * q[i];
+    }
+}
+
+// model12: the 3 x 4 block [R | t] row-major (the first twelve entries of the 4 x 4 model).  res = sum |d|^2;
+// g12[4 i + j] = -sum d_i p_j (j < 3), g12[4 i + 3] = -sum d_i: half of d res / d model12.
+template <class T, class AT>
+DRB_HD void rigid_residual_from_moments(const AT* mom, AT n_points, const T* model12, AT& res, AT* g12) {
+    const AT Spp[3][3] = {{mom[0], mom[1], mom[2]}, {mom[1], mom[3], mom[4]}, {mom[2], mom[4], mom[5]}};
+    res = mom[21];
+    DRB_UNROLL
+    for (int i = 0; i < 3; ++i) {
+        const AT r[3] = {AT(model12[4 * i]), AT(model12[4 * i + 1]), AT(model12[4 * i + 2])};
+        const AT t = AT(model12[4 * i + 3]);
+        AT rS[3];                    // R_i . S_pp[:, j]
+        DRB_UNROLL
+        for (int j = 0; j < 3; ++j) rS[j] = r[0] * Spp[0][j] + r[1] * Spp[1][j] + r[2] * Spp[2][j];
+        const AT r_sp = r[0] * mom[15] + r[1] * mom[16] + r[2] * mom[17];
+        const AT r_sqp = r[0] * mom[6 + 3 * i] + r[1] * mom[7 + 3 * i] + r[2] * mom[8 + 3 * i];
+        res += AT(-2) * (r_sqp + t * mom[18 + i]) + (rS[0] * r[0] + rS[1] * r[1] + rS[2] * r[2]) + AT(2) * t * r_sp +
+               n_points * t * t;
+        DRB_UNROLL
+        for (int j = 0; j < 3; ++j) g12[4 * i + j] = -(mom[6 + 3 * i + j] - rS[j] - t * mom[15 + j]);
+        g12[4 * i + 3] = -(mom[18 + i] - r_sp - n_points * t);
+    }
+}
+
 }  // namespace drb

@@ -16,6 +16,7 @@
 #include "drb_common.cuh"
 #include "f32x2.cuh"
 #include "msac_records.cuh"
+#include "rigid_math.cuh"
 #include "sampson.cuh"
 #include "tile_pipe.cuh"
 
@@ -325,7 +326,7 @@ rigid_residual_kernel(const float* __restrict__ points, const float* __restrict_
 // per-point kernel to fp32 rounding (closer to the reference run in fp64); the per-point kernel stays for callers
 // that want the inlier counts, which are not a function of the moments.
 constexpr int kMomThreads = 256;
-constexpr int kMoments = 22;
+constexpr int kMoments = kRigidMoments;
 
 template <bool BWD>
 __global__ void __launch_bounds__(kMomThreads)
@@ -343,17 +344,7 @@ rigid_residual_moments_kernel(const float* __restrict__ points, const float* __r
     for (int n = threadIdx.x; n < N; n += kMomThreads) {
         const float2 a = __ldg(src + 3 * n), c = __ldg(src + 3 * n + 1), e = __ldg(src + 3 * n + 2);
         const double p[3] = {(double)a.x, (double)a.y, (double)c.x}, q[3] = {(double)c.y, (double)e.x, (double)e.y};
-        // S_pp (xx, xy, xz, yy, yz, zz) | S_qp row-major | s_p | s_q | s_qq
-        s[0] = fma(p[0], p[0], s[0]); s[1] = fma(p[0], p[1], s[1]); s[2] = fma(p[0], p[2], s[2]);
-        s[3] = fma(p[1], p[1], s[3]); s[4] = fma(p[1], p[2], s[4]); s[5] = fma(p[2], p[2], s[5]);
-        DRB_UNROLL
-        for (int i = 0; i < 3; ++i) {
-            DRB_UNROLL
-            for (int j = 0; j < 3; ++j) s[6 + 3 * i + j] = fma(q[i], p[j], s[6 + 3 * i + j]);
-            s[15 + i] += p[i];
-            s[18 + i] += q[i];
-            s[21] = fma(q[i], q[i], s[21]);
-        }
+        rigid_moments_add<double>(p, q, s);
     }
     DRB_UNROLL
     for (int i = 0; i < kMoments; ++i) {
@@ -374,25 +365,11 @@ rigid_residual_moments_kernel(const float* __restrict__ points, const float* __r
     __syncthreads();
     const int k = blockIdx.x * kMomThreads + threadIdx.x;
     if (k >= K) return;
-    const float* mp = models + ((size_t)b * K + k) * 16;
-    const double Spp[3][3] = {{mom[0], mom[1], mom[2]}, {mom[1], mom[3], mom[4]}, {mom[2], mom[4], mom[5]}};
-    const double nd = (double)N;
-    double res = mom[21];
-    double g[12];
+    float m12[12];
     DRB_UNROLL
-    for (int i = 0; i < 3; ++i) {
-        const double r[3] = {(double)__ldg(mp + 4 * i), (double)__ldg(mp + 4 * i + 1), (double)__ldg(mp + 4 * i + 2)};
-        const double t = (double)__ldg(mp + 4 * i + 3);
-        double rS[3];                    // R_i . S_pp[:, j]
-        DRB_UNROLL
-        for (int j = 0; j < 3; ++j) rS[j] = r[0] * Spp[0][j] + r[1] * Spp[1][j] + r[2] * Spp[2][j];
-        const double r_sp = r[0] * mom[15] + r[1] * mom[16] + r[2] * mom[17];
-        const double r_sqp = r[0] * mom[6 + 3 * i] + r[1] * mom[7 + 3 * i] + r[2] * mom[8 + 3 * i];
-        res += -2.0 * (r_sqp + t * mom[18 + i]) + (rS[0] * r[0] + rS[1] * r[1] + rS[2] * r[2]) + 2.0 * t * r_sp + nd * t * t;
-        DRB_UNROLL
-        for (int j = 0; j < 3; ++j) g[4 * i + j] = -(mom[6 + 3 * i + j] - rS[j] - t * mom[15 + j]);   // -sum d_i p_j
-        g[4 * i + 3] = -(mom[18 + i] - r_sp - nd * t);                                                  // -sum d_i
-    }
+    for (int i = 0; i < 12; ++i) m12[i] = __ldg(models + ((size_t)b * K + k) * 16 + i);
+    double res, g[12];
+    rigid_residual_from_moments<float, double>(mom, (double)N, m12, res, g);
     if (res_out) res_out[(size_t)b * K + k] = (float)res;
     if (BWD) {
         const double gr = 2.0 * (double)__ldg(g_res + (size_t)b * K + k);

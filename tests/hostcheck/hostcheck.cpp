@@ -210,6 +210,22 @@ HC_RIGID(hc_rigid3_solve_f64, double)
 HC_RIGIDB(hc_rigid3_backward_f32, float)
 HC_RIGIDB(hc_rigid3_backward_f64, double)
 
+// rigid residual from second moments (score.cu: rigid_residual_moments_kernel): points [N,6] float, models [K,16]
+// float -> res [K], g [K,12] (= d res / d [R | t], i.e. twice the header's g12), accumulated in double
+void hc_rigid_residual_moments(const float* points, int N, const float* models, int K, double* res, double* g) {
+    double mom[drb::kRigidMoments] = {0};
+    for (int n = 0; n < N; ++n) {
+        const double p[3] = {points[6 * n], points[6 * n + 1], points[6 * n + 2]};
+        const double q[3] = {points[6 * n + 3], points[6 * n + 4], points[6 * n + 5]};
+        drb::rigid_moments_add<double>(p, q, mom);
+    }
+    for (int k = 0; k < K; ++k) {
+        double g12[12];
+        drb::rigid_residual_from_moments<float, double>(mom, (double)N, models + (size_t)k * 16, res[k], g12);
+        for (int i = 0; i < 12; ++i) g[(size_t)k * 12 + i] = 2.0 * g12[i];
+    }
+}
+
 // Serial restatement of refit.cu's moment accumulation + the shared serial tail (refit_math.cuh).
 int hc_refit(int fmat, const float* matches, const unsigned char* mask, const float* weights, int N, float* models) {
     drb::HartleyNorm<double> h;

@@ -160,6 +160,44 @@ def test_rigid_forward_backward(lib, golden, flag):
     assert ok.all() and rel.max() < 1e-8
 
 
+def test_rigid_residual_from_moments(lib, golden):
+    """The moments form of the rigid residual (rigid_math.cuh, used by score.cu's rigid_residual_moments_kernel):
+    against the golden of squared_residual (rigid_transformation_SVD_based_solver.py:76-89) and against fp64 autograd
+    of the point-by-point sum, including a model that fits every point (where fp32 moments would cancel)."""
+    g = golden("rigid")
+    for flag in (0, 1):
+        pts = np.ascontiguousarray(g["points"].numpy().astype(np.float32))
+        models = np.ascontiguousarray(g[f"model_{flag}"].reshape(-1, 16).numpy().astype(np.float32))
+        K, N = models.shape[0], pts.shape[0]
+        res, grad = np.zeros(K), np.zeros((K, 12))
+        lib.hc_rigid_residual_moments(vp(pts), N, vp(models), K, vp(res), vp(grad))
+        assert torch.allclose(torch.from_numpy(res).float(), g[f"res_{flag}"], rtol=1e-4)
+        md = torch.from_numpy(models).double().view(K, 4, 4).clone().requires_grad_(True)
+        p, q = torch.from_numpy(pts[:, :3]).double(), torch.from_numpy(pts[:, 3:]).double()
+        d = q[None] - (torch.einsum("kij,nj->kni", md[:, :3, :3], p) + md[:, None, :3, 3])
+        want = (d * d).sum((-1, -2))
+        want.sum().backward()
+        assert (torch.from_numpy(res) - want.detach()).abs().max() <= 1e-9 * want.detach().abs().max()
+        wg = md.grad[:, :3, :].reshape(K, 12)
+        assert (torch.from_numpy(grad) - wg).abs().max() <= 1e-9 * wg.abs().max()
+    # exact fit: sum |q|^2 ~ 1e5, residual sum ~ 6e-4
+    gen = torch.Generator().manual_seed(3)
+    N = 20000
+    p = torch.randn(N, 3, generator=gen, dtype=torch.float64) * 2
+    R = torch.linalg.qr(torch.randn(3, 3, generator=gen, dtype=torch.float64)).Q
+    t = torch.tensor([0.3, -1.2, 2.0], dtype=torch.float64)
+    q = p @ R.T + t + 1e-4 * torch.randn(N, 3, generator=gen, dtype=torch.float64)
+    pts = np.ascontiguousarray(torch.cat((p, q), -1).float().numpy())
+    model = np.eye(4, dtype=np.float32)
+    model[:3, :3], model[:3, 3] = R.float().numpy(), t.float().numpy()
+    res, grad = np.zeros(1), np.zeros((1, 12))
+    lib.hc_rigid_residual_moments(vp(pts), N, vp(np.ascontiguousarray(model.reshape(1, 16))), 1, vp(res), vp(grad))
+    pp, qq = torch.from_numpy(pts[:, :3]).double(), torch.from_numpy(pts[:, 3:]).double()
+    want = float(((qq - (pp @ torch.from_numpy(model[:3, :3]).double().T + torch.from_numpy(model[:3, 3]).double())) ** 2).sum())
+    # nine orders of magnitude cancel in fp64: 1e-4 relative is what is left (fp32 moments would leave nothing)
+    assert want < 1e-2 and abs(res[0] - want) < 1e-4 * want
+
+
 def run_refit(lib, fmat, matches, mask=None, weights=None):
     m = np.ascontiguousarray(matches.numpy(), dtype=np.float32)
     out = np.zeros((10, 9), np.float32)
