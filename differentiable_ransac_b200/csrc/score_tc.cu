@@ -56,6 +56,14 @@
 #define DRB_TC_ABLATE 0
 #endif
 
+// DRB_TC_HALF: the accumulator is handed over in HALVES of 128 columns (64 models) -- per tile two groups of six
+// N = 128 MMAs, each with its own full / empty barrier pair and its own group of epilogue warps -- instead of as one
+// 256-column unit: four half-buffers in flight instead of two buffers, so the MMAs of one half overlap the epilogue of
+// the other and a slow warp holds back 128 columns, not 256.
+#ifndef DRB_TC_HALF
+#define DRB_TC_HALF 0
+#endif
+
 namespace drb {
 namespace tc {
 
@@ -100,7 +108,7 @@ struct Carve {
     static constexpr int kOffA = 0;
     static constexpr int kOffB = kOffA + STAGES * kABytes;            //  98304 with four stages
     static constexpr int kOffBars = kOffB + 2 * kBBytes;              // 196608
-    static constexpr int kNumBars = 2 * STAGES + 2 + 2 + 2 + 2;       // a_full/a_empty, d_full, d_empty, b_full, b_empty
+    static constexpr int kNumBars = 2 * STAGES + 4 + 4 + 2 + 2;       // a_full/a_empty, d_full, d_empty (per half), b_full, b_empty
     static constexpr int kOffTmemPtr = kOffBars + kNumBars * 8;
     static constexpr int kOffPrefix = kOffTmemPtr + 16;
     static constexpr int kOffPart = kOffPrefix + (kMaxPairs + 1) * 4 + 12;
@@ -166,9 +174,9 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + C::kOffBars);
     uint64_t* a_full = bars;
     uint64_t* a_empty = bars + kStagesA;
-    uint64_t* d_full = bars + 2 * kStagesA;
-    uint64_t* d_empty = d_full + 2;
-    uint64_t* b_full = d_empty + 2;
+    uint64_t* d_full = bars + 2 * kStagesA;      // [buffer][half]: index 2 * buffer + half (half 0 alone unless DRB_TC_HALF)
+    uint64_t* d_empty = d_full + 4;
+    uint64_t* b_full = d_empty + 4;
     uint64_t* b_empty = b_full + 2;
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(smem + C::kOffTmemPtr);
     int* prefix = reinterpret_cast<int*>(smem + C::kOffPrefix);
@@ -183,8 +191,10 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
             mbar_init(&a_empty[i], 1);    // tcgen05.commit
         }
         for (int i = 0; i < 2; ++i) {
-            mbar_init(&d_full[i], 1);                  // tcgen05.commit
-            mbar_init(&d_empty[i], EPI);               // one arrival per epilogue warp
+            for (int h = 0; h < 2; ++h) {
+                mbar_init(&d_full[2 * i + h], 1);                             // tcgen05.commit
+                mbar_init(&d_empty[2 * i + h], DRB_TC_HALF ? EPI / 2 : EPI);  // one arrival per epilogue warp (of the half)
+            }
             mbar_init(&b_full[i], kBuildThreads / 32); // one arrival per builder warp
             mbar_init(&b_empty[i], 1);                 // tcgen05.commit
         }
@@ -228,10 +238,29 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 const uint64_t bdesc = smem_desc(smem_u32(smem + kOffB + rb.idx * kBBytes));
 #pragma unroll 1
                 for (int t = 0; t < tiles; ++t) {
-                    mbar_wait_idle(&d_empty[rd.idx], rd.phase ^ 1u);
+                    const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
+                    if (DRB_TC_HALF) {
+                        // idesc with N = 128: the N field (bits 17-22, N >> 3) of the 256-column descriptor halved
+                        const uint32_t idesc_h = (idesc & ~(0x3fu << 17)) | ((uint32_t)(kTileN / 2 >> 3) << 17);
+                        DRB_UNROLL
+                        for (int h = 0; h < 2; ++h) {
+                            mbar_wait_idle(&d_empty[2 * rd.idx + h], rd.phase ^ 1u);
+                            if (h == 0) mbar_wait_idle(&a_full[ra.idx], ra.phase);
+                            tc_fence_after();
+                            const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN + h * (kTileN / 2));
+                            const uint64_t bd = bdesc + (uint64_t)((h * (kBBytes / 2)) >> 4);   // rows 128 h .. of the B image
+                            DRB_UNROLL
+                            for (int k = 0; k < kKSteps; ++k) {
+                                if (BF16) mma_bf16(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bd, k), idesc_h, k > 0 ? 1u : 0u);
+                                else mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bd, k), idesc_h, k > 0 ? 1u : 0u);
+                            }
+                            if (h == 1) mma_commit(&a_empty[ra.idx]);
+                            mma_commit(&d_full[2 * rd.idx + h]);
+                        }
+                    } else {
+                    mbar_wait_idle(&d_empty[2 * rd.idx], rd.phase ^ 1u);
                     mbar_wait_idle(&a_full[ra.idx], ra.phase);
                     tc_fence_after();
-                    const uint64_t adesc = smem_desc(smem_u32(smem + kOffA + ra.idx * kABytes));
                     const uint32_t d = tmem_base + (uint32_t)(rd.idx * kTileN);
                     DRB_UNROLL
                     for (int k = 0; k < ((DRB_TC_ABLATE & 1) ? 0 : (DRB_TC_ABLATE & 32) ? 4 : (DRB_TC_ABLATE & 64) ? 3 : kKSteps); ++k) {
@@ -239,7 +268,8 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                         else mma_tf32(d, smem_desc_kstep(adesc, k), smem_desc_kstep(bdesc, k), idesc, k > 0 ? 1u : 0u);
                     }
                     mma_commit(&a_empty[ra.idx]);   // the stage may be refilled once these MMAs have read it
-                    mma_commit(&d_full[rd.idx]);    // the accumulator is complete
+                    mma_commit(&d_full[2 * rd.idx]);    // the accumulator is complete
+                    }
                     ra.advance(kStagesA);
                     rd.advance(2);
                 }
@@ -297,6 +327,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
         const int et = threadIdx.x - kWarpEpi0 * 32;   // 0 .. 32 EPI - 1
         const int quarter = warp & 3;                  // the TMEM lanes this warp may read: 32 quarter .. + 31
         const int half = (warp - kWarpEpi0) >> 2;      // this warp's column part: columns kCols half .. + kCols - 1
+        const int dh = DRB_TC_HALF ? (half * kCols) / (kTileN / 2) : 0;   // which half of the accumulator that is
         Ring rd;
         int parity = 0;
 #pragma unroll 1
@@ -311,7 +342,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
             for (int i = 0; i < kAcc; ++i) acc[i] = pk2_splat(0.f);
 #pragma unroll 1
             for (int t = 0; t < tiles; ++t) {
-                mbar_wait(&d_full[rd.idx], rd.phase);
+                mbar_wait(&d_full[2 * rd.idx + dh], rd.phase);
                 __syncwarp();          // tcgen05.ld is .sync.aligned: the warp must be converged
                 tc_fence_after();
                 // a row past N contributes 0: max(0, min(1, u * nci + 0)) with u * nci <= 0 (or NaN -> 0)
@@ -332,7 +363,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                         // chunk, is 2 % slower (0.1096 vs 0.1075 ms, profiles/r2_tc_ablate.jsonl)
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
+                        if (lane == 0) mbar_arrive(&d_empty[2 * rd.idx + dh]);
                     }
                     if (DRB_TC_ABLATE & 2) {
                         acc[c * 8] = pk2_add(acc[c * 8], pk2_make(__uint_as_float(v[0]), __uint_as_float(v[31])));
@@ -369,7 +400,7 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
                 if (!(DRB_TC_ABLATE & 16)) {
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&d_empty[rd.idx]);
+                    if (lane == 0) mbar_arrive(&d_empty[2 * rd.idx + dh]);
                 }
                 rd.advance(2);
             }

@@ -18,7 +18,8 @@ CSRC = os.path.join(ROOT, "differentiable_ransac_b200", "csrc")
 OUT = os.path.join(HERE, "build")
 ABLATIONS = {0: "none", 16: "early release of the accumulator", 1: "no MMA", 2: "no epilogue math", 3: "no MMA, no math",
              8: "no MUFU", 32: "4 of 6 K steps", 64: "3 of 6 K steps", 34: "4 of 6 K steps, no epilogue math",
-             128: "idle roles poll without the nanosleep back-off"}
+             128: "idle roles poll without the nanosleep back-off",
+             1000: "accumulator handed over in halves (DRB_TC_HALF=1)"}
 if os.environ.get("DRB_ABLATE_ONLY"):
     ABLATIONS = {int(k): ABLATIONS.get(int(k), "?") for k in os.environ["DRB_ABLATE_ONLY"].split(",")}
 
@@ -29,7 +30,7 @@ def build():
     for n in ABLATIONS:
         so = os.path.join(OUT, f"libtc_ablate{n}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-               "--expt-relaxed-constexpr", f"-DDRB_TC_ABLATE={n}", "-shared", "-o", so,
+               "--expt-relaxed-constexpr", *( [f"-DDRB_TC_ABLATE={n}"] if n < 1000 else ["-DDRB_TC_HALF=1"]), "-shared", "-o", so,
                os.path.join(CSRC, "score_tc.cu"), os.path.join(CSRC, "score_tc2.cu"), "-lcudart"]
         procs.append(subprocess.Popen(cmd))
     for p in procs:
@@ -52,6 +53,7 @@ def main(variants):
     M = cm.shape[1]
     P = ctypes.c_void_p
     stream = torch.cuda.current_stream().cuda_stream
+    ref_best = {}
     for n, what in ABLATIONS.items():
         lib = ctypes.CDLL(os.path.join(OUT, f"libtc_ablate{n}.so"))
         lib.drb_score_msac_tc_workspace_bytes.restype = ctypes.c_size_t
@@ -76,8 +78,14 @@ def main(variants):
                 b.record()
             torch.cuda.synchronize()
             ts = sorted(a.elapsed_time(b) for a, b in ev)
+            best.zero_()
+            call()
+            torch.cuda.synchronize()
+            if n == 0:
+                ref_best[name] = best.clone()
+            same = int((best == ref_best[name]).sum()) if name in ref_best else None
             print(json.dumps(dict(ablate=n, what=what, kernel=name, ms_median=round(ts[len(ts) // 2], 5), ms_min=round(ts[0], 5),
-                                  models=int(cc.sum()))), flush=True)
+                                  models=int(cc.sum()), same_winners_as_unablated=same)), flush=True)
 
 
 if __name__ == "__main__":
