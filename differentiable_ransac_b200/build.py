@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libdrb.so")
-SOURCES = ["api.cu", "sampler.cu", "solver_e5.cu", "solver_misc.cu", "score.cu", "score_stream.cu", "score_tc.cu", "score_tc2.cu", "refit.cu", "pose.cu", "adaptive.cu", "fp64_path.cu"]
+SOURCES = ["api.cu", "sampler.cu", "solver_e5.cu", "solver_misc.cu", "score.cu", "score_stream.cu", "score_tc.cu", "score_tc2.cu", "score_tc_pair.cu", "refit.cu", "pose.cu", "adaptive.cu", "fp64_path.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "--expt-relaxed-constexpr"]
 

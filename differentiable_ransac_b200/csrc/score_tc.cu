@@ -462,12 +462,25 @@ score_msac_tc_kernel(const uint32_t* __restrict__ images, const float* __restric
 
 static int tc_sm_count() { return sm_count_current_device(); }
 
+// the operand images with `tiles` (>= ceil(N / 128)) tiles per pair -- rows past N are zero -- for score_tc_pair.cu,
+// whose SM pairs consume the tiles two at a time
+int launch_features(bool bf16, const float* matches, int B, int N, int tiles, uint32_t* images, cudaStream_t s) {
+    if (bf16) msac_tc_features_kernel<true, false><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
+    else msac_tc_features_kernel<false, false><<<dim3(tiles, B), kTileM, 0, s>>>(matches, N, tiles, images);
+    return cudaGetLastError() == cudaSuccess ? DRB_OK : DRB_ERR_CUDA;
+}
+
 }  // namespace tc
 }  // namespace drb
 
 using namespace drb;
 
 namespace drb {
+namespace tcp {   // score_tc_pair.cu: two SMs per tile (cta_group::2)
+int dispatch(bool bf16, const float* matches, const float* models, const int32_t* count, const int32_t* ids,
+             const float* thr, int B, int M, int N, float* scores, unsigned long long* best_packed, uint32_t* images,
+             cudaStream_t s);
+}
 namespace tc2 {   // score_tc2.cu: the model-stationary arrangement
 size_t workspace_bytes(int B, int N);
 int dispatch(bool bf16, bool e16, bool pair, const float* matches, const float* models, const int32_t* count,
@@ -478,7 +491,7 @@ int dispatch(bool bf16, bool e16, bool pair, const float* matches, const float* 
 
 extern "C" size_t drb_score_msac_tc_workspace_bytes(int B, int N) {
     if (B <= 0 || N <= 0) return 0;
-    const size_t v1 = (size_t)B * ((N + tc::kTileM - 1) / tc::kTileM) * tc::kABytes;
+    const size_t v1 = (size_t)B * (2 * ((N + 2 * tc::kTileM - 1) / (2 * tc::kTileM))) * tc::kABytes;   // an even tile count (+ 512)
     const size_t v2 = tc2::workspace_bytes(B, N);     // tiles of 80 correspondences: a different padding
     return v1 > v2 ? v1 : v2;
 }
@@ -516,11 +529,14 @@ extern "C" int drb_score_msac_tc(const float* matches, const float* models, cons
     // (all measured on the B200: DESIGN.md section 10)
     const int split = words & 15;
     const bool pair = (words & 16) != 0, e16 = (words & 32) != 0, v2 = (words & 64) != 0, fold = (words & 128) != 0,
-               slim = (words & 256) != 0;
-    if ((split != 2 && split != 3) || (words & ~511) || (fold && (!pair || v2)) || (slim && (!pair || fold || e16 || v2)))
+               slim = (words & 256) != 0, two_sm = (words & 512) != 0;
+    if ((split != 2 && split != 3) || (words & ~1023) || (fold && (!pair || v2)) || (slim && (!pair || fold || e16 || v2)) ||
+        (two_sm && (!pair || fold || e16 || v2 || slim)))
         return DRB_ERR_UNSUPPORTED;
     uint32_t* images = reinterpret_cast<uint32_t*>(workspace);
     cudaStream_t s = (cudaStream_t)stream;
+    if (two_sm) return tcp::dispatch(split == 3, matches, models, count, ids, thr, B, M, N, scores, best_packed,
+                                     reinterpret_cast<uint32_t*>(workspace), (cudaStream_t)stream);
     if (v2) return tc2::dispatch(split == 3, e16, pair, matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s);
 #define DRB_TC_ARGS matches, models, count, ids, thr, B, M, N, scores, best_packed, images, s
 #define DRB_TC_PICK(BF, PR) (e16 ? tc::launch<BF, PR, 16, false>(DRB_TC_ARGS) : tc::launch<BF, PR, 8, false>(DRB_TC_ARGS))

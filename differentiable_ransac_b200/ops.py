@@ -363,6 +363,8 @@ _TC_WORDS = {"tc": 3, "tc_bf16": 3, "tc_tf32": 2, "tc_bf16p": 3 + 16, "tc_tf32p"
 _TC_WORDS.update({k + "_e16": v + 32 for k, v in list(_TC_WORDS.items()) if k != "tc"})
 # "*_s": the slim build of the pair variant (+256: 128 registers, three stages; leaves room for a five-point CTA on the SM)
 _TC_WORDS.update({"tc_bf16p_s": 3 + 16 + 256, "tc_tf32p_s": 2 + 16 + 256})
+# "*2": two SMs per tile (+512: tcgen05 cta_group::2, csrc/score_tc_pair.cu)
+_TC_WORDS.update({"tc_bf16p2": 3 + 16 + 512, "tc_tf32p2": 2 + 16 + 512})
 # "tc2_*": the model-stationary arrangement (csrc/score_tc2.cu, +64)
 _TC_WORDS.update({"tc2_tf32": 2 + 64, "tc2_bf16": 3 + 64, "tc2_tf32_e16": 2 + 64 + 32, "tc2_bf16_e16": 3 + 64 + 32,
                   "tc2_tf32p": 2 + 64 + 16, "tc2_bf16p": 3 + 64 + 16, "tc2_tf32p_e16": 2 + 64 + 16 + 32,

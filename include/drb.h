@@ -188,6 +188,9 @@ int drb_score_msac_stream(const float* matches, const float* models, const int32
  *        that are not finite are flagged in the sixteenth K slot and answer exactly -1 (msac_tc_layout.cuh)
  *  + 256 (with + 16 alone) the slim build: 128 registers per thread and three correspondence stages, which leaves 16 K
  *        registers and ~50 KB of shared memory of every SM to a five-point CTA of the next batch on another stream
+ *  + 512 (with + 16 alone) two SMs per tile (score_tc_pair.cu): clusters of two CTAs, tcgen05 cta_group::2 MMAs of 256
+ *        correspondences x 128 models, half of the operand stream and of the model operand per CTA; correct and slower
+ *        (0.138 vs 0.108 ms at the headline shape: the cross-SM hand-over every six MMAs), opt-in
  * (every variant is pinned to the fp64 oracle on the B200, tests/test_gpu_score_tc.py.)  B <= 1024; matches 16-byte
  * aligned.  Needs a 128-byte aligned workspace of drb_score_msac_tc_workspace_bytes(B, N) bytes (contents
  * irrelevant on entry: the call writes the operand images of the correspondences there first).           */

@@ -19,7 +19,9 @@ OUT = os.path.join(HERE, "build")
 ABLATIONS = {0: "none", 16: "early release of the accumulator", 1: "no MMA", 2: "no epilogue math", 3: "no MMA, no math",
              8: "no MUFU", 32: "4 of 6 K steps", 64: "3 of 6 K steps", 34: "4 of 6 K steps, no epilogue math",
              128: "idle roles poll without the nanosleep back-off",
-             1000: "accumulator handed over in halves (DRB_TC_HALF=1)"}
+             1000: "accumulator handed over in halves (DRB_TC_HALF=1)",
+             2001: "two-SM kernel: no MMAs issued", 2002: "two-SM kernel: no epilogue arithmetic",
+             2003: "two-SM kernel: barriers, copies and tcgen05.ld only"}
 if os.environ.get("DRB_ABLATE_ONLY"):
     ABLATIONS = {int(k): ABLATIONS.get(int(k), "?") for k in os.environ["DRB_ABLATE_ONLY"].split(",")}
 
@@ -30,8 +32,9 @@ def build():
     for n in ABLATIONS:
         so = os.path.join(OUT, f"libtc_ablate{n}.so")
         cmd = ["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
-               "--expt-relaxed-constexpr", *( [f"-DDRB_TC_ABLATE={n}"] if n < 1000 else ["-DDRB_TC_HALF=1"]), "-shared", "-o", so,
-               os.path.join(CSRC, "score_tc.cu"), os.path.join(CSRC, "score_tc2.cu"), "-lcudart"]
+               "--expt-relaxed-constexpr", *([f"-DDRB_TC_ABLATE={n}"] if n < 1000 else ["-DDRB_TC_HALF=1"] if n == 1000 else [f"-DDRB_TCP_ABLATE={n - 2000}"]),
+               "-shared", "-o", so, os.path.join(CSRC, "score_tc.cu"), os.path.join(CSRC, "score_tc2.cu"),
+               os.path.join(CSRC, "score_tc_pair.cu"), "-lcudart"]
         procs.append(subprocess.Popen(cmd))
     for p in procs:
         if p.wait():

@@ -142,7 +142,7 @@ CASES = [
     (32, 1100, 2000, None),        # more units than SMs, every ring wraps many times
     (40, 200, 500, None),
 ]
-KERNELS = ["tc_bf16", "tc_tf32", "tc_bf16p", "tc_tf32p", "tc_bf16q", "tc_tf32q", "tc_bf16p_s", "tc_tf32_e16", "tc_bf16p_e16", "tc2_tf32", "tc2_bf16",
+KERNELS = ["tc_bf16", "tc_tf32", "tc_bf16p", "tc_tf32p", "tc_bf16q", "tc_tf32q", "tc_bf16p_s", "tc_bf16p2", "tc_tf32p2", "tc_tf32_e16", "tc_bf16p_e16", "tc2_tf32", "tc2_bf16",
            "tc2_tf32_e16", "tc2_tf32p", "tc2_bf16p_e16"]
 
 
